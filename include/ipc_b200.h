@@ -1,0 +1,127 @@
+/* ipc_b200.h — C ABI of the B200-native IPC hot path.
+ *
+ * The reference has no FFI: its boundary is the C++ class template IPC<EDGE,VERTEX>
+ * (/root/reference/include/ipc/consensus.hpp:5-33) operating on g2o objects. This header is the
+ * flat-array C ABI a binding of that class would call; every entry point cites the reference
+ * interface it replaces. All pointers are plain host pointers unless the name says `_dev`.
+ * Every function returns IPC_OK (0) or a negative error code; ipc_last_error() gives the text.
+ * No entry point has a CPU fallback: without a CUDA device every compute call fails with
+ * IPC_ERR_CUDA.
+ *
+ * Flat formats
+ *   SE(2): measurement / pose = (x, y, theta), information = 3x3 row-major full symmetric.
+ *   SE(3): measurement / pose = (x, y, z, qx, qy, qz, qw) (g2o EDGE_SE3:QUAT order), information =
+ *          6x6 row-major full symmetric (translation block first, then the quaternion-vector block).
+ *   Vertex ids must be 0..n_poses-1 and odometry edge j must connect j -> j+1
+ *   (the reference assumes both: src/consensus_utils.cpp:32-40, src/consensus.cpp:55).
+ */
+#ifndef IPC_B200_H
+#define IPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ipc_handle ipc_handle;
+
+enum {
+    IPC_OK = 0,
+    IPC_ERR_ARG = -1,      /* bad argument (null pointer, bad id, bad dimension)            */
+    IPC_ERR_CUDA = -2,     /* CUDA runtime error or no device                               */
+    IPC_ERR_STATE = -3,    /* call not valid in the current state (e.g. no candidate table) */
+    IPC_ERR_UNSUPPORTED = -4
+};
+
+/* The fields of struct Config the hot path reads (include/ipc/utils.hpp:22-38, consumed at
+ * src/consensus.cpp:18-32). */
+typedef struct ipc_config {
+    double s_factor;
+    double fast_reject_th;
+    double slow_reject_th;
+    int fast_reject_iter_base;
+    int slow_reject_iter_base;
+} ipc_config;
+
+/* Per-check diagnostics (optional outputs). */
+typedef struct ipc_check_info {
+    double max_chi2;    /* max chi2 over every edge of the sub-problem after optimisation        */
+    double cand_chi2;   /* chi2 of the candidate edge                                            */
+    double sum_chi2;    /* sum over the sub-problem                                              */
+    int iterations;     /* Dogleg iterations executed                                            */
+    int evals;          /* step evaluations (tries)                                              */
+    int window_len;     /* L = hi - lo                                                           */
+    int n_loops;        /* K: loop edges in the sub-problem (candidate included)                 */
+} ipc_check_info;
+
+const char* ipc_last_error(void);
+int ipc_device_count(void);
+
+/* IPC<EDGE,VERTEX>::IPC(optimizer, cfg) — src/consensus.cpp:9-33: scales the odometry information
+ * by s_factor (robustifyVoters, src/consensus_utils.cpp:123-130), dead-reckons every pose from the
+ * origin (propagateGuess, :98-116) and snapshots. dim = 2 (EdgeSE2/VertexSE2) or 3 (EdgeSE3/VertexSE3).
+ * odom_meas: [n_poses-1][3|7], odom_info: [n_poses-1][d*d]. device: CUDA ordinal. */
+int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom_info,
+               const ipc_config* cfg, int device, ipc_handle** out);
+/* IPC::~IPC — src/consensus.cpp:35-40 */
+void ipc_destroy(ipc_handle* h);
+
+/* bool IPC::agreementCheck(EDGE*) — src/consensus.cpp:42-75. Stateful and sequential: cluster
+ * discovery, fast/slow thresholds, Dogleg on the window, commit (consensus set grows, poses after the
+ * window re-dead-reckoned) or rollback. *accepted = 1/0. info may be NULL. */
+int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, const double* info,
+                        int* accepted, ipc_check_info* out_info);
+/* bool IPC::removeEdgeFromCnS(EDGE*) — src/consensus.cpp:77-98. *removed = 1/0. */
+int ipc_remove_edge(ipc_handle* h, int from, int to, int* removed);
+/* void IPC::addEdgeToCnS(EDGE*) — src/consensus.cpp:100-121. */
+int ipc_add_edge(ipc_handle* h, int from, int to, const double* meas, const double* info);
+/* getMaxConsensusSet() — include/ipc/consensus.hpp:16. from_to receives 2 ints per edge. */
+int ipc_consensus_size(ipc_handle* h, int* n);
+int ipc_get_consensus(ipc_handle* h, int* from_to, int capacity);
+/* Current vertex estimates (what simulation.cpp:93-97 writes out): [n_poses][3|7]. */
+int ipc_get_poses(ipc_handle* h, double* out);
+
+/* ---- batched, independent checks: the throughput path --------------------------------------
+ * A check is one isAgreeingWithCurrentState test (src/consensus_utils.cpp:6-22) on a window that
+ * starts from the dead-reckoned state of a fresh IPC object: with member < 0 it is exactly
+ * `IPC ipc(...); ipc.agreementCheck(cand)` (fast path, K = 1); with member >= 0 it is
+ * `IPC ipc(...); ipc.addEdgeToCnS(member); ipc.agreementCheck(cand)` (pair, K = 2 when the two
+ * intervals overlap per src/consensus.cpp:157-159, otherwise the fast path on cand alone). */
+
+/* Upload the loop-candidate table (device resident until replaced). */
+int ipc_set_candidates(ipc_handle* h, int n_loops, const int* from, const int* to,
+                       const double* meas, const double* info);
+/* Host-buffer entry point (end-to-end: H2D of the check list, kernels, D2H of the results).
+ * member/cand: [n_checks] indices into the candidate table. out_bits: ceil(n_checks/32) words,
+ * bit c%32 of word c/32 = verdict of check c. out_info may be NULL. */
+int ipc_check_batch(ipc_handle* h, int n_checks, const int* member, const int* cand,
+                    uint32_t* out_bits, ipc_check_info* out_info);
+/* Device-resident variant: all pointers are device pointers; kernels are enqueued on `stream`
+ * (a cudaStream_t, may be NULL) and the call does not synchronise. */
+int ipc_check_batch_dev(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev,
+                        uint32_t* out_bits_dev, ipc_check_info* out_info_dev, void* stream);
+/* Plan for ipc_check_batch_dev: the call sorts checks by window length into launch buckets on the
+ * device; these report what the last batch processed (sum of window lengths L and loop counts K —
+ * the algorithmic-bytes inputs of SURVEY.md §8(d)) and how many kernels it launched. */
+int ipc_last_batch_stats(ipc_handle* h, int64_t* sum_L, int64_t* sum_K, int* n_launches);
+
+/* N_c x N_c pairwise consistency matrix over the candidate table, candidates in time order
+ * (stable sort by max vertex id, src/simulation.cpp:26): diagonal = fast check, (i, j) i<j = pair
+ * check of j against {i} when the intervals overlap, else diag(i) AND diag(j) (no solve).
+ * rows_bits: [n_loops][ceil(n_loops/32)] words, symmetric. order_out (may be NULL): the time order
+ * used, n_loops ints. n_solved (may be NULL): number of checks actually solved. */
+int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved);
+
+/* Greedy consensus-set growth over a consistency matrix (row-AND + popcount): candidate k (in the
+ * matrix's order) joins iff it is consistent with every current member. in_set: n_loops bytes. */
+int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsigned char* in_set);
+
+/* Knobs (non-reference): noise_exit = 1 stops the Dogleg retry loop once a rejected step's predicted
+ * gain is below round-off of chi2 (DESIGN.md "Termination"); 0 replays all 100 retries like g2o. */
+int ipc_set_option(ipc_handle* h, const char* name, double value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPC_B200_H */

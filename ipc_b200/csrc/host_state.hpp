@@ -1,0 +1,115 @@
+// host_state.hpp — host mirror of the IPC object: odometry records, consensus set and the integer
+// logic of /root/reference/src/consensus.cpp:77-171 (consensus-set edits, cluster discovery).
+// No solver lives here: all numerical work runs on the GPU.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace ipcb {
+
+struct HostEdge {
+    int from = 0, to = 0;
+    std::vector<double> meas;   // 3 | 7
+    std::vector<double> info;   // d*d
+};
+
+struct HostState {
+    int dim = 2, d = 3, mw = 3, n = 0;
+    std::vector<double> odom_meas;   // [n-1][mw]
+    std::vector<double> odom_info;   // [n-1][d*d], already multiplied by s_factor (robustifyVoters, consensus_utils.cpp:123-130)
+    std::vector<HostEdge> cns;       // _max_consensus_set
+
+    static double norm_theta(double t) {
+        const double pi = 3.14159265358979323846;
+        if (t >= -pi && t < pi) return t;
+        double m = std::floor(t / (2 * pi));
+        t = t - m * 2 * pi;
+        if (t >= pi) t -= 2 * pi;
+        if (t < -pi) t += 2 * pi;
+        return t;
+    }
+
+    bool init(int dim_, int n_poses, const double* om, const double* oi, double s_factor, std::string& err) {
+        dim = dim_; d = dim == 2 ? 3 : 6; mw = dim == 2 ? 3 : 7; n = n_poses;
+        odom_meas.assign(om, om + (size_t)(n - 1) * mw);
+        odom_info.assign(oi, oi + (size_t)(n - 1) * d * d);
+        for (auto& v : odom_info) v *= s_factor;
+        for (size_t i = 0; i < odom_meas.size(); ++i) if (!std::isfinite(odom_meas[i])) { err = "non-finite odometry measurement"; return false; }
+        for (size_t i = 0; i < odom_info.size(); ++i) if (!std::isfinite(odom_info[i])) { err = "non-finite odometry information"; return false; }
+        return true;
+    }
+
+    // SE(2) record in the edge's relative-pose frame: residual d = r - z with r = Xi^-1 Xj as (x, y, theta),
+    // chi2 = d^T D d, D = E^T (s * Omega) E, E = blockdiag(R_z^T, 1)   (e_g2o = E d, edge_se2.cpp)
+    static void se2_edge_record(const double* meas, const double* info, double scale, double* z_out, double* D_out) {
+        z_out[0] = meas[0]; z_out[1] = meas[1]; z_out[2] = norm_theta(meas[2]);
+        double c = std::cos(z_out[2]), s = std::sin(z_out[2]);
+        double E[9] = {c, s, 0, -s, c, 0, 0, 0, 1};
+        double W[9], T[9];
+        for (int i = 0; i < 9; ++i) W[i] = info[i] * scale;
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) { double a = 0; for (int k = 0; k < 3; ++k) a += W[r * 3 + k] * E[k * 3 + q]; T[r * 3 + q] = a; }
+        double Dm[9];
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) { double a = 0; for (int k = 0; k < 3; ++k) a += E[k * 3 + r] * T[k * 3 + q]; Dm[r * 3 + q] = a; }
+        D_out[0] = Dm[0]; D_out[1] = 0.5 * (Dm[1] + Dm[3]); D_out[2] = 0.5 * (Dm[2] + Dm[6]);
+        D_out[3] = Dm[4]; D_out[4] = 0.5 * (Dm[5] + Dm[7]); D_out[5] = Dm[8];
+    }
+
+    // SoA layout in HBM: component c of edge k at soa[c * n_pad + k]; SE2: zx zy zt d00 d01 d02 d11 d12 d22
+    void build_odom_soa(int n_pad, std::vector<double>& soa) const {
+        if (dim == 2) {
+            soa.assign((size_t)9 * n_pad, 0.0);
+            for (int k = 0; k + 1 < n; ++k) {
+                double z[3], D[6];
+                se2_edge_record(&odom_meas[(size_t)k * 3], &odom_info[(size_t)k * 9], 1.0, z, D);
+                for (int c = 0; c < 3; ++c) soa[(size_t)c * n_pad + k] = z[c];
+                for (int c = 0; c < 6; ++c) soa[(size_t)(3 + c) * n_pad + k] = D[c];
+            }
+            // padding entries keep D = identity so stray reads stay finite
+            for (int k = n - 1; k < n_pad; ++k) { soa[(size_t)3 * n_pad + k] = 1; soa[(size_t)6 * n_pad + k] = 1; soa[(size_t)8 * n_pad + k] = 1; }
+        } else {
+            soa.clear();
+        }
+    }
+
+    // removeEdgeFromCnS, src/consensus.cpp:77-98
+    bool remove_edge(int from, int to) {
+        int v0 = std::min(from, to), v1 = std::max(from, to);
+        for (auto it = cns.begin(); it != cns.end(); ++it) {
+            int t0 = std::min(it->from, it->to), t1 = std::max(it->from, it->to);
+            if (v0 != t0 || v1 != t1) continue;
+            cns.erase(it);
+            return true;
+        }
+        return false;
+    }
+    // addEdgeToCnS, src/consensus.cpp:100-121 (stable sort by max id)
+    void add_edge(int from, int to, const double* meas, const double* info) {
+        int v0 = std::min(from, to), v1 = std::max(from, to);
+        for (auto& t : cns) if (v0 == std::min(t.from, t.to) && v1 == std::max(t.from, t.to)) return;
+        HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + mw); e.info.assign(info, info + d * d);
+        cns.push_back(std::move(e));
+        std::stable_sort(cns.begin(), cns.end(), [](const HostEdge& a, const HostEdge& b) { return std::max(a.from, a.to) < std::max(b.from, b.to); });
+    }
+    // computeIndependentSubgraph, src/consensus.cpp:123-171
+    std::pair<int, int> independent_subgraph(int from, int to, std::vector<int>& members) const {
+        int lo = std::min(from, to), hi = std::max(from, to);
+        std::vector<char> inc(cns.size(), 0);
+        bool found = true;
+        while (found) {
+            found = false;
+            for (size_t k = 0; k < cns.size(); ++k) {
+                if (inc[k]) continue;
+                int t0 = std::min(cns[k].from, cns[k].to), t1 = std::max(cns[k].from, cns[k].to);
+                if (std::min(t1, hi) - std::max(t0, lo) <= 0) continue;
+                lo = std::min(lo, t0); hi = std::max(hi, t1);
+                inc[k] = 1; found = true; members.push_back((int)k);
+            }
+        }
+        return {lo, hi};
+    }
+};
+
+}  // namespace ipcb

@@ -1,0 +1,359 @@
+// ipc_capi.cu — C ABI (include/ipc_b200.h) over the CUDA kernels. Host side of the handle:
+// IPC<EDGE,VERTEX> state of /root/reference/include/ipc/consensus.hpp:23-32 kept as flat arrays,
+// with the graph resident in HBM. No CPU fallback: every compute entry point launches kernels.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "check_se2.cuh"
+#include "host_state.hpp"
+
+using namespace ipcb;
+
+namespace ipcb {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+}  // namespace ipcb
+
+#define CUDA_TRY(x)                                                                                                   \
+    do {                                                                                                              \
+        cudaError_t _e = (x);                                                                                         \
+        if (_e != cudaSuccess) return fail(IPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// planning kernels: bucket checks by window length (K3: interval overlap) and pack verdict bits
+// ------------------------------------------------------------------------------------------------
+namespace ipcb {
+
+__global__ void plan_checks(const int* __restrict__ lfrom_to, int loop_stride_ints, int n_checks, const int* __restrict__ member,
+                            const int* __restrict__ cand, const int* __restrict__ bucket_cap, int n_buckets, int* __restrict__ counts,
+                            int* __restrict__ work, unsigned long long* __restrict__ stats) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long sl = 0, sk = 0;
+    if (c < n_checks) {
+        const int* lc = lfrom_to + (size_t)cand[c] * loop_stride_ints;
+        int ca = min(lc[0], lc[1]), cb = max(lc[0], lc[1]);
+        int lo = ca, hi = cb, K = 1;
+        int m = member[c];
+        if (m >= 0) {
+            const int* lm = lfrom_to + (size_t)m * loop_stride_ints;
+            int ma = min(lm[0], lm[1]), mb = max(lm[0], lm[1]);
+            if (min(mb, cb) - max(ma, ca) > 0) { K = 2; lo = min(ca, ma); hi = max(cb, mb); }   // src/consensus.cpp:157-159
+        }
+        int L = hi - lo;
+        int b = 0;
+        while (b < n_buckets - 1 && L > bucket_cap[b]) ++b;
+        int pos = atomicAdd(&counts[b], 1);
+        work[(size_t)b * n_checks + pos] = c;
+        sl = (unsigned long long)L; sk = (unsigned long long)K;
+    }
+    // warp-aggregate the statistics
+    for (int o = 16; o > 0; o >>= 1) { sl += __shfl_xor_sync(0xffffffffu, sl, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); }
+    if ((threadIdx.x & 31) == 0 && (sl | sk)) { atomicAdd(&stats[0], sl); atomicAdd(&stats[1], sk); }
+}
+
+__global__ void pack_bits(const unsigned char* __restrict__ verdict, int n, uint32_t* __restrict__ bits) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = (c < n) ? verdict[c] : 0;
+    unsigned w = __ballot_sync(0xffffffffu, v != 0);
+    if ((threadIdx.x & 31) == 0 && c < n) bits[c >> 5] = w;
+}
+
+}  // namespace ipcb
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int NB = 6;   // launch buckets
+struct Bucket { int cap; int nt; int mode; };
+// window-length caps (edges), threads per CTA, memory mode (see check_se2.cuh)
+const Bucket kBuckets2[NB] = {{64, 32, 0}, {256, 64, 0}, {768, 128, 0}, {1800, 256, 0}, {4600, 512, 1}, {1 << 30, 512, 2}};
+
+size_t smem_bytes(int nt, int mode, int cap) {
+    size_t capv = cap + 2;
+    size_t n = (nt / 32) * 32 + 2 + (mode == 0 ? 15 : mode == 1 ? 6 : 0) * capv;
+    return n * sizeof(double);
+}
+
+template <int NT, int MODE> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st) {
+    size_t sm = smem_bytes(NT, MODE, a.Lcap);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(check_chain_se2<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    check_chain_se2<NT, MODE><<<grid, NT, sm, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return IPC_OK;
+}
+
+}  // namespace
+
+struct ipc_handle {
+    int dim = 2, d = 3, mw = 3;
+    int n = 0, n_pad = 0;
+    int device = 0;
+    int n_sm = 148;
+    ipc_config cfg{};
+    int noise_exit = 1;
+    int max_tries = 100;
+    HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
+    // device graph
+    double* d_odom = nullptr;         // SoA components
+    void* d_loops = nullptr;  int n_loops = 0;
+    std::vector<int> h_lfrom, h_lto;  // host copy of candidate endpoints
+    std::vector<double> h_lmeas, h_linfo;
+    // batch work buffers (grown on demand)
+    int cap_checks = 0;
+    int *d_member = nullptr, *d_cand = nullptr, *d_work = nullptr, *d_counts = nullptr, *d_bucket_cap = nullptr;
+    unsigned char* d_verdict = nullptr;
+    uint32_t* d_bits = nullptr;
+    ipc_check_info* d_info = nullptr;
+    unsigned long long* d_stats = nullptr;
+    double* d_scratch = nullptr; size_t scratch_doubles = 0;
+    int scratch_grid = 0;
+    int last_launches = 0;
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+int ensure_batch_buffers(ipc_handle* h, int n_checks) {
+    if (n_checks <= h->cap_checks) return IPC_OK;
+    int cap = std::max(n_checks, 1024);
+    cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info);
+    h->d_member = h->d_cand = h->d_work = nullptr; h->d_verdict = nullptr; h->d_bits = nullptr; h->d_info = nullptr;
+    h->cap_checks = 0;
+    CUDA_TRY(cudaMalloc(&h->d_member, sizeof(int) * cap));
+    CUDA_TRY(cudaMalloc(&h->d_cand, sizeof(int) * cap));
+    CUDA_TRY(cudaMalloc(&h->d_work, sizeof(int) * (size_t)cap * NB));
+    CUDA_TRY(cudaMalloc(&h->d_verdict, cap));
+    CUDA_TRY(cudaMalloc(&h->d_bits, sizeof(uint32_t) * ((cap + 31) / 32)));
+    CUDA_TRY(cudaMalloc(&h->d_info, sizeof(ipc_check_info) * cap));
+    h->cap_checks = cap;
+    return IPC_OK;
+}
+
+// enqueue plan + bucket launches + pack on `st`; all pointers device; work buffer sized for cap >= n_checks
+int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev, int* work_dev, int work_stride,
+                  unsigned char* verdict_dev, uint32_t* bits_dev, ipc_check_info* info_dev, cudaStream_t st) {
+    if (h->dim != 2) return fail(IPC_ERR_UNSUPPORTED, "SE(3) batch kernel not built in this revision");
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, sizeof(int) * NB, st));
+    CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * 2, st));
+    const int loop_stride_ints = (int)(sizeof(LoopRec2) / sizeof(int));
+    plan_checks<<<(n_checks + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int*>(h->d_loops), loop_stride_ints, n_checks, member_dev, cand_dev,
+                                                        h->d_bucket_cap, NB, h->d_counts, work_dev, h->d_stats);
+    CUDA_TRY(cudaGetLastError());
+    int launches = 1;
+    for (int b = 0; b < NB; ++b) {
+        const Bucket& bk = kBuckets2[b];
+        int lo_cap = b == 0 ? 0 : kBuckets2[b - 1].cap;
+        if (lo_cap >= h->n - 1) break;                 // no window can be this long
+        BatchArgs a{};
+        a.odom = h->d_odom; a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
+        a.work = work_dev + (size_t)b * work_stride; a.n_work = h->d_counts + b;
+        a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
+        a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
+        a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
+        a.noise_exit = h->noise_exit; a.max_tries = h->max_tries;
+        a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch;
+        size_t sm = smem_bytes(bk.nt, bk.mode, a.Lcap);
+        int per_sm = std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
+        per_sm = std::min(per_sm, 2048 / bk.nt);
+        int grid = std::min(n_checks, h->n_sm * per_sm * 8);
+        int rc = IPC_OK;
+        if (bk.mode == 2) {
+            grid = std::min(grid, h->scratch_grid);
+            rc = launch_se2<512, 2>(a, grid, st);
+        } else if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st);
+        else if (bk.nt == 32) rc = launch_se2<32, 0>(a, grid, st);
+        else if (bk.nt == 64) rc = launch_se2<64, 0>(a, grid, st);
+        else if (bk.nt == 128) rc = launch_se2<128, 0>(a, grid, st);
+        else rc = launch_se2<256, 0>(a, grid, st);
+        if (rc != IPC_OK) return rc;
+        ++launches;
+    }
+    if (bits_dev) {
+        pack_bits<<<(n_checks + 255) / 256, 256, 0, st>>>(verdict_dev, n_checks, bits_dev);
+        CUDA_TRY(cudaGetLastError());
+        ++launches;
+    }
+    h->last_launches = launches;
+    return IPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ipc_last_error(void) { return g_err.c_str(); }
+
+int ipc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom_info, const ipc_config* cfg, int device, ipc_handle** out) {
+    if (!out) return fail(IPC_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (dim != 2 && dim != 3) return fail(IPC_ERR_ARG, "dim must be 2 or 3");
+    if (n_poses < 2 || !odom_meas || !odom_info || !cfg) return fail(IPC_ERR_ARG, "need n_poses >= 2 and non-null odometry / cfg");
+    int ndev = ipc_device_count();
+    if (ndev <= 0) return fail(IPC_ERR_CUDA, "no CUDA device: this library has no CPU path");
+    if (device < 0 || device >= ndev) return fail(IPC_ERR_ARG, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(device));
+    ipc_handle* h = new ipc_handle();
+    h->dim = dim; h->d = dim == 2 ? 3 : 6; h->mw = dim == 2 ? 3 : 7;
+    h->n = n_poses; h->n_pad = (n_poses + 3) & ~1; h->device = device; h->cfg = *cfg;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    h->n_sm = prop.multiProcessorCount;
+    std::string err;
+    if (!h->hs.init(dim, n_poses, odom_meas, odom_info, cfg->s_factor, err)) { delete h; return fail(IPC_ERR_ARG, err); }
+    // device SoA odometry records
+    std::vector<double> soa;
+    h->hs.build_odom_soa(h->n_pad, soa);
+    CUDA_TRY(cudaMalloc(&h->d_odom, soa.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(h->d_odom, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&h->d_counts, sizeof(int) * NB));
+    CUDA_TRY(cudaMalloc(&h->d_bucket_cap, sizeof(int) * NB));
+    CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * 2));
+    int caps[NB];
+    for (int b = 0; b < NB; ++b) caps[b] = kBuckets2[b].cap;
+    CUDA_TRY(cudaMemcpy(h->d_bucket_cap, caps, sizeof(caps), cudaMemcpyHostToDevice));
+    if (n_poses - 1 > kBuckets2[NB - 2].cap) {   // MODE 2 scratch
+        h->scratch_grid = h->n_sm * 2;
+        h->scratch_doubles = (size_t)h->scratch_grid * 6 * (((n_poses - 1 + 1) & ~1) + 2);
+        CUDA_TRY(cudaMalloc(&h->d_scratch, h->scratch_doubles * sizeof(double)));
+    }
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    *out = h;
+    return IPC_OK;
+}
+
+void ipc_destroy(ipc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_odom); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
+    cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int ipc_set_option(ipc_handle* h, const char* name, double value) {
+    if (!h || !name) return fail(IPC_ERR_ARG, "null argument");
+    if (!strcmp(name, "noise_exit")) { h->noise_exit = value != 0; return IPC_OK; }
+    if (!strcmp(name, "max_tries")) { h->max_tries = (int)value; return IPC_OK; }
+    return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
+}
+
+int ipc_set_candidates(ipc_handle* h, int n_loops, const int* from, const int* to, const double* meas, const double* info) {
+    if (!h || n_loops < 0 || (n_loops && (!from || !to || !meas || !info))) return fail(IPC_ERR_ARG, "bad candidate table");
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int i = 0; i < n_loops; ++i) {
+        if (from[i] < 0 || to[i] < 0 || from[i] >= h->n || to[i] >= h->n || from[i] == to[i])
+            return fail(IPC_ERR_ARG, "candidate " + std::to_string(i) + " has invalid vertex ids");
+    }
+    cudaFree(h->d_loops); h->d_loops = nullptr; h->n_loops = 0;
+    h->h_lfrom.assign(from, from + n_loops); h->h_lto.assign(to, to + n_loops);
+    h->h_lmeas.assign(meas, meas + (size_t)n_loops * h->mw); h->h_linfo.assign(info, info + (size_t)n_loops * h->d * h->d);
+    if (h->dim == 2) {
+        std::vector<LoopRec2> recs(n_loops);
+        for (int i = 0; i < n_loops; ++i) {
+            recs[i].from = from[i]; recs[i].to = to[i];
+            HostState::se2_edge_record(meas + 3 * i, info + 9 * i, 1.0, recs[i].meas, recs[i].D);
+        }
+        if (n_loops) {
+            CUDA_TRY(cudaMalloc(&h->d_loops, sizeof(LoopRec2) * n_loops));
+            CUDA_TRY(cudaMemcpy(h->d_loops, recs.data(), sizeof(LoopRec2) * n_loops, cudaMemcpyHostToDevice));
+        }
+    } else {
+        return fail(IPC_ERR_UNSUPPORTED, "SE(3) candidate table not built in this revision");
+    }
+    h->n_loops = n_loops;
+    return IPC_OK;
+}
+
+int ipc_check_batch_dev(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev, uint32_t* out_bits_dev,
+                        ipc_check_info* out_info_dev, void* stream) {
+    if (!h || n_checks < 0) return fail(IPC_ERR_ARG, "bad arguments");
+    if (!h->d_loops) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");
+    if (n_checks == 0) return IPC_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_batch_buffers(h, n_checks);
+    if (rc != IPC_OK) return rc;
+    return enqueue_batch(h, n_checks, member_dev, cand_dev, h->d_work, h->cap_checks, h->d_verdict, out_bits_dev, out_info_dev,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int ipc_check_batch(ipc_handle* h, int n_checks, const int* member, const int* cand, uint32_t* out_bits, ipc_check_info* out_info) {
+    if (!h || n_checks < 0 || (n_checks && (!member || !cand || !out_bits))) return fail(IPC_ERR_ARG, "bad arguments");
+    if (!h->d_loops) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");
+    if (n_checks == 0) return IPC_OK;
+    for (int i = 0; i < n_checks; ++i)
+        if (cand[i] < 0 || cand[i] >= h->n_loops || member[i] >= h->n_loops) return fail(IPC_ERR_ARG, "check " + std::to_string(i) + " indexes outside the candidate table");
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = ensure_batch_buffers(h, n_checks);
+    if (rc != IPC_OK) return rc;
+    cudaStream_t st = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(h->d_member, member, sizeof(int) * n_checks, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->d_cand, cand, sizeof(int) * n_checks, cudaMemcpyHostToDevice, st));
+    rc = enqueue_batch(h, n_checks, h->d_member, h->d_cand, h->d_work, h->cap_checks, h->d_verdict, h->d_bits, out_info ? h->d_info : nullptr, st);
+    if (rc != IPC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_bits, h->d_bits, sizeof(uint32_t) * ((n_checks + 31) / 32), cudaMemcpyDeviceToHost, st));
+    if (out_info) CUDA_TRY(cudaMemcpyAsync(out_info, h->d_info, sizeof(ipc_check_info) * n_checks, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return IPC_OK;
+}
+
+int ipc_last_batch_stats(ipc_handle* h, int64_t* sum_L, int64_t* sum_K, int* n_launches) {
+    if (!h) return fail(IPC_ERR_ARG, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long s[2] = {0, 0};
+    CUDA_TRY(cudaMemcpy(s, h->d_stats, sizeof(s), cudaMemcpyDeviceToHost));
+    if (sum_L) *sum_L = (int64_t)s[0];
+    if (sum_K) *sum_K = (int64_t)s[1];
+    if (n_launches) *n_launches = h->last_launches;
+    return IPC_OK;
+}
+
+// ---- consensus-set API: integer logic on the host mirror (src/consensus.cpp:77-171) ---------------
+int ipc_remove_edge(ipc_handle* h, int from, int to, int* removed) {
+    if (!h) return fail(IPC_ERR_ARG, "null handle");
+    int r = h->hs.remove_edge(from, to) ? 1 : 0;
+    if (removed) *removed = r;
+    return IPC_OK;
+}
+int ipc_add_edge(ipc_handle* h, int from, int to, const double* meas, const double* info) {
+    if (!h || !meas || !info) return fail(IPC_ERR_ARG, "null argument");
+    if (from < 0 || to < 0 || from >= h->n || to >= h->n || from == to) return fail(IPC_ERR_ARG, "invalid vertex ids");
+    h->hs.add_edge(from, to, meas, info);
+    return IPC_OK;
+}
+int ipc_consensus_size(ipc_handle* h, int* n) {
+    if (!h || !n) return fail(IPC_ERR_ARG, "null argument");
+    *n = (int)h->hs.cns.size();
+    return IPC_OK;
+}
+int ipc_get_consensus(ipc_handle* h, int* from_to, int capacity) {
+    if (!h || !from_to) return fail(IPC_ERR_ARG, "null argument");
+    if (capacity < (int)h->hs.cns.size()) return fail(IPC_ERR_ARG, "capacity too small");
+    for (size_t i = 0; i < h->hs.cns.size(); ++i) { from_to[2 * i] = h->hs.cns[i].from; from_to[2 * i + 1] = h->hs.cns[i].to; }
+    return IPC_OK;
+}
+
+int ipc_agreement_check(ipc_handle*, int, int, const double*, const double*, int*, ipc_check_info*) {
+    return fail(IPC_ERR_UNSUPPORTED, "stateful agreementCheck not built in this revision");
+}
+int ipc_get_poses(ipc_handle*, double*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
+int ipc_consistency_matrix(ipc_handle*, uint32_t*, int*, int64_t*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
+int ipc_greedy_consensus(ipc_handle*, const uint32_t*, int, unsigned char*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
+
+}  // extern "C"
