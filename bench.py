@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — pairwise consistency checks/sec on the BASELINE.json workload.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU path (oracle port; g2o cannot be built here)
+
+Workload at N = 1 (BASELINE.json configs[1]): Manhattan3500-shaped SE(2) graph + 1000 outliers
+(synthetic, seed 2); one STEP = every solved check of the N_c x N_c pairwise consistency matrix in
+time order — the N_c fast checks on the diagonal plus every pair (i < j) whose intervals overlap
+(src/consensus.cpp:157-159); non-overlapping pairs need no solve and are not counted.
+For N > 1 every rank runs the same-size batch on its own M3500-shaped graph (seed 2 + 100*rank): weak
+scaling, no data-path collective except one all_gather of the packed verdict words per step.
+
+One JSON line on stdout (rank 0). `value` = checks/s with the check list resident in HBM, `e2e` = the
+same through ipc_check_batch with HOST buffers (H2D of the check list and D2H of the verdict words inside
+the timed region), `roofline` = algorithmic bytes of the check kernels / their CUDA-event time against the
+measured HBM peak, `cpu_baseline` = the oracle port on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pairwise consistency checks/sec"
+UNIT = "checks/s"
+B_ODOM = {2: 72, 3: 224}     # algorithmic bytes per odometry record
+B_LOOP = {2: 80, 3: 232}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+                if k in j:
+                    return float(j[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_workload(name: str, seed_shift: int, max_checks: int):
+    from ipc_b200 import api, synth
+    c = dict(synth.CONFIGS[name])
+    if seed_shift:
+        synth.CONFIGS[name] = dict(c, seed=c["seed"] + seed_shift)
+    g, cfg = synth.make_config(name)
+    synth.CONFIGS[name] = c
+    mem, cnd = api.pair_checks(g)
+    total = len(cnd)
+    if max_checks and total > max_checks:
+        sel = np.sort(np.random.default_rng(0).choice(total, max_checks, replace=False))
+        mem, cnd = mem[sel], cnd[sel]
+    return g, cfg, mem, cnd, total
+
+
+def workload_desc(name, g, n_checks, total):
+    shapes = {"m3500": "Manhattan3500-shape SE(2) + 1000 outliers", "intel": "INTEL-shape SE(2) + 100 outliers",
+              "sphere": "Sphere2500 SE(3) + 2000 outliers", "city10k": "City10000-shape SE(2) + 5000 outliers",
+              "synth50k": "synthetic SE(2) 50k poses / 10k candidates"}
+    s = f"{shapes.get(name, name)}: {g.n_poses} poses, {g.n_loops} candidates; consistency-matrix checks (diagonal fast + overlapping pairs)"
+    return s + (f", all {total}" if n_checks == total else f", seeded sample of {n_checks} of {total}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_leg(g, cfg, mem, cnd, budget_s: float, threads: int, noise_exit: bool):
+    """Oracle port (kind "port") on a bounded, seeded sample of the same check list."""
+    from ipc_b200 import api
+    from oracle import pyoracle as po
+    orc = po.OracleIPC(g, cfg, noise_exit=noise_exit)
+    rng = np.random.default_rng(1)
+    probe = np.sort(rng.choice(len(cnd), min(len(cnd), 4 * threads), replace=False))
+    ptr, idx = api.checks_to_csr(mem[probe], cnd[probe])
+    t = time.perf_counter(); orc.check_batch(ptr, idx, n_threads=threads); dt = time.perf_counter() - t
+    rate = len(probe) / dt
+    n = int(min(len(cnd), max(len(probe), rate * budget_s)))
+    sel = np.sort(rng.choice(len(cnd), n, replace=False))
+    ptr, idx = api.checks_to_csr(mem[sel], cnd[sel])
+    t = time.perf_counter(); acc, rep = orc.check_batch(ptr, idx, n_threads=threads); dt = time.perf_counter() - t
+    return n / dt, n, dt, sel, acc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g, cfg, mem, cnd, total = build_workload(args.config, 0, args.checks)
+    threads = os.cpu_count() or 1
+    per_step_budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    rates, n_s = [], 0
+    for i in range(args.warmup + args.steps):
+        r, n_s, dt, _, _ = cpu_leg(g, cfg, mem, cnd, per_step_budget, threads, noise_exit=False)
+        if i >= args.warmup:
+            rates.append((n_s, dt))
+    n_tot = sum(n for n, _ in rates); t_tot = sum(t for _, t in rates)
+    v = n_tot / t_tot
+    sample = f"seeded random sample of ~{n_s} checks per step of the same check list (full g2o retry semantics, noise_exit off)"
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": workload_desc(args.config, g, len(cnd), total), "l2": "n/a (CPU)"},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "note": "reference needs g2o/Eigen (absent offline): CPU arm is the dependency-free oracle port, one check per thread"}))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from ipc_b200 import api
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g, cfg, mem, cnd, total = build_workload(args.config, 100 * rank, args.checks)
+    n = len(cnd)
+    ipc = api.IPC.from_graph(g, cfg, device=local)
+    ipc.set_option("noise_exit", args.noise_exit)
+    dev = torch.device("cuda", local)
+    mem_d = torch.from_numpy(mem).to(dev); cnd_d = torch.from_numpy(cnd).to(dev)
+    words = (n + 31) // 32
+    bits_d = torch.zeros(words, dtype=torch.int32, device=dev)
+    gathered = [torch.zeros_like(bits_d) for _ in range(world)] if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        ipc.check_batch_dev(n, mem_d.data_ptr(), cnd_d.data_ptr(), bits_d.data_ptr(), None, stream.cuda_stream)
+        if world > 1:
+            dist.all_gather(gathered, bits_d)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_(); step()
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    with ClockSampler(local) as clk:
+        sync_all()
+        t_wall = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()                      # L2 flush between timed iterations (not inside the event pair)
+            ev[i][0].record(stream); step(); ev[i][1].record(stream)
+            if not args.no_kernel_timing:
+                kern_ms.append(ipc.last_kernel_ms())
+        sync_all()
+        t_wall = time.perf_counter() - t_wall
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_ms = float(tot_ms.item())
+    sum_L, sum_K, n_launch = ipc.last_batch_stats()
+    value = world * n * args.steps / (tot_ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI call --------------------------------------------
+    mem_h = torch.from_numpy(mem).pin_memory(); cnd_h = torch.from_numpy(cnd).pin_memory()
+    bits_h = torch.zeros(words, dtype=torch.int32).pin_memory()
+    L = api.lib()
+    import ctypes as C
+
+    def e2e_step():
+        rc = L.ipc_check_batch(ipc.handle, n, C.c_void_p(mem_h.data_ptr()), C.c_void_p(cnd_h.data_ptr()), C.c_void_p(bits_h.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(L.ipc_last_error().decode())
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step(); sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(t_e2e.item())
+    # the e2e verdict words must equal the device-resident ones
+    same = bool((bits_h.to(dev) == bits_d).all().item())
+
+    out = None
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        alg_bytes = B_ODOM[g.dim] * sum_L + B_LOOP[g.dim] * sum_K + n / 8.0
+        k_ms = float(np.mean(kern_ms)) if kern_ms else float(np.mean(step_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic",
+               "config": {"workload": workload_desc(args.config, g, n, total), "checks_per_gpu_per_step": n, "sum_window_len": sum_L,
+                          "sum_loops": sum_K, "l2": "flushed between timed iterations (256 MiB memset)", "noise_exit": args.noise_exit,
+                          "parallelism": f"{world} x independent check shards" + (" + all_gather of verdict words" if world > 1 else "")},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * words,
+                       "matches_device_resident": same},
+               "gpu_launches": n_launch * (args.steps + args.warmup + e2e_steps + 1),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes, "kernel_ms": k_ms,
+                            "note": "working set is L2-resident; the kernel is fp64-pipe / latency bound, not HBM bound (DESIGN.md)"},
+               "clocks": clk.summary(), "wall_s_timed_region": t_wall}
+        if not args.no_cpu:
+            v, ns, dt, sel, oacc = cpu_leg(g, cfg, mem, cnd, args.cpu_seconds, os.cpu_count() or 1, noise_exit=False)
+            bits = bits_h.numpy().view(np.uint32)
+            gacc = ((bits[sel >> 5] >> (sel & 31).astype(np.uint32)) & 1).astype(bool)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                   "sample": f"seeded random sample of {ns} checks of the same list, {dt:.1f} s, one check per thread",
+                                   "verdict_mismatches_vs_gpu": int((gacc != oacc).sum())}
+        print(json.dumps(out))
+    ipc.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="m3500")
+    ap.add_argument("--checks", type=int, default=0, help="cap on checks per step (0 = the whole consistency matrix)")
+    ap.add_argument("--noise-exit", type=int, default=1)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

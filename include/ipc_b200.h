@@ -105,6 +105,9 @@ int ipc_check_batch_dev(ipc_handle* h, int n_checks, const int* member_dev, cons
  * device; these report what the last batch processed (sum of window lengths L and loop counts K —
  * the algorithmic-bytes inputs of SURVEY.md §8(d)) and how many kernels it launched. */
 int ipc_last_batch_stats(ipc_handle* h, int64_t* sum_L, int64_t* sum_K, int* n_launches);
+/* Device time (CUDA events on the launching stream) spent in the check kernels of the last batch, i.e.
+ * without the plan / pack kernels and without copies. Blocks until that batch has finished. */
+int ipc_last_kernel_ms(ipc_handle* h, float* ms);
 
 /* N_c x N_c pairwise consistency matrix over the candidate table, candidates in time order
  * (stable sort by max vertex id, src/simulation.cpp:26): diagonal = fast check, (i, j) i<j = pair

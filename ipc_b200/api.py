@@ -22,7 +22,7 @@ _LIB = None
 # every symbol include/ipc_b200.h declares
 SYMBOLS = ["ipc_last_error", "ipc_device_count", "ipc_create", "ipc_destroy", "ipc_agreement_check", "ipc_remove_edge",
            "ipc_add_edge", "ipc_consensus_size", "ipc_get_consensus", "ipc_get_poses", "ipc_set_candidates", "ipc_check_batch",
-           "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option"]
+           "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_last_kernel_ms", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option"]
 
 
 class IpcError(RuntimeError):
@@ -65,6 +65,7 @@ def lib():
         L.ipc_check_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_check_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_last_batch_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.ipc_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.ipc_consistency_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.ipc_greedy_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ipc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
@@ -188,6 +189,11 @@ class IPC:
         _chk(lib().ipc_last_batch_stats(self._h, C.byref(sl), C.byref(sk), C.byref(nl)))
         return sl.value, sk.value, nl.value
 
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float(0)
+        _chk(lib().ipc_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
     def consistency_matrix(self):
         n = self.n_candidates
         words = (n + 31) // 32
@@ -221,3 +227,17 @@ def pair_checks(graph, order=None):
             mem.append(order[idx].astype(np.int32))
             cnd.append(np.full(idx.size, order[j], dtype=np.int32))
     return np.concatenate(mem), np.concatenate(cnd)
+
+
+def checks_to_csr(member, cand):
+    """(member, cand) check list -> CSR loop lists (all but the last entry of a row are consensus members,
+    the last is the candidate): the format the oracle's batch entry point takes."""
+    member, cand = np.asarray(member), np.asarray(cand)
+    k = 1 + (member >= 0).astype(np.int64)
+    ptr = np.zeros(len(cand) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum(k)
+    idx = np.zeros(int(ptr[-1]), dtype=np.int32)
+    idx[ptr[1:] - 1] = cand
+    two = member >= 0
+    idx[ptr[:-1][two]] = member[two]
+    return ptr, idx

@@ -120,6 +120,8 @@ struct ipc_handle {
     int scratch_grid = 0;
     int last_launches = 0;
     cudaStream_t stream = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
+    bool ev_valid = false;
 };
 
 namespace {
@@ -151,6 +153,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
                                                         h->d_bucket_cap, NB, h->d_counts, work_dev, h->d_stats);
     CUDA_TRY(cudaGetLastError());
     int launches = 1;
+    CUDA_TRY(cudaEventRecord(h->ev_k0, st));
     for (int b = 0; b < NB; ++b) {
         const Bucket& bk = kBuckets2[b];
         int lo_cap = b == 0 ? 0 : kBuckets2[b - 1].cap;
@@ -179,6 +182,8 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         if (rc != IPC_OK) return rc;
         ++launches;
     }
+    CUDA_TRY(cudaEventRecord(h->ev_k1, st));
+    h->ev_valid = true;
     if (bits_dev) {
         pack_bits<<<(n_checks + 255) / 256, 256, 0, st>>>(verdict_dev, n_checks, bits_dev);
         CUDA_TRY(cudaGetLastError());
@@ -234,6 +239,8 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
         CUDA_TRY(cudaMalloc(&h->d_scratch, h->scratch_doubles * sizeof(double)));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&h->ev_k0));
+    CUDA_TRY(cudaEventCreate(&h->ev_k1));
     *out = h;
     return IPC_OK;
 }
@@ -244,6 +251,8 @@ void ipc_destroy(ipc_handle* h) {
     cudaFree(h->d_odom); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
     if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
+    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     delete h;
 }
 
@@ -321,6 +330,15 @@ int ipc_last_batch_stats(ipc_handle* h, int64_t* sum_L, int64_t* sum_K, int* n_l
     if (sum_L) *sum_L = (int64_t)s[0];
     if (sum_K) *sum_K = (int64_t)s[1];
     if (n_launches) *n_launches = h->last_launches;
+    return IPC_OK;
+}
+
+int ipc_last_kernel_ms(ipc_handle* h, float* ms) {
+    if (!h || !ms) return fail(IPC_ERR_ARG, "null argument");
+    if (!h->ev_valid) return fail(IPC_ERR_STATE, "no batch has been enqueued");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->ev_k1));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->ev_k0, h->ev_k1));
     return IPC_OK;
 }
 

@@ -1,0 +1,109 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI
+(libipc_b200.so via ipc_b200.api); the oracle / golden fixtures are only the checker.
+Bar (BASELINE.json north_star): verdict bits identical, chi2 within 1e-4 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from ipc_b200 import api, synth
+from tests.golden_util import load, rel_err
+
+pytestmark = pytest.mark.gpu
+CHI2_RTOL = 1e-4
+
+
+def _compare(acc, info, z):
+    assert np.array_equal(acc, z["accept"]), f"verdict mismatches at {np.nonzero(acc != z['accept'])[0][:10]}"
+    assert rel_err(info["max_chi2"], z["max_chi2"]).max() < CHI2_RTOL
+    assert rel_err(info["cand_chi2"], z["cand_chi2"]).max() < CHI2_RTOL
+    assert np.array_equal(info["window_len"], z["hi"] - z["lo"])
+
+
+@pytest.mark.parametrize("name", ["pairs_se2_intel.npz", "pairs_se2_m3500.npz"])
+@pytest.mark.parametrize("noise_exit", [1, 0])
+def test_pair_batch_matches_golden(gpu_lib, name, noise_exit):
+    z, g, cfg = load(name)
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    ipc.set_option("noise_exit", noise_exit)
+    acc, info = ipc.check_batch(z["member"], z["cand"])
+    _compare(acc, info, z)
+    sl, sk, nl = ipc.last_batch_stats()
+    assert sl == int((z["hi"] - z["lo"]).sum()) and nl >= 2
+    ipc.close()
+
+
+def test_pair_batch_matches_oracle_live(gpu_lib, oracle_lib):
+    """Fresh seeded input (not a fixture) at a size the oracle finishes in seconds."""
+    g, cfg = synth.make_config("m3500", scale=0.12)
+    mem, cnd = api.pair_checks(g)
+    sel = np.sort(np.random.default_rng(5).choice(len(cnd), 3000, replace=False))
+    mem, cnd = mem[sel], cnd[sel]
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem, cnd)
+    ptr, idx = api.checks_to_csr(mem, cnd)
+    oacc, orep = oracle_lib.OracleIPC(g, cfg).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
+    ipc.close()
+
+
+def test_edge_cases(gpu_lib, oracle_lib):
+    """Shortest windows (L = 2), reversed loop direction, touching intervals (no overlap -> fast path on the
+    candidate alone, src/consensus.cpp:157-159), identical intervals, member listed but disjoint, empty batch."""
+    g0 = synth.manhattan(200, 40, seed=9, noise_scale=0.5, reverse_frac=0.5)
+    rng = np.random.default_rng(1)
+    lf = [0, 5, 10, 12, 12, 20, 150, 198, 30, 60]
+    lt = [2, 3, 12, 20, 20, 12, 10, 196, 60, 30]
+    lm = np.array([oracle_lib.compose(2, oracle_lib.inverse(2, g0.gt[a]), g0.gt[b]) for a, b in zip(lf, lt)]) + rng.normal(size=(10, 3)) * 0.05
+    g = synth.Graph(2, g0.n_poses, g0.odom_meas, g0.odom_info, np.concatenate([g0.loop_from, np.array(lf, dtype=np.int32)]),
+                    np.concatenate([g0.loop_to, np.array(lt, dtype=np.int32)]), np.concatenate([g0.loop_meas, lm]),
+                    np.concatenate([g0.loop_info, np.tile(g0.loop_info[0], (10, 1, 1))]), g0.n_true)
+    cfg = dict(s_factor=10.0, fast_reject_th=6.251, fast_reject_iter_base=50, slow_reject_th=11.345, slow_reject_iter_base=100)
+    mem, cnd = api.pair_checks(g)
+    b = g0.n_loops
+    extra_m = [b + 2, b + 3, b + 4, b + 0, b + 8, b + 9, b + 7]
+    extra_c = [b + 3, b + 4, b + 5, b + 7, b + 9, b + 8, b + 6]     # touching, identical, reversed-identical, disjoint, ...
+    mem = np.concatenate([mem, np.array(extra_m, dtype=np.int32)])
+    cnd = np.concatenate([cnd, np.array(extra_c, dtype=np.int32)])
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem, cnd)
+    ptr, idx = api.checks_to_csr(mem, cnd)
+    oacc, orep = oracle_lib.OracleIPC(g, cfg).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
+    assert np.array_equal(info["n_loops"], orep["n_cluster"] + 1)
+    acc0, info0 = ipc.check_batch(np.zeros(0, dtype=np.int32), np.zeros(0, dtype=np.int32))
+    assert acc0.shape == (0,)
+    with pytest.raises(api.IpcError):
+        ipc.check_batch(np.array([-1], dtype=np.int32), np.array([g.n_loops], dtype=np.int32))
+    ipc.close()
+
+
+def test_full_size_properties(gpu_lib):
+    """BASELINE config 2 size (M3500 + 1000 outliers): properties that need no oracle.
+    (1) zero-noise true loops are all accepted with chi2 ~ 0 on every pair; (2) a pair check equals the
+    fast check of the candidate when the member does not overlap; (3) results are deterministic."""
+    g, cfg = synth.make_config("m3500", noise_scale=0.0)
+    mem, cnd = api.pair_checks(g)
+    true_pair = (cnd < g.n_true) & ((mem < 0) | (mem < g.n_true))
+    sel = np.nonzero(true_pair)[0]
+    sel = np.sort(np.random.default_rng(2).choice(sel, 20000, replace=False))
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem[sel], cnd[sel])
+    assert acc.all() and info["max_chi2"].max() < 1e-9
+    g, cfg = synth.make_config("m3500")
+    ipc2 = gpu_lib.IPC.from_graph(g, cfg)
+    a, b = np.minimum(g.loop_from, g.loop_to), np.maximum(g.loop_from, g.loop_to)
+    rng = np.random.default_rng(3)
+    c = rng.integers(0, g.n_loops, 20000).astype(np.int32)
+    m = rng.integers(0, g.n_loops, 20000).astype(np.int32)
+    disjoint = (np.minimum(b[m], b[c]) - np.maximum(a[m], a[c])) <= 0
+    acc_p, info_p = ipc2.check_batch(m, c)
+    acc_f, info_f = ipc2.check_batch(np.full_like(c, -1), c)
+    assert disjoint.sum() > 1000
+    assert np.array_equal(acc_p[disjoint], acc_f[disjoint])
+    assert np.array_equal(info_p["max_chi2"][disjoint], info_f["max_chi2"][disjoint])
+    acc_p2, info_p2 = ipc2.check_batch(m, c)
+    assert np.array_equal(acc_p, acc_p2) and np.array_equal(info_p["max_chi2"], info_p2["max_chi2"])
+    ipc.close(); ipc2.close()
