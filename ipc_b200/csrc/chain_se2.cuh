@@ -1,0 +1,1013 @@
+// chain_se2.cuh — SE(2) window check, one CTA per check (K = 1 or 2 loop edges), ONE pass per Dogleg iteration.
+//
+// Replaces, for independent fast-path / pair sub-problems, the reference's
+//   isAgreeingWithCurrentState  /root/reference/src/consensus_utils.cpp:6-22
+// driven as in IPC::agreementCheck /root/reference/src/consensus.cpp:42-75 from the dead-reckoned state of
+// IPC::IPC (:9-33), with g2o's Dogleg semantics.
+//
+// Formulation (DESIGN.md "Chain solve"). With the twist of odometry edge k as unknown,
+//   xi_k = Q_k q_k,  Q_k = [R_k, -S t_{k+1}; 0 1],   u_j = T_j Xi_j,  Xi_j = sum_{k<j} xi_k,  T_j = [I, S t_j; 0 1]
+// the odometry part of the Gauss-Newton matrix is block diagonal and every loop edge is a rank-3 term on an
+// interval of edges, so the exact GN step is
+//   Xi_j = Pm_j - PM_j z_rho(j) - C_rho(j),     PM_j = sum_{k<j} Q_k V_k Q_k^T,  Pm_j = -sum_{k<j} Q_k d_k
+// where the per-region "forces" z come from a 3x3 (K = 1) or 6x6 (K = 2) capacitance solve on interval sums of PM, Pm.
+// One sweep over the window therefore (i) applies the step of the previous linearisation to every pose,
+// (ii) re-linearises every edge at the new pose (one sincos per pose), (iii) accumulates chi2 / max chi2 of the trial
+// state and (iv) produces the prefix sums PM, Pm of the NEW linearisation, i.e. everything the next step needs.
+// The predicted gain of a GN step is chi2 - model(h_gn) with model = sum_r z_r^T P_r z_r + loop terms (O(1)).
+// Trust-region-limited steps (steepest-descent / dog-leg blends) need the gradient in g2o's vertex coordinates:
+// two extra sweeps (b, b^T H b) into a per-CTA scratch, then the same trial sweep reading h = c1 b + c2 h_gn.
+// Rejected trials roll the poses back from a per-CTA backup (written by the sweep) and re-linearise.
+//
+// The sweep code is __host__ __device__: tests/ compiles it with NT = 1 on the CPU to validate the arithmetic and
+// the control flow against the oracle without a GPU (tests/host_emul/); the product only ever runs the CUDA build.
+#pragma once
+#include "common.cuh"
+
+namespace ipcb {
+
+#ifdef __CUDACC__
+#define IPC_HD __host__ __device__ __forceinline__
+#define IPC_HD_COLD __host__ __device__ __noinline__      // cold / once-per-sweep code: keep its registers out of the hot loop
+#else
+#define IPC_HD inline
+#define IPC_HD_COLD inline
+#endif
+
+// sin / cos for |t| <= pi + small (every angle here is normalised): Cody-Waite reduction by multiples of pi/2 and the
+// fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp each). The CUDA library sincos carries a Payne-Hanek slow path
+// (local-memory table) that this kernel never needs.
+IPC_HD void ipc_sincos(double t, double* s, double* c) {
+#ifdef __CUDA_ARCH__
+    const double q = rint(t * 0.63661977236758134308);            // 2 / pi
+    double r = fma(-q, 1.57079632679489655800e+00, t);             // pi/2 hi
+    r = fma(-q, 6.12323399573676603587e-17, r);                    // pi/2 lo
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double sr = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const int n = (int)q & 3;
+    const double ss = (n & 1) ? cr : sr, cc = (n & 1) ? sr : cr;
+    *s = (n & 2) ? -ss : ss;
+    *c = ((n + 1) & 2) ? -cc : cc;
+#else
+    *s = sin(t); *c = cos(t);
+#endif
+}
+IPC_HD double wrap_pi_hd(double t) {   // g2o normalize_theta: [-pi, pi)
+    const double pi = 3.14159265358979323846;
+    if (t >= -pi && t < pi) return t;
+    double m = floor(t / (2 * pi));
+    t = t - m * 2 * pi;
+    if (t >= pi) t -= 2 * pi;
+    if (t < -pi) t += 2 * pi;
+    return t;
+}
+
+struct P2 { double x, y, t; };
+struct Lin2 {            // linearisation of one relative-pose edge a -> b in its own frame
+    double c, s;         // cos / sin of theta_a
+    double rx, ry;       // R_a^T (t_b - t_a)
+    double d0, d1, d2;   // residual in the relative frame (r - z)
+    double w0, w1, w2;   // D d
+    double chi;
+};
+IPC_HD void lin2cs(double c, double s, const P2& a, const P2& b, double zx, double zy, double zt, const double* D, Lin2& e) {
+    e.c = c; e.s = s;
+    double dx = b.x - a.x, dy = b.y - a.y;
+    e.rx = c * dx + s * dy;
+    e.ry = -s * dx + c * dy;
+    e.d0 = e.rx - zx; e.d1 = e.ry - zy; e.d2 = wrap_pi_hd(b.t - a.t - zt);
+    e.w0 = D[0] * e.d0 + D[1] * e.d1 + D[2] * e.d2;
+    e.w1 = D[1] * e.d0 + D[3] * e.d1 + D[4] * e.d2;
+    e.w2 = D[2] * e.d0 + D[4] * e.d1 + D[5] * e.d2;
+    e.chi = e.d0 * e.w0 + e.d1 * e.w1 + e.d2 * e.w2;
+}
+IPC_HD double quad3(const double* D, double a, double b, double c) {
+    return a * (D[0] * a + D[1] * b + D[2] * c) + b * (D[1] * a + D[3] * b + D[4] * c) + c * (D[2] * a + D[4] * b + D[5] * c);
+}
+// linearised change of the edge residual under vertex increments ha (at a) and hb (at b)
+IPC_HD void dlin2(const Lin2& e, const double* ha, const double* hb, double& q0, double& q1, double& q2) {
+    double ux = hb[0] - ha[0], uy = hb[1] - ha[1];
+    q0 = e.c * ux + e.s * uy + e.ry * ha[2];
+    q1 = -e.s * ux + e.c * uy - e.rx * ha[2];
+    q2 = hb[2] - ha[2];
+}
+// gradient pieces of chi2/2 w.r.t. the vertex increments: gi (at a), gj (at b)
+IPC_HD void grad2(const Lin2& e, double* gi, double* gj) {
+    double rwx = e.c * e.w0 - e.s * e.w1, rwy = e.s * e.w0 + e.c * e.w1;   // R_a w_t
+    gj[0] = rwx; gj[1] = rwy; gj[2] = e.w2;
+    gi[0] = -rwx; gi[1] = -rwy; gi[2] = e.ry * e.w0 - e.rx * e.w1 - e.w2;
+}
+IPC_HD void inv_sym3(const double* D, double* V) {
+    double c00 = D[3] * D[5] - D[4] * D[4];
+    double c01 = D[2] * D[4] - D[1] * D[5];
+    double c02 = D[1] * D[4] - D[2] * D[3];
+    double det = D[0] * c00 + D[1] * c01 + D[2] * c02;
+    double id = 1.0 / det;
+    V[0] = c00 * id; V[1] = c01 * id; V[2] = c02 * id;
+    V[3] = (D[0] * D[5] - D[2] * D[2]) * id;
+    V[4] = (D[1] * D[2] - D[0] * D[4]) * id;
+    V[5] = (D[0] * D[3] - D[1] * D[1]) * id;
+}
+// dense n x n solve with partial pivoting (n <= 6), A row-major, b overwritten by the solution
+template <int N> IPC_HD void solve_small(double* A, double* b) {
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        int p = c; double best = fabs(A[c * N + c]);
+#pragma unroll
+        for (int r = c + 1; r < N; ++r) { double v = fabs(A[r * N + c]); if (v > best) { best = v; p = r; } }
+        if (p != c) {
+#pragma unroll
+            for (int r = 0; r < N; ++r) if (r == p) {
+#pragma unroll
+                for (int k = 0; k < N; ++k) { double t = A[c * N + k]; A[c * N + k] = A[r * N + k]; A[r * N + k] = t; }
+                double t = b[c]; b[c] = b[r]; b[r] = t;
+            }
+        }
+        double inv = 1.0 / A[c * N + c];
+#pragma unroll
+        for (int r = c + 1; r < N; ++r) {
+            double f = A[r * N + c] * inv;
+#pragma unroll
+            for (int k = c + 1; k < N; ++k) A[r * N + k] -= f * A[c * N + k];
+            b[r] -= f * b[c];
+        }
+    }
+#pragma unroll
+    for (int c = N - 1; c >= 0; --c) {
+        double s = b[c];
+#pragma unroll
+        for (int k = c + 1; k < N; ++k) s -= A[c * N + k] * b[k];
+        b[c] = s / A[c * N + c];
+    }
+}
+IPC_HD void sym3_mul(const double* S, const double* v, double* o) {
+    o[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
+    o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
+    o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
+}
+IPC_HD void sym3_sym3(const double* P, const double* L, double* A) {   // A (full) = P (sym) * L (sym)
+    const double Pf[9] = {P[0], P[1], P[2], P[1], P[3], P[4], P[2], P[4], P[5]};
+    const double Lf[9] = {L[0], L[1], L[2], L[1], L[3], L[4], L[2], L[4], L[5]};
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A[r * 3 + c] = Pf[r * 3] * Lf[c] + Pf[r * 3 + 1] * Lf[3 + c] + Pf[r * 3 + 2] * Lf[6 + c];
+}
+
+// one loop edge at the current state
+struct LoopLin2 {
+    int jf, jt;          // local vertex indices of from / to
+    int a, b;            // local edge interval [a, b)
+    Lin2 e;
+    double G[9];         // d(residual) / d(total twist over the interval)
+    double g[3];         // G^T D d
+    double Lam[6];       // G^T D G (sym)
+};
+IPC_HD void loop_lin2(const LoopRec2& L, int lo, const P2& pf, const P2& pt, LoopLin2& o) {
+    o.jf = L.from - lo; o.jt = L.to - lo;
+    const bool hi_is_to = L.to > L.from;
+    o.a = o.jf < o.jt ? o.jf : o.jt; o.b = o.jf < o.jt ? o.jt : o.jf;
+    double s, c; ipc_sincos(pf.t, &s, &c);
+    lin2cs(c, s, pf, pt, L.meas[0], L.meas[1], L.meas[2], L.D, o.e);
+    const Lin2& e = o.e;
+    double* G = o.G;
+    if (hi_is_to) {   // G = [R_f^T, R_f^T S t_t; 0 1],  S t = (-y, x)
+        G[0] = e.c; G[1] = e.s; G[2] = e.c * (-pt.y) + e.s * pt.x;
+        G[3] = -e.s; G[4] = e.c; G[5] = -e.s * (-pt.y) + e.c * pt.x;
+        G[6] = 0; G[7] = 0; G[8] = 1;
+    } else {          // G = [-R_f^T, -R_f^T S t_f + (ry, -rx)^T; 0 -1]
+        G[0] = -e.c; G[1] = -e.s; G[2] = -(e.c * (-pf.y) + e.s * pf.x) + e.ry;
+        G[3] = e.s; G[4] = -e.c; G[5] = -(-e.s * (-pf.y) + e.c * pf.x) - e.rx;
+        G[6] = 0; G[7] = 0; G[8] = -1;
+    }
+    o.g[0] = G[0] * e.w0 + G[3] * e.w1 + G[6] * e.w2;
+    o.g[1] = G[1] * e.w0 + G[4] * e.w1 + G[7] * e.w2;
+    o.g[2] = G[2] * e.w0 + G[5] * e.w1 + G[8] * e.w2;
+    double DG[9];
+    const double* D = L.D;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        DG[0 + q] = D[0] * G[q] + D[1] * G[3 + q] + D[2] * G[6 + q];
+        DG[3 + q] = D[1] * G[q] + D[3] * G[3 + q] + D[4] * G[6 + q];
+        DG[6 + q] = D[2] * G[q] + D[4] * G[3 + q] + D[5] * G[6 + q];
+    }
+    o.Lam[0] = G[0] * DG[0] + G[3] * DG[3] + G[6] * DG[6];
+    o.Lam[1] = G[0] * DG[1] + G[3] * DG[4] + G[6] * DG[7];
+    o.Lam[2] = G[0] * DG[2] + G[3] * DG[5] + G[6] * DG[8];
+    o.Lam[3] = G[1] * DG[1] + G[4] * DG[4] + G[7] * DG[7];
+    o.Lam[4] = G[1] * DG[2] + G[4] * DG[5] + G[7] * DG[8];
+    o.Lam[5] = G[2] * DG[2] + G[5] * DG[5] + G[8] * DG[8];
+}
+
+// ------------------------------------------------------------------------------------------------
+// block collectives. Host build (tests/host_emul): NT == 1, everything is the identity.
+// ------------------------------------------------------------------------------------------------
+constexpr int NPRE = 9;      // prefix quantities: PM (00 01 02 11 12 22), Pm (0 1 2)
+constexpr int NSPEC = 4;     // special vertices of a check: 0, rs, re, L (all loop end points are among them)
+constexpr int SPECW = NPRE + 3;   // published per special vertex: full prefix + pose
+
+template <int NT> IPC_HD void bsync() {
+#ifdef __CUDA_ARCH__
+    if (NT <= 32) __syncwarp(); else __syncthreads();
+#endif
+}
+IPC_HD int hd_tid() {
+#ifdef __CUDA_ARCH__
+    return threadIdx.x;
+#else
+    return 0;
+#endif
+}
+
+// Exclusive scan over threads of NPRE values + block sums of NS scalars + block max of one value with ONE barrier.
+// red: [NW][NPRE + NS + 1] staging (caller double-buffers it).
+template <int NT, int NS> struct ScanSumMax {
+    static constexpr int W = NPRE + NS + 1;
+    static constexpr int NW = NT / 32 > 0 ? NT / 32 : 1;
+    IPC_HD static void run(double* v /* in: thread total, out: exclusive prefix */, double* s, double& mx, double* red) {
+#ifdef __CUDA_ARCH__
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        double inc[NPRE];
+#pragma unroll
+        for (int m = 0; m < NPRE; ++m) {
+            double x = v[m];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { double y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            inc[m] = x;
+        }
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s[m] += __shfl_xor_sync(0xffffffffu, s[m], o);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (NT <= 32) {
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) v[m] = inc[m] - v[m];
+            return;
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) red[w * W + m] = inc[m];
+#pragma unroll
+            for (int m = 0; m < NS; ++m) red[w * W + NPRE + m] = s[m];
+            red[w * W + NPRE + NS] = mx;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < NPRE; ++m) {
+            double base = 0;
+            for (int i = 0; i < w; ++i) base += red[i * W + m];
+            v[m] = base + inc[m] - v[m];
+        }
+#pragma unroll
+        for (int m = 0; m < NS; ++m) {
+            double t = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) t += red[i * W + NPRE + m];
+            s[m] = t;
+        }
+        double t = red[NPRE + NS];
+#pragma unroll
+        for (int i = 1; i < NW; ++i) t = fmax(t, red[i * W + NPRE + NS]);
+        mx = t;
+#else
+        for (int m = 0; m < NPRE; ++m) v[m] = 0;
+        (void)s; (void)mx; (void)red;
+#endif
+    }
+};
+
+// plain block sum of M values (slow-path sweeps): two barriers, result in every thread
+template <int NT, int M> IPC_HD void hd_block_sum(double* v, double* red) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[m] += __shfl_xor_sync(0xffffffffu, v[m], o);
+    }
+    if (NT <= 32) return;
+    const int w = threadIdx.x >> 5, NW = NT / 32;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) red[w * M + m] = v[m];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double s = 0;
+        for (int i = 0; i < NW; ++i) s += red[i * M + m];
+        v[m] = s;
+    }
+#else
+    (void)v; (void)red;
+#endif
+}
+// exclusive prefix over threads of M values (dead-reckoning): two barriers
+template <int NT, int M> IPC_HD void hd_block_excl_scan(double* v, double* red) {
+#ifdef __CUDA_ARCH__
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, NW = NT / 32;
+    double inc[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double x = v[m];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { double y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        inc[m] = x;
+    }
+    if (NT > 32) {
+        __syncthreads();
+        if (lane == 31) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) red[w * M + m] = inc[m];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        double base = 0;
+        if (NT > 32) { for (int i = 0; i < NW; ++i) if (i < w) base += red[i * M + m]; }
+        v[m] = base + inc[m] - v[m];
+    }
+#else
+    for (int m = 0; m < M; ++m) v[m] = 0;
+    (void)red;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-check working set
+// ------------------------------------------------------------------------------------------------
+enum { STEP_NONE = 0, STEP_GN = 1, STEP_BLEND = 2 };
+
+struct StepSpec {            // GN solution of one linearisation (uniform; lives in shared memory)
+    double z[3][3];          // force per region
+    double C[3][3];          // constant per region
+    double model;            // sum of linearised chi2 after the GN step
+    int rs, re;              // region boundaries (local vertex / edge indices)
+};
+
+struct UniBlock {            // uniform per-check data (shared memory): read by every thread, written by thread 0
+    LoopRec2 Lc, Lm;
+    StepSpec sol;
+    double n_c, n_m;         // chi2 of the loop edges at the state of the last sweep
+};
+constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
+
+struct ChainMem {
+    // per-vertex state, index j in [0, L]. Shared memory (MODE 0) or per-CTA global scratch (MODE 1).
+    double *X, *Y, *TH;
+    double* P[NPRE];         // thread-LOCAL inclusive prefix of (PM, Pm) at vertex j (edges k0 .. j-1 of the owner thread)
+    // per-CTA global scratch (L2 resident)
+    double *BX, *BY, *BT;    // pose backup: state before the last trial sweep
+    double* GB[3];           // gradient b_j in g2o vertex coordinates (steepest-descent sweeps)
+    double* GH[3];           // h_gn,j in g2o vertex coordinates
+    double* red;             // collective staging, 2 buffers of RED_DOUBLES
+    double* spec;            // special-vertex table, 2 buffers of NSPEC * SPECW
+    UniBlock* U;
+};
+constexpr int RED_DOUBLES = 32 * (NPRE + 3);     // NW <= 32 warps x (NPRE + NS + 1), NS = 2
+constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
+constexpr int CHAIN_STATE_ARRAYS = 3 + NPRE;     // per-vertex doubles in shared memory (MODE 0)
+constexpr int CHAIN_SCRATCH_ARRAYS = 9;          // per-vertex doubles in the global scratch (backup, b, h_gn)
+
+IPC_HD void chain_mem_small(ChainMem& M, double* small) {
+    M.red = small; M.spec = small + 2 * RED_DOUBLES; M.U = reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES + 2 * NSPEC * SPECW);
+}
+
+struct OdomView {            // odometry records of the window, SoA in HBM/L2: zx zy zt d00 d01 d02 d11 d12 d22
+    const double* base;      // component c of local edge k at base[c * stride + k]
+    size_t stride;
+    const double* Du;        // UNI: the one information matrix every odometry edge shares (isotropic in x, y => frame independent)
+    const double* Vu;        //      and its inverse
+    IPC_HD double z(int c, int k) const {
+#ifdef __CUDA_ARCH__
+        return __ldg(base + (size_t)c * stride + k);
+#else
+        return base[(size_t)c * stride + k];
+#endif
+    }
+};
+
+struct ThreadState {         // registers carried from sweep to sweep
+    int k0, k1;              // owned edges [k0, k1); owned vertices k0+1 .. k1
+    P2 pa; double ca, sa;    // pose (+ cos / sin) of vertex k0 at the current state
+    double base[NPRE];       // prefix (PM, Pm) at vertex k0 for the linearisation held in M.P
+};
+
+// twist Xi_j = Pm_j - PM_j z_r - C_r of the GN step at vertex j (region r by position)
+IPC_HD void twist_at(const StepSpec* sp, int j, const double* pre, double* Xi) {
+    const int r = (j <= sp->rs) ? 0 : (j <= sp->re ? 1 : 2);
+    const double* z = sp->z[r]; const double* C = sp->C[r];
+    const double z0 = z[0], z1 = z[1], z2 = z[2];
+    Xi[0] = pre[6] - (pre[0] * z0 + pre[1] * z1 + pre[2] * z2) - C[0];
+    Xi[1] = pre[7] - (pre[1] * z0 + pre[3] * z1 + pre[4] * z2) - C[1];
+    Xi[2] = pre[8] - (pre[2] * z0 + pre[4] * z1 + pre[5] * z2) - C[2];
+}
+IPC_HD void gn_step_at(const StepSpec* sp, int j, const double* pre /* full prefix at j */, double x, double y, double* h) {
+    double X[3]; twist_at(sp, j, pre, X);
+    h[0] = X[0] - y * X[2];      // u = T Xi, T = [I, S t; 0 1]
+    h[1] = X[1] + x * X[2];
+    h[2] = X[2];
+}
+
+// contribution of one linearised odometry edge to the prefix sums: M = Q V Q^T (6), m = -Q d (3); Q = [c -s yb; s c -xb; 0 0 1]
+IPC_HD void edge_prefix_terms(const Lin2& e, const double* V, double xb, double yb, double* t) {
+    const double q02 = yb, q12 = -xb;
+    const double r00 = e.c * V[0] - e.s * V[1] + q02 * V[2], r01 = e.c * V[1] - e.s * V[3] + q02 * V[4], r02 = e.c * V[2] - e.s * V[4] + q02 * V[5];
+    const double r10 = e.s * V[0] + e.c * V[1] + q12 * V[2], r11 = e.s * V[1] + e.c * V[3] + q12 * V[4], r12 = e.s * V[2] + e.c * V[4] + q12 * V[5];
+    t[0] = r00 * e.c - r01 * e.s + r02 * q02;
+    t[1] = r00 * e.s + r01 * e.c + r02 * q12;
+    t[2] = r02;
+    t[3] = r10 * e.s + r11 * e.c + r12 * q12;
+    t[4] = r12;
+    t[5] = V[5];
+    t[6] = -(e.c * e.d0 - e.s * e.d1 + q02 * e.d2);
+    t[7] = -(e.s * e.d0 + e.c * e.d1 + q12 * e.d2);
+    t[8] = -e.d2;
+}
+
+struct SweepOut { double chi, mx, hh; };   // odometry chi2 sum / max at the new state, |h|^2 of the applied step
+
+// The sweep: apply a step (none / GN of M.U->sol / blend c1 b + c2 h_gn from the scratch), re-linearise, new local
+// prefixes, chi2, and publish the special vertices. Writes the pose backup when a step is applied. Two block barriers.
+template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts, SweepOut& out,
+                                              int& buf, const int* spec_v) {
+    const int k0 = ts.k0, k1 = ts.k1;
+    const StepSpec* sp = &M.U->sol;
+    double b0[NPRE];
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) b0[m] = ts.base[m];
+    P2 na = ts.pa; double nca = ts.ca, nsa = ts.sa;
+    if (mode != STEP_NONE && k0 > 0 && k0 < k1) {   // boundary vertex k0: same arithmetic as its owner => identical bits
+        double h[3];
+        if (mode == STEP_GN) gn_step_at(sp, k0, b0, na.x, na.y, h);
+        else {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) h[q] = c1 * M.GB[q][k0] + c2 * M.GH[q][k0];
+        }
+        na.x += h[0]; na.y += h[1]; na.t = wrap_pi_hd(na.t + h[2]);
+        ipc_sincos(na.t, &nsa, &nca);
+    }
+    ts.pa = na; ts.ca = nca; ts.sa = nsa;
+    double run[NPRE];
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) run[m] = 0;
+    double chi = 0, mx = 0, hh = 0;
+    for (int k = k0; k < k1; ++k) {
+        const int j = k + 1;
+        P2 nb{M.X[j], M.Y[j], M.TH[j]};
+        if (mode != STEP_NONE) {
+            double h[3];
+            if (mode == STEP_GN) {
+                double pre[NPRE];
+#pragma unroll
+                for (int m = 0; m < NPRE; ++m) pre[m] = b0[m] + M.P[m][j];
+                gn_step_at(sp, j, pre, nb.x, nb.y, h);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 3; ++q) h[q] = c1 * M.GB[q][j] + c2 * M.GH[q][j];
+            }
+            M.BX[j] = nb.x; M.BY[j] = nb.y; M.BT[j] = nb.t;
+            nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
+            hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+            M.X[j] = nb.x; M.Y[j] = nb.y; M.TH[j] = nb.t;
+        }
+        double D[6], V[6];
+        if (UNI) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { D[c] = O.Du[c]; V[c] = O.Vu[c]; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) D[c] = O.z(3 + c, k);
+            inv_sym3(D, V);
+        }
+        Lin2 e; lin2cs(nca, nsa, na, nb, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+        chi += e.chi; mx = fmax(mx, e.chi);
+        double t[NPRE]; edge_prefix_terms(e, V, nb.x, nb.y, t);
+#pragma unroll
+        for (int m = 0; m < NPRE; ++m) { run[m] += t[m]; M.P[m][j] = run[m]; }
+        na = nb;
+        if (j < k1) ipc_sincos(nb.t, &nsa, &nca);
+    }
+    double s[2] = {chi, hh};
+    ScanSumMax<NT, 2>::run(run, s, mx, M.red + (size_t)buf * RED_DOUBLES);
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) ts.base[m] = run[m];
+    out.chi = s[0]; out.hh = s[1]; out.mx = mx;
+    double* spec = M.spec + (size_t)buf * NSPEC * SPECW;
+#pragma unroll
+    for (int q = 1; q < NSPEC; ++q) {
+        const int v = spec_v[q];
+        if (v > k0 && v <= k1) {
+            double* o = spec + q * SPECW;
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) o[m] = ts.base[m] + M.P[m][v];
+            o[NPRE] = M.X[v]; o[NPRE + 1] = M.Y[v]; o[NPRE + 2] = M.TH[v];
+        }
+    }
+    bsync<NT>();
+    buf ^= 1;
+}
+
+// undo the last applied sweep: poses from the backup, boundary registers re-read. The prefix arrays / bases are NOT restored:
+// every caller re-linearises (GN rejection) or only runs blend sweeps (which do not read them) until a step is accepted.
+template <int NT> IPC_HD_COLD void rollback(const ChainMem& M, ThreadState& ts) {
+    for (int k = ts.k0; k < ts.k1; ++k) { const int j = k + 1; M.X[j] = M.BX[j]; M.Y[j] = M.BY[j]; M.TH[j] = M.BT[j]; }
+    bsync<NT>();
+    if (ts.k0 < ts.k1) {
+        ts.pa.x = M.X[ts.k0]; ts.pa.y = M.Y[ts.k0]; ts.pa.t = M.TH[ts.k0];
+        ipc_sincos(ts.pa.t, &ts.sa, &ts.ca);
+    }
+    bsync<NT>();
+}
+
+// what the uniform part needs about one check
+struct CheckGeom {
+    int K, lo, L;
+    int rs, re, first_is_c, last_is_c;
+    int spec_v[NSPEC];       // 0, rs, re, L
+    // end points of the loop intervals: every start is 0 or rs, every end is re or L
+    int c_a_is_rs, c_b_is_L, m_a_is_rs, m_b_is_L;
+};
+
+struct SpecVals {            // prefix (PM, Pm) and pose at the special vertices rs, re, L (vertex 0: zeros / origin)
+    double pre1[NPRE], pre2[NPRE], pre3[NPRE];
+    P2 p1, p2, p3;
+};
+IPC_HD void spec_load(const double* spec, const CheckGeom& g, SpecVals& sv) {
+    const double* o1 = spec + 1 * SPECW; const double* o2 = spec + 2 * SPECW; const double* o3 = spec + 3 * SPECW;
+    const bool z1 = g.rs == 0;      // nobody owns vertex 0
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) { sv.pre1[m] = z1 ? 0.0 : o1[m]; sv.pre2[m] = o2[m]; sv.pre3[m] = o3[m]; }
+    sv.p1.x = z1 ? 0.0 : o1[NPRE]; sv.p1.y = z1 ? 0.0 : o1[NPRE + 1]; sv.p1.t = z1 ? 0.0 : o1[NPRE + 2];
+    sv.p2.x = o2[NPRE]; sv.p2.y = o2[NPRE + 1]; sv.p2.t = o2[NPRE + 2];
+    sv.p3.x = o3[NPRE]; sv.p3.y = o3[NPRE + 1]; sv.p3.t = o3[NPRE + 2];
+}
+IPC_HD P2 sel_pose(bool c, const P2& a, const P2& b) { P2 r; r.x = c ? a.x : b.x; r.y = c ? a.y : b.y; r.t = c ? a.t : b.t; return r; }
+
+// loop edges linearised at the published state
+IPC_HD void loops_eval(const SpecVals& sv, const CheckGeom& g, const LoopRec2& Lc, const LoopRec2& Lm, LoopLin2& lc, LoopLin2& lm) {
+    const P2 org{0, 0, 0};
+    {
+        const P2 pa = sel_pose(g.c_a_is_rs, sv.p1, org), pb = sel_pose(g.c_b_is_L, sv.p3, sv.p2);
+        const bool to_hi = Lc.to > Lc.from;
+        loop_lin2(Lc, g.lo, sel_pose(to_hi, pa, pb), sel_pose(to_hi, pb, pa), lc);
+    }
+    if (g.K == 2) {
+        const P2 pa = sel_pose(g.m_a_is_rs, sv.p1, org), pb = sel_pose(g.m_b_is_L, sv.p3, sv.p2);
+        const bool to_hi = Lm.to > Lm.from;
+        loop_lin2(Lm, g.lo, sel_pose(to_hi, pa, pb), sel_pose(to_hi, pb, pa), lm);
+    }
+}
+
+// GN solution of the published linearisation: capacitance solve on the interval sums, forces per region, model value
+IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopLin2& lc, const LoopLin2& lm, const double* Dc, const double* Dm, StepSpec* sp) {
+    // region sums: region 0 = [0, rs), region 1 = [rs, re), region 2 = [re, L)
+    double acc[3][NPRE];
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) { acc[0][m] = sv.pre1[m]; acc[1][m] = sv.pre2[m] - sv.pre1[m]; acc[2][m] = sv.pre3[m] - sv.pre2[m]; }
+    double zc[3], zm[3] = {0, 0, 0};
+    if (g.K == 1) {
+        double Amat[9], rhs[3], t[3];
+        const double* P = acc[1];
+        sym3_sym3(P, lc.Lam, Amat);
+        Amat[0] += 1; Amat[4] += 1; Amat[8] += 1;
+        sym3_mul(P, lc.g, t);
+        rhs[0] = acc[1][6] - t[0]; rhs[1] = acc[1][7] - t[1]; rhs[2] = acc[1][8] - t[2];
+        solve_small<3>(Amat, rhs);
+        sym3_mul(lc.Lam, rhs, t);
+        zc[0] = lc.g[0] + t[0]; zc[1] = lc.g[1] + t[1]; zc[2] = lc.g[2] + t[2];
+    } else {
+        double Pcc[6], Pmm[6], Pcm[6], qc[3], qm[3];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            Pcm[q] = acc[1][q];
+            Pcc[q] = acc[1][q] + (g.first_is_c ? acc[0][q] : 0.0) + (g.last_is_c ? acc[2][q] : 0.0);
+            Pmm[q] = acc[1][q] + (g.first_is_c ? 0.0 : acc[0][q]) + (g.last_is_c ? 0.0 : acc[2][q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            qc[q] = acc[1][6 + q] + (g.first_is_c ? acc[0][6 + q] : 0.0) + (g.last_is_c ? acc[2][6 + q] : 0.0);
+            qm[q] = acc[1][6 + q] + (g.first_is_c ? 0.0 : acc[0][6 + q]) + (g.last_is_c ? 0.0 : acc[2][6 + q]);
+        }
+        double Amat[36], rhs[6], B[9], t[3], t2[3];
+        sym3_sym3(Pcc, lc.Lam, B);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Amat[r * 6 + c] = B[r * 3 + c] + (r == c ? 1.0 : 0.0);
+        sym3_sym3(Pcm, lm.Lam, B);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Amat[r * 6 + 3 + c] = B[r * 3 + c];
+        sym3_sym3(Pcm, lc.Lam, B);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Amat[(3 + r) * 6 + c] = B[r * 3 + c];
+        sym3_sym3(Pmm, lm.Lam, B);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Amat[(3 + r) * 6 + 3 + c] = B[r * 3 + c] + (r == c ? 1.0 : 0.0);
+        sym3_mul(Pcc, lc.g, t); sym3_mul(Pcm, lm.g, t2);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) rhs[q] = qc[q] - t[q] - t2[q];
+        sym3_mul(Pcm, lc.g, t); sym3_mul(Pmm, lm.g, t2);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) rhs[3 + q] = qm[q] - t[q] - t2[q];
+        solve_small<6>(Amat, rhs);
+        sym3_mul(lc.Lam, rhs, t);
+        sym3_mul(lm.Lam, rhs + 3, t2);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { zc[q] = lc.g[q] + t[q]; zm[q] = lm.g[q] + t2[q]; }
+    }
+    sp->rs = g.rs; sp->re = g.re;
+    double z[3][3], C[3][3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (g.K == 1) { z[0][q] = 0; z[1][q] = zc[q]; z[2][q] = 0; }
+        else {
+            z[0][q] = g.first_is_c ? zc[q] : zm[q];
+            z[1][q] = zc[q] + zm[q];
+            z[2][q] = g.last_is_c ? zc[q] : zm[q];
+        }
+    }
+    // C_0 = 0, C_1 = PM(rs) (z_0 - z_1), C_2 = C_1 + PM(re) (z_1 - z_2)
+    {
+        double dz[3], t[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { C[0][q] = 0; dz[q] = z[0][q] - z[1][q]; }
+        sym3_mul(sv.pre1, dz, t);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { C[1][q] = t[q]; dz[q] = z[1][q] - z[2][q]; }
+        sym3_mul(sv.pre2, dz, t);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) C[2][q] = C[1][q] + t[q];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { sp->z[r][q] = z[r][q]; sp->C[r][q] = C[r][q]; }
+    // model value after the GN step: odometry edges sum_r z_r^T P_r z_r, loop edges (d + G dXi)^T D (d + G dXi)
+    double model = 0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) model += quad3(acc[r], z[r][0], z[r][1], z[r][2]);
+    double X1[3], X2[3], X3[3];
+    twist_at(sp, g.rs, sv.pre1, X1); twist_at(sp, g.re, sv.pre2, X2); twist_at(sp, g.L, sv.pre3, X3);
+    {
+        double dX[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) dX[q] = (g.c_b_is_L ? X3[q] : X2[q]) - (g.c_a_is_rs ? X1[q] : 0.0);
+        const double* G = lc.G;
+        const double n0 = lc.e.d0 + G[0] * dX[0] + G[1] * dX[1] + G[2] * dX[2];
+        const double n1 = lc.e.d1 + G[3] * dX[0] + G[4] * dX[1] + G[5] * dX[2];
+        const double n2 = lc.e.d2 + G[6] * dX[0] + G[7] * dX[1] + G[8] * dX[2];
+        model += quad3(Dc, n0, n1, n2);
+    }
+    if (g.K == 2) {
+        double dX[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) dX[q] = (g.m_b_is_L ? X3[q] : X2[q]) - (g.m_a_is_rs ? X1[q] : 0.0);
+        const double* G = lm.G;
+        const double n0 = lm.e.d0 + G[0] * dX[0] + G[1] * dX[1] + G[2] * dX[2];
+        const double n1 = lm.e.d1 + G[3] * dX[0] + G[4] * dX[1] + G[5] * dX[2];
+        const double n2 = lm.e.d2 + G[6] * dX[0] + G[7] * dX[1] + G[8] * dX[2];
+        model += quad3(Dm, n0, n1, n2);
+    }
+    sp->model = model;
+}
+
+// After a sweep: thread 0 evaluates the loop edges at the published state and, if the trial is going to be kept
+// (rho > 0, or `force`), solves the new linearisation into M.U->sol. One barrier; every thread gets the loop chi2.
+IPC_HD_COLD void eval_and_solve_t0(const ChainMem& M, const CheckGeom& g, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
+    SpecVals sv; LoopLin2 lc, lm;
+    spec_load(M.spec + (size_t)(buf ^ 1) * NSPEC * SPECW, g, sv);
+    loops_eval(sv, g, M.U->Lc, M.U->Lm, lc, lm);
+    const double c = lc.e.chi, m = g.K == 2 ? lm.e.chi : 0.0;
+    if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
+    const double rho = (cur_chi - (odom_chi + c + m)) / linearGain;
+    if (force || rho > 0) gn_solve(sv, g, lc, lm, M.U->Lc.D, M.U->Lm.D, &M.U->sol);
+    M.U->n_c = c; M.U->n_m = m;
+}
+template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, const CheckGeom& g, int buf, double odom_chi, double cur_chi, double linearGain,
+                                             bool force, double& n_c, double& n_m) {
+    if (hd_tid() == 0) eval_and_solve_t0(M, g, buf, odom_chi, cur_chi, linearGain, force);
+    bsync<NT>();
+    n_c = M.U->n_c; n_m = M.U->n_m;
+}
+
+// |h_gn|^2 of the current linearisation without applying it
+template <int NT> IPC_HD_COLD double gn_norm_sq(const ChainMem& M, const ThreadState& ts) {
+    double v[1] = {0};
+    const StepSpec* sp = &M.U->sol;
+    for (int k = ts.k0; k < ts.k1; ++k) {
+        const int j = k + 1;
+        double pre[NPRE], h[3];
+#pragma unroll
+        for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m] + M.P[m][j];
+        gn_step_at(sp, j, pre, M.X[j], M.Y[j], h);
+        v[0] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+    }
+    hd_block_sum<NT, 1>(v, M.red);
+    return v[0];
+}
+
+// steepest-descent sweeps at the current state (poses + prefixes valid): gradient b and h_gn per vertex into the scratch,
+// bb = |b|^2, bh = b . h_gn, hh = |h_gn|^2, bHb = b^T H b.
+template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const OdomView& O, const CheckGeom& g, const ThreadState& ts, double& bb,
+                                                  double& bh, double& hh, double& bHb) {
+    const int k0 = ts.k0, k1 = ts.k1, L = g.L;
+    const StepSpec* sp = &M.U->sol;
+    const LoopRec2& Lc = M.U->Lc; const LoopRec2& Lm = M.U->Lm;
+    // loop edges at the current state (poses are stable in M.X: nobody writes them during these sweeps)
+    Lin2 ec, em; const int cjf = Lc.from - g.lo, cjt = Lc.to - g.lo; int mjf = -1, mjt = -1;
+    {
+        P2 pf{M.X[cjf], M.Y[cjf], M.TH[cjf]}, pt{M.X[cjt], M.Y[cjt], M.TH[cjt]};
+        double s, c; ipc_sincos(pf.t, &s, &c);
+        lin2cs(c, s, pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
+    }
+    double gci[3], gcj[3], gmi[3] = {0, 0, 0}, gmj[3] = {0, 0, 0};
+    grad2(ec, gci, gcj);
+    if (g.K == 2) {
+        mjf = Lm.from - g.lo; mjt = Lm.to - g.lo;
+        P2 pf{M.X[mjf], M.Y[mjf], M.TH[mjf]}, pt{M.X[mjt], M.Y[mjt], M.TH[mjt]};
+        double s, c; ipc_sincos(pf.t, &s, &c);
+        lin2cs(c, s, pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
+        grad2(em, gmi, gmj);
+    }
+    double v[3] = {0, 0, 0};
+    auto finish_vertex = [&](int j, const double* gsum, double x, double y) {   // b_j = -(odometry terms) - loop terms
+        double b[3] = {-gsum[0], -gsum[1], -gsum[2]};
+        if (j == cjf) { b[0] -= gci[0]; b[1] -= gci[1]; b[2] -= gci[2]; }
+        if (j == cjt) { b[0] -= gcj[0]; b[1] -= gcj[1]; b[2] -= gcj[2]; }
+        if (j == mjf) { b[0] -= gmi[0]; b[1] -= gmi[1]; b[2] -= gmi[2]; }
+        if (j == mjt) { b[0] -= gmj[0]; b[1] -= gmj[1]; b[2] -= gmj[2]; }
+        double pre[NPRE], h[3];
+#pragma unroll
+        for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m] + M.P[m][j];
+        gn_step_at(sp, j, pre, x, y, h);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { M.GB[q][j] = b[q]; M.GH[q][j] = h[q]; }
+        v[0] += b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+        v[1] += b[0] * h[0] + b[1] * h[1] + b[2] * h[2];
+        v[2] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+    };
+    if (k0 < k1) {
+        P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
+        double gprev[3] = {0, 0, 0};   // gj of the edge that ends at the current vertex
+        for (int k = k0; k <= k1 && k < L; ++k) {      // one extra edge (k1) for the gradient at the last owned vertex
+            P2 pb{M.X[k + 1], M.Y[k + 1], M.TH[k + 1]};
+            double D[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : O.z(3 + c, k);
+            Lin2 e; lin2cs(ca, sa, pa, pb, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+            double gi[3], gj[3]; grad2(e, gi, gj);
+            if (k > k0) {   // vertex j = k is complete: gj(edge j-1) + gi(edge j)
+                const double gs[3] = {gprev[0] + gi[0], gprev[1] + gi[1], gprev[2] + gi[2]};
+                finish_vertex(k, gs, pa.x, pa.y);
+            }
+            gprev[0] = gj[0]; gprev[1] = gj[1]; gprev[2] = gj[2];
+            pa = pb; ipc_sincos(pb.t, &sa, &ca);
+        }
+        if (k1 == L) finish_vertex(L, gprev, pa.x, pa.y);   // last vertex of the window: no outgoing odometry edge
+    }
+    if (hd_tid() == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { M.GB[q][0] = 0; M.GH[q][0] = 0; }   // vertex 0 is fixed
+    }
+    hd_block_sum<NT, 3>(v, M.red);
+    bsync<NT>();                        // GB / GH visible to the neighbours
+    bb = v[0]; bh = v[1]; hh = v[2];
+    // b^T H b = sum over edges |J b|^2_D
+    double w[1] = {0};
+    if (k0 < k1) {
+        P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
+        double ba[3] = {M.GB[0][k0], M.GB[1][k0], M.GB[2][k0]};
+        for (int k = k0; k < k1; ++k) {
+            P2 pb{M.X[k + 1], M.Y[k + 1], M.TH[k + 1]};
+            double D[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : O.z(3 + c, k);
+            Lin2 e; lin2cs(ca, sa, pa, pb, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+            double bv[3] = {M.GB[0][k + 1], M.GB[1][k + 1], M.GB[2][k + 1]};
+            double q0, q1, q2; dlin2(e, ba, bv, q0, q1, q2);
+            w[0] += quad3(D, q0, q1, q2);
+            ba[0] = bv[0]; ba[1] = bv[1]; ba[2] = bv[2];
+            pa = pb; ipc_sincos(pb.t, &sa, &ca);
+        }
+    }
+    if (hd_tid() == 0) {
+        double bf[3] = {M.GB[0][cjf], M.GB[1][cjf], M.GB[2][cjf]}, bt[3] = {M.GB[0][cjt], M.GB[1][cjt], M.GB[2][cjt]}, q0, q1, q2;
+        dlin2(ec, bf, bt, q0, q1, q2); w[0] += quad3(Lc.D, q0, q1, q2);
+        if (g.K == 2) {
+            double mf[3] = {M.GB[0][mjf], M.GB[1][mjf], M.GB[2][mjf]}, mt[3] = {M.GB[0][mjt], M.GB[1][mjt], M.GB[2][mjt]};
+            dlin2(em, mf, mt, q0, q1, q2); w[0] += quad3(Lm.D, q0, q1, q2);
+        }
+    }
+    hd_block_sum<NT, 1>(w, M.red);
+    bHb = w[0];
+}
+
+struct CheckParams {
+    double fast_th, slow_th;
+    int fast_iter, slow_iter;
+    double noise_eps;        // > 0: stop retrying once a rejected trial's own predicted gain is <= noise_eps * chi2 (below the
+                             // round-off of the chi2 evaluation every later, smaller, retry is a coin flip on noise); 0 = replay all retries
+    int max_tries, speculate, early_accept;
+};
+struct CheckResult {
+    int verdict;
+    double max_chi2, cand_chi2, sum_chi2;
+    int iterations, evals, window_len, n_loops;
+    int n_sweeps;            // diagnostics: sweeps of every kind executed
+};
+
+// One check, executed cooperatively by NT threads (device) or by the calling thread (host, NT = 1).
+template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const double* odom, size_t odom_stride, const double* Du, const double* Vu,
+                                                  const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res) {
+    const int tid = hd_tid();
+    bsync<NT>();                                            // previous check is done with every array and with M.U
+    if (tid == 0) { M.U->Lc = *Lc_in; M.U->Lm = Lm_in ? *Lm_in : *Lc_in; }
+    bsync<NT>();
+    CheckGeom g;
+    int ma_l = 0, mb_l = 0;
+    {
+        const int cf = M.U->Lc.from, ct = M.U->Lc.to;
+        const int ca = cf < ct ? cf : ct, cb = cf < ct ? ct : cf;
+        int lo = ca, hi = cb; g.K = 1;
+        int ma = 0, mb = 0;
+        if (Lm_in) {
+            const int mf = M.U->Lm.from, mt = M.U->Lm.to;
+            ma = mf < mt ? mf : mt; mb = mf < mt ? mt : mf;
+            // src/consensus.cpp:157-159: positive-length overlap pulls the member into the cluster
+            if ((mb < cb ? mb : cb) - (ma > ca ? ma : ca) > 0) { g.K = 2; lo = ca < ma ? ca : ma; hi = cb > mb ? cb : mb; }
+        }
+        const int L = hi - lo;
+        g.lo = lo; g.L = L;
+        const int ca_l = ca - lo, cb_l = cb - lo;
+        g.rs = 0; g.re = L; g.first_is_c = 1; g.last_is_c = 1;
+        ma_l = 0; mb_l = L;
+        if (g.K == 2) {
+            ma_l = ma - lo; mb_l = mb - lo;
+            g.rs = ca_l > ma_l ? ca_l : ma_l; g.re = cb_l < mb_l ? cb_l : mb_l;
+            g.first_is_c = (ca_l == 0); g.last_is_c = (cb_l == L);
+        }
+        g.spec_v[0] = 0; g.spec_v[1] = g.rs; g.spec_v[2] = g.re; g.spec_v[3] = L;
+        g.c_a_is_rs = ca_l != 0; g.c_b_is_L = cb_l == L; g.m_a_is_rs = ma_l != 0; g.m_b_is_L = mb_l == L;
+    }
+    const int L = g.L;
+    const double th = (g.K == 2) ? prm.slow_th : prm.fast_th;
+    int max_iter = (g.K == 2) ? prm.slow_iter : prm.fast_iter;
+    if (L + g.K > 100) max_iter *= 5;                      // src/consensus_utils.cpp:12-13
+    OdomView O{odom + g.lo, odom_stride, Du, Vu};
+
+    ThreadState ts;
+    int S = (L + NT - 1) / NT; if (S < 1) S = 1; S |= 1;   // odd segment length: conflict-free strided shared-memory access
+    ts.k0 = tid * S < L ? tid * S : L; ts.k1 = ts.k0 + S < L ? ts.k0 + S : L;
+    const int k0 = ts.k0, k1 = ts.k1;
+
+    // ---- dead-reckoning (propagateGuess, src/consensus_utils.cpp:98-116) as two block scans --------------
+    {
+        double v[1] = {0};
+        for (int k = k0; k < k1; ++k) v[0] += O.z(2, k);
+        hd_block_excl_scan<NT, 1>(v, M.red);
+        double acc = v[0];
+        const double th0 = wrap_pi_hd(acc);                 // heading of vertex k0
+        if (tid == 0) { M.X[0] = 0; M.Y[0] = 0; M.TH[0] = 0; }
+        double p[2] = {0, 0};
+        double thk = th0;
+        for (int k = k0; k < k1; ++k) {
+            double s, c; ipc_sincos(thk, &s, &c);
+            p[0] += c * O.z(0, k) - s * O.z(1, k); p[1] += s * O.z(0, k) + c * O.z(1, k);
+            acc += O.z(2, k); thk = wrap_pi_hd(acc); M.TH[k + 1] = thk;
+        }
+        bsync<NT>();
+        hd_block_excl_scan<NT, 2>(p, M.red);
+        double ax = p[0], ay = p[1];
+        ts.pa.x = ax; ts.pa.y = ay; ts.pa.t = th0;
+        ipc_sincos(th0, &ts.sa, &ts.ca);
+        thk = th0;
+        for (int k = k0; k < k1; ++k) {
+            double s, c; ipc_sincos(thk, &s, &c);
+            ax += c * O.z(0, k) - s * O.z(1, k); ay += s * O.z(0, k) + c * O.z(1, k);
+            M.X[k + 1] = ax; M.Y[k + 1] = ay; thk = M.TH[k + 1];
+        }
+#pragma unroll
+        for (int m = 0; m < NPRE; ++m) ts.base[m] = 0;
+    }
+    int buf = 0, n_sweeps = 0;
+    SweepOut so;
+    double n_c, n_m;
+    sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps;
+    eval_and_solve<NT>(M, g, buf, so.chi, 0, 1, true, n_c, n_m);
+    double cur_chi = so.chi + n_c + n_m;
+    double cur_max = fmax(so.mx, fmax(n_c, n_m));
+    double cand_chi = n_c;
+
+    // ---- Dogleg (OptimizationAlgorithmDogleg::solve + SparseOptimizer::optimize) --------------------------
+    double delta = 1e4;
+    int iterations = 0, evals = 0;
+    bool ok = true;
+    double prev_hnorm = -1;      // norm of the last accepted step (speculation heuristic)
+    for (int it = 0; it < max_iter && ok; ++it) {
+        if (prm.early_accept && !want_info && cur_chi <= th) break;     // every edge chi2 <= sum <= th, and the sum only decreases
+        bool have_norm = false, have_sd = false, good = false;
+        double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0;
+        int tries = 0;
+        do {
+            ++tries;
+            bool trial_done = false, trial_gn = false;
+            double linearGain = 0;
+            const double gn_gain = cur_chi - M.U->sol.model;     // predicted gain of the GN step of the current linearisation
+            if (!have_norm) {
+                if (prm.speculate && prev_hnorm >= 0 && 4 * prev_hnorm < delta) {
+                    sweep<NT, UNI>(M, O, STEP_GN, 0, 1, ts, so, buf, g.spec_v); ++n_sweeps;
+                    hgnNorm = sqrt(so.hh); have_norm = true;
+                    if (hgnNorm < delta) { trial_done = true; trial_gn = true; }
+                    else {   // the GN step does not fit the trust region after all: undo, restore the linearisation
+                        rollback<NT>(M, ts);
+                        sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps;
+                    }
+                } else {
+                    hgnNorm = sqrt(gn_norm_sq<NT>(M, ts)); have_norm = true;
+                }
+            }
+            if (!trial_done) {
+                if (hgnNorm < delta) {
+                    sweep<NT, UNI>(M, O, STEP_GN, 0, 1, ts, so, buf, g.spec_v); ++n_sweeps;
+                    trial_gn = true;
+                } else {
+                    if (!have_sd) {
+                        sd_sweeps<NT, UNI>(M, O, g, ts, bb, bh, hh, bHb); n_sweeps += 2;
+                        alpha = bb / bHb;
+                        hsdNorm = alpha * sqrt(bb);
+                        have_sd = true;
+                    }
+                    double c1, c2;
+                    if (hsdNorm > delta) { c1 = delta / hsdNorm * alpha; c2 = 0; }
+                    else {
+                        const double hsdSq = alpha * alpha * bb;
+                        const double c = alpha * bh - hsdSq;                     // hsd . (hgn - hsd)
+                        const double bma = hh - 2 * alpha * bh + hsdSq;           // |hgn - hsd|^2
+                        double beta;
+                        if (c <= 0) beta = (-c + sqrt(c * c + bma * (delta * delta - hsdSq))) / bma;
+                        else beta = (delta * delta - hsdSq) / (c + sqrt(c * c + bma * (delta * delta - hsdSq)));
+                        c1 = alpha * (1 - beta); c2 = beta;
+                    }
+                    // H h_gn = b  =>  h^T H h = c1^2 bHb + 2 c1 c2 bb + c2^2 bh,  b^T h = c1 bb + c2 bh
+                    linearGain = -(c1 * c1 * bHb + 2 * c1 * c2 * bb + c2 * c2 * bh) + 2 * (c1 * bb + c2 * bh);
+                    sweep<NT, UNI>(M, O, STEP_BLEND, c1, c2, ts, so, buf, g.spec_v); ++n_sweeps;
+                }
+            }
+            if (trial_gn) linearGain = gn_gain;
+            const double hdlNorm = sqrt(so.hh);
+            ++evals;
+            // loop edges at the trial state; thread 0 also solves the new linearisation when the step is going to be kept
+            eval_and_solve<NT>(M, g, buf, so.chi, cur_chi, linearGain, false, n_c, n_m);
+            const double newChi = so.chi + n_c + n_m;
+            const double rawGain = linearGain;
+            if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
+            const double rho = (cur_chi - newChi) / linearGain;
+            if (rho > 0) {
+                good = true;
+                cur_chi = newChi; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
+                prev_hnorm = hdlNorm;
+            } else {
+                rollback<NT>(M, ts);
+                if (trial_gn) { sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps; }   // prefixes of the old state again
+                prev_hnorm = -1;
+            }
+            if (rho > 0.75) delta = fmax(delta, 3 * hdlNorm);
+            else if (rho < 0.25) delta *= 0.5;
+            if (!good) {
+                // a rejected Gauss-Newton step is retried verbatim while it still fits the trust region: every such retry
+                // reproduces the same rho (<= 0), so only the halving of delta and the try counter advance
+                if (trial_gn) while (tries < prm.max_tries && hgnNorm < delta) { ++tries; ++evals; delta *= 0.5; }
+                if (prm.noise_eps > 0 && rawGain <= prm.noise_eps * cur_chi + 1e-300) tries = prm.max_tries;
+            }
+        } while (!good && tries < prm.max_tries);
+        ++iterations;
+        if (tries >= prm.max_tries || !good) ok = false;       // Terminate
+    }
+    res.verdict = (cur_max > th) ? 0 : 1;                      // every edge chi2 <= th (src/consensus_utils.cpp:17-19)
+    res.max_chi2 = cur_max; res.cand_chi2 = cand_chi; res.sum_chi2 = cur_chi;
+    res.iterations = iterations; res.evals = evals; res.window_len = L; res.n_loops = g.K; res.n_sweeps = n_sweeps;
+}
+
+}  // namespace ipcb

@@ -1,0 +1,43 @@
+// chain_se2_kernel.cuh — CUDA entry of the SE(2) window check (see chain_se2.cuh for the algorithm).
+// MODE 0: per-vertex state (pose + prefix sums, 12 doubles / vertex) in shared memory;
+// MODE 1: state in the per-CTA global scratch (windows longer than shared memory holds).
+#pragma once
+#include "chain_se2.cuh"
+
+namespace ipcb {
+
+template <int NT, int MODE, bool UNI>
+__global__ void __launch_bounds__(NT) chain_check_se2(BatchArgs A) {
+    extern __shared__ __align__(16) double sm[];
+    const int capv = A.Lcap + 2;
+    ChainMem M;
+    chain_mem_small(M, sm);
+    double* scr = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
+    M.BX = scr; M.BY = scr + capv; M.BT = scr + 2 * (size_t)capv;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { M.GB[q] = scr + (size_t)(3 + q) * capv; M.GH[q] = scr + (size_t)(6 + q) * capv; }
+    double* st = (MODE == 0) ? sm + CHAIN_SMALL_DOUBLES : scr + (size_t)CHAIN_SCRATCH_ARRAYS * capv;
+    M.X = st; M.Y = st + capv; M.TH = st + 2 * (size_t)capv;
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) M.P[m] = st + (size_t)(3 + m) * capv;
+    const LoopRec2* loops = static_cast<const LoopRec2*>(A.loops);
+    CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept};
+    const int n_work = *A.n_work;
+    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+        const int chk = A.work[wi];
+        const int midx = A.member[chk];
+        CheckResult r;
+        run_check<NT, UNI>(M, A.odom, (size_t)A.n_pad, A.Du, A.Vu, loops + A.cand[chk], midx >= 0 ? loops + midx : nullptr, prm, A.info != nullptr, r);
+        if (threadIdx.x == 0) {
+            A.verdict[chk] = (unsigned char)r.verdict;
+            if (A.info) {
+                ipc_check_info o;
+                o.max_chi2 = r.max_chi2; o.cand_chi2 = r.cand_chi2; o.sum_chi2 = r.sum_chi2;
+                o.iterations = r.iterations; o.evals = r.evals; o.window_len = r.window_len; o.n_loops = r.n_loops;
+                A.info[chk] = o;
+            }
+        }
+    }
+}
+
+}  // namespace ipcb

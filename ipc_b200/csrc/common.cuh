@@ -18,98 +18,24 @@ struct LoopRec2 {
 struct BatchArgs {
     const double* odom;        // SoA: NCOMP component arrays of length n_pad
     int n_pad;
+    double Du[6], Vu[6];       // uniform-information specialisation (kernels instantiated with UNI = true)
     const void* loops;         // LoopRec2 / LoopRec3
     const int* member;         // per check: member loop index or -1
     const int* cand;           // per check: candidate loop index
     const int* work;           // check ids handled by this launch (sorted by window length, longest first)
     const int* n_work;         // device counter: number of entries in `work`
-    double* scratch;           // MODE 2: per-CTA state arrays
-    int Lcap;                  // capacity (edges) of the shared-memory arrays, even
+    double* scratch;           // per-CTA global scratch (pose backup, gradient, h_gn; MODE 1: the state arrays too)
+    size_t scratch_stride;     // doubles per CTA
+    int Lcap;                  // capacity (edges) of the per-vertex arrays, even
     double fast_th, slow_th;
     int fast_iter, slow_iter;
-    int noise_exit;
+    double noise_eps;          // see CheckParams::noise_eps
     int max_tries;
+    int speculate;             // apply the GN step before its norm is known when the trust region is far away
+    int early_accept;          // verdict-only batches: stop once sum chi2 <= th (the verdict can no longer change)
     unsigned char* verdict;    // per check
     ipc_check_info* info;      // per check (may be null)
 };
-
-// ---- g2o normalize_theta: [-pi, pi) ---------------------------------------------------------------
-__device__ __forceinline__ double wrap_pi(double t) {
-    const double pi = 3.14159265358979323846;
-    if (t >= -pi && t < pi) return t;
-    double m = floor(t / (2 * pi));
-    t = t - m * 2 * pi;
-    if (t >= pi) t -= 2 * pi;
-    if (t < -pi) t += 2 * pi;
-    return t;
-}
-
-template <int NT> __device__ __forceinline__ void bsync() {
-    if (NT == 32) __syncwarp(); else __syncthreads();
-}
-
-// sum of M values over the block, result identical in every thread (xor butterfly + fixed-order cross-warp sum)
-template <int NT, int M> __device__ __forceinline__ void block_sum(double (&v)[M], double* red) {
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v[m] += __shfl_xor_sync(0xffffffffu, v[m], o);
-    }
-    if (NT == 32) return;
-    const int w = threadIdx.x >> 5, NW = NT / 32;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) {
-#pragma unroll
-        for (int m = 0; m < M; ++m) red[w * M + m] = v[m];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        double s = 0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) s += red[i * M + m];
-        v[m] = s;
-    }
-}
-template <int NT> __device__ __forceinline__ double block_max(double v, double* red) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    if (NT == 32) return v;
-    const int w = threadIdx.x >> 5, NW = NT / 32;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[w] = v;
-    __syncthreads();
-    double s = red[0];
-#pragma unroll
-    for (int i = 1; i < NW; ++i) s = fmax(s, red[i]);
-    return s;
-}
-// exclusive prefix over threads of M values (thread t receives sum over threads < t); v is replaced
-template <int NT, int M> __device__ __forceinline__ void block_excl_scan(double (&v)[M], double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, NW = NT / 32;
-    double inc[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        double x = v[m];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { double y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        inc[m] = x;
-    }
-    if (NT > 32) {
-        __syncthreads();
-        if (lane == 31) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) red[w * M + m] = inc[m];
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        double base = 0;
-        if (NT > 32) { for (int i = 0; i < NW; ++i) if (i < w) base += red[i * M + m]; }
-        v[m] = base + inc[m] - v[m];
-    }
-}
 
 // ---- mbarrier + 1-D bulk copy (TMA engine, UBLKCP in SASS) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

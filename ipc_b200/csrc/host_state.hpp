@@ -21,6 +21,8 @@ struct HostState {
     std::vector<double> odom_meas;   // [n-1][mw]
     std::vector<double> odom_info;   // [n-1][d*d], already multiplied by s_factor (robustifyVoters, consensus_utils.cpp:123-130)
     std::vector<HostEdge> cns;       // _max_consensus_set
+    bool uniform_iso = false;        // every odometry edge carries the same information, isotropic in (x, y) and with no
+    double Du[6] = {0}, Vu[6] = {0}; // x/y-theta coupling: E^T Omega E = Omega for every edge, kernels skip the per-edge loads
 
     static double norm_theta(double t) {
         const double pi = 3.14159265358979323846;
@@ -39,6 +41,17 @@ struct HostState {
         for (auto& v : odom_info) v *= s_factor;
         for (size_t i = 0; i < odom_meas.size(); ++i) if (!std::isfinite(odom_meas[i])) { err = "non-finite odometry measurement"; return false; }
         for (size_t i = 0; i < odom_info.size(); ++i) if (!std::isfinite(odom_info[i])) { err = "non-finite odometry information"; return false; }
+        uniform_iso = false;
+        if (dim == 2) {
+            const double* W = odom_info.data();
+            bool u = W[0] == W[4] && W[1] == 0 && W[3] == 0 && W[2] == 0 && W[5] == 0 && W[6] == 0 && W[7] == 0;
+            for (int k = 1; u && k + 1 < n; ++k) u = std::equal(W, W + 9, W + (size_t)k * 9);
+            if (u) {
+                uniform_iso = true;
+                Du[0] = W[0]; Du[1] = 0; Du[2] = 0; Du[3] = W[4]; Du[4] = 0; Du[5] = W[8];
+                Vu[0] = 1.0 / W[0]; Vu[1] = 0; Vu[2] = 0; Vu[3] = 1.0 / W[4]; Vu[4] = 0; Vu[5] = 1.0 / W[8];
+            }
+        }
         return true;
     }
 
@@ -64,6 +77,7 @@ struct HostState {
             for (int k = 0; k + 1 < n; ++k) {
                 double z[3], D[6];
                 se2_edge_record(&odom_meas[(size_t)k * 3], &odom_info[(size_t)k * 9], 1.0, z, D);
+                if (uniform_iso) for (int c = 0; c < 6; ++c) D[c] = Du[c];
                 for (int c = 0; c < 3; ++c) soa[(size_t)c * n_pad + k] = z[c];
                 for (int c = 0; c < 6; ++c) soa[(size_t)(3 + c) * n_pad + k] = D[c];
             }

@@ -8,7 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "check_se2.cuh"
+#include "chain_se2_kernel.cuh"
 #include "host_state.hpp"
 
 using namespace ipcb;
@@ -31,7 +31,7 @@ namespace ipcb {
 
 __global__ void plan_checks(const int* __restrict__ lfrom_to, int loop_stride_ints, int n_checks, const int* __restrict__ member,
                             const int* __restrict__ cand, const int* __restrict__ bucket_cap, int n_buckets, int* __restrict__ counts,
-                            int* __restrict__ work, unsigned long long* __restrict__ stats) {
+                            int* __restrict__ work, int work_stride, unsigned long long* __restrict__ stats) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long sl = 0, sk = 0;
     if (c < n_checks) {
@@ -48,7 +48,7 @@ __global__ void plan_checks(const int* __restrict__ lfrom_to, int loop_stride_in
         int b = 0;
         while (b < n_buckets - 1 && L > bucket_cap[b]) ++b;
         int pos = atomicAdd(&counts[b], 1);
-        work[(size_t)b * n_checks + pos] = c;
+        work[(size_t)b * work_stride + pos] = c;
         sl = (unsigned long long)L; sk = (unsigned long long)K;
     }
     // warp-aggregate the statistics
@@ -72,25 +72,33 @@ namespace {
 
 constexpr int NB = 6;   // launch buckets
 struct Bucket { int cap; int nt; int mode; };
-// window-length caps (edges), threads per CTA, memory mode (see check_se2.cuh)
-const Bucket kBuckets2[NB] = {{64, 32, 0}, {256, 64, 0}, {768, 128, 0}, {1800, 256, 0}, {4600, 512, 1}, {1 << 30, 512, 2}};
+// window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh). MODE 0 keeps 12 doubles per
+// vertex in shared memory: 227 KB holds windows up to ~2300 edges; longer windows run from the global scratch.
+const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 128, 0}, {800, 256, 0}, {1400, 512, 0}, {2100, 512, 0}, {1 << 30, 512, 1}};
 
-size_t smem_bytes(int nt, int mode, int cap) {
+size_t smem_bytes(int mode, int cap) {
     size_t capv = cap + 2;
-    size_t n = (nt / 32) * 32 + 2 + (mode == 0 ? 15 : mode == 1 ? 6 : 0) * capv;
+    size_t n = CHAIN_SMALL_DOUBLES + (mode == 0 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0);
     return n * sizeof(double);
 }
+size_t scratch_doubles_per_cta(int mode, int cap) {
+    size_t capv = cap + 2;
+    return (size_t)(CHAIN_SCRATCH_ARRAYS + (mode == 1 ? CHAIN_STATE_ARRAYS : 0)) * capv;
+}
 
-template <int NT, int MODE> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st) {
-    size_t sm = smem_bytes(NT, MODE, a.Lcap);
+template <int NT, int MODE, bool UNI> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
+    size_t sm = smem_bytes(MODE, a.Lcap);
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(check_chain_se2<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    check_chain_se2<NT, MODE><<<grid, NT, sm, st>>>(a);
+    chain_check_se2<NT, MODE, UNI><<<grid, NT, sm, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return IPC_OK;
+}
+template <int NT, int MODE> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
+    return uni ? launch_se2u<NT, MODE, true>(a, grid, st) : launch_se2u<NT, MODE, false>(a, grid, st);
 }
 
 }  // namespace
@@ -101,8 +109,11 @@ struct ipc_handle {
     int device = 0;
     int n_sm = 148;
     ipc_config cfg{};
-    int noise_exit = 1;
+    double noise_eps = 1e-13;         // DESIGN.md "Termination"; 0 = replay every retry like g2o
     int max_tries = 100;
+    int speculate = 1;
+    int early_accept = 0;
+    int use_uniform = 1;              // allow the uniform-information kernels when the graph qualifies
     HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
     // device graph
     double* d_odom = nullptr;         // SoA components
@@ -116,8 +127,7 @@ struct ipc_handle {
     uint32_t* d_bits = nullptr;
     ipc_check_info* d_info = nullptr;
     unsigned long long* d_stats = nullptr;
-    double* d_scratch = nullptr; size_t scratch_doubles = 0;
-    int scratch_grid = 0;
+    double* d_scratch = nullptr; size_t scratch_doubles = 0;   // per-CTA scratch, shared by the (serialised) bucket launches
     int last_launches = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
@@ -150,7 +160,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
     CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * 2, st));
     const int loop_stride_ints = (int)(sizeof(LoopRec2) / sizeof(int));
     plan_checks<<<(n_checks + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int*>(h->d_loops), loop_stride_ints, n_checks, member_dev, cand_dev,
-                                                        h->d_bucket_cap, NB, h->d_counts, work_dev, h->d_stats);
+                                                        h->d_bucket_cap, NB, h->d_counts, work_dev, work_stride, h->d_stats);
     CUDA_TRY(cudaGetLastError());
     int launches = 1;
     CUDA_TRY(cudaEventRecord(h->ev_k0, st));
@@ -159,26 +169,27 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         int lo_cap = b == 0 ? 0 : kBuckets2[b - 1].cap;
         if (lo_cap >= h->n - 1) break;                 // no window can be this long
         BatchArgs a{};
+        for (int c = 0; c < 6; ++c) { a.Du[c] = h->hs.Du[c]; a.Vu[c] = h->hs.Vu[c]; }
+        const bool uni = h->hs.uniform_iso && h->use_uniform;
         a.odom = h->d_odom; a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
         a.work = work_dev + (size_t)b * work_stride; a.n_work = h->d_counts + b;
         a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
         a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
-        a.noise_exit = h->noise_exit; a.max_tries = h->max_tries;
+        a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept;
         a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch;
-        size_t sm = smem_bytes(bk.nt, bk.mode, a.Lcap);
-        int per_sm = std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
+        a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap);
+        size_t sm = smem_bytes(bk.mode, a.Lcap);
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
         per_sm = std::min(per_sm, 2048 / bk.nt);
-        int grid = std::min(n_checks, h->n_sm * per_sm * 8);
+        int grid = std::min(n_checks, h->n_sm * per_sm);
+        grid = (int)std::min<size_t>(grid, h->scratch_doubles / a.scratch_stride);
         int rc = IPC_OK;
-        if (bk.mode == 2) {
-            grid = std::min(grid, h->scratch_grid);
-            rc = launch_se2<512, 2>(a, grid, st);
-        } else if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st);
-        else if (bk.nt == 32) rc = launch_se2<32, 0>(a, grid, st);
-        else if (bk.nt == 64) rc = launch_se2<64, 0>(a, grid, st);
-        else if (bk.nt == 128) rc = launch_se2<128, 0>(a, grid, st);
-        else rc = launch_se2<256, 0>(a, grid, st);
+        if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st, uni);
+        else if (bk.nt == 32) rc = launch_se2<32, 0>(a, grid, st, uni);
+        else if (bk.nt == 128) rc = launch_se2<128, 0>(a, grid, st, uni);
+        else if (bk.nt == 256) rc = launch_se2<256, 0>(a, grid, st, uni);
+        else rc = launch_se2<512, 0>(a, grid, st, uni);
         if (rc != IPC_OK) return rc;
         ++launches;
     }
@@ -233,10 +244,19 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     int caps[NB];
     for (int b = 0; b < NB; ++b) caps[b] = kBuckets2[b].cap;
     CUDA_TRY(cudaMemcpy(h->d_bucket_cap, caps, sizeof(caps), cudaMemcpyHostToDevice));
-    if (n_poses - 1 > kBuckets2[NB - 2].cap) {   // MODE 2 scratch
-        h->scratch_grid = h->n_sm * 2;
-        h->scratch_doubles = (size_t)h->scratch_grid * 6 * (((n_poses - 1 + 1) & ~1) + 2);
-        CUDA_TRY(cudaMalloc(&h->d_scratch, h->scratch_doubles * sizeof(double)));
+    {   // per-CTA scratch: every bucket launch fits grid * stride into it
+        size_t need = 0;
+        for (int b = 0; b < NB; ++b) {
+            int lo_cap = b == 0 ? 0 : kBuckets2[b - 1].cap;
+            if (lo_cap >= n_poses - 1) break;
+            int Lcap = (std::min(kBuckets2[b].cap, n_poses - 1) + 1) & ~1;
+            size_t sm = smem_bytes(kBuckets2[b].mode, Lcap);
+            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
+            per_sm = std::min(per_sm, 2048 / kBuckets2[b].nt);
+            need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kBuckets2[b].mode, Lcap));
+        }
+        h->scratch_doubles = need;
+        CUDA_TRY(cudaMalloc(&h->d_scratch, need * sizeof(double)));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&h->ev_k0));
@@ -258,7 +278,10 @@ void ipc_destroy(ipc_handle* h) {
 
 int ipc_set_option(ipc_handle* h, const char* name, double value) {
     if (!h || !name) return fail(IPC_ERR_ARG, "null argument");
-    if (!strcmp(name, "noise_exit")) { h->noise_exit = value != 0; return IPC_OK; }
+    if (!strcmp(name, "noise_exit")) { h->noise_eps = value == 1.0 ? 1e-13 : value; return IPC_OK; }   // 0 = off, 1 = default eps, else eps
+    if (!strcmp(name, "use_uniform")) { h->use_uniform = value != 0; return IPC_OK; }
+    if (!strcmp(name, "speculate")) { h->speculate = value != 0; return IPC_OK; }
+    if (!strcmp(name, "early_accept")) { h->early_accept = value != 0; return IPC_OK; }
     if (!strcmp(name, "max_tries")) { h->max_tries = (int)value; return IPC_OK; }
     return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
 }

@@ -86,9 +86,10 @@ void* orc_create(int dim, int n_poses, const double* odom_meas, const double* od
 }
 void orc_destroy(void* h) { delete static_cast<HandleBase*>(h); }
 
-void orc_set_noise_exit(void* hv, int on) {
+void orc_set_noise_exit(void* hv, double eps) {   // eps > 0 enables the retry shortcut with that threshold, 0 disables it
     auto* hb = static_cast<HandleBase*>(hv);
-    if (hb->dim == 2) static_cast<Handle<G2>*>(hb)->ipc.noise_exit = on != 0; else static_cast<Handle<G3>*>(hb)->ipc.noise_exit = on != 0;
+    if (hb->dim == 2) { auto& i = static_cast<Handle<G2>*>(hb)->ipc; i.noise_exit = eps > 0; i.noise_eps = eps; }
+    else { auto& i = static_cast<Handle<G3>*>(hb)->ipc; i.noise_exit = eps > 0; i.noise_eps = eps; }
 }
 
 int orc_agreement_check(void* hv, int from, int to, const double* meas, const double* info, orc_report* rep) {

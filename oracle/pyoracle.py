@@ -44,7 +44,7 @@ def lib():
         _LIB.orc_create.restype = C.c_void_p
         _LIB.orc_create.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Config)]
         _LIB.orc_destroy.argtypes = [C.c_void_p]
-        _LIB.orc_set_noise_exit.argtypes = [C.c_void_p, C.c_int]
+        _LIB.orc_set_noise_exit.argtypes = [C.c_void_p, C.c_double]
         _LIB.orc_agreement_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(Report)]
         _LIB.orc_add_edge.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _LIB.orc_remove_edge.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -70,7 +70,8 @@ def _f64(a):
 class OracleIPC:
     """IPC<EDGE,VERTEX> of the reference (include/ipc/consensus.hpp:5-33) on flat arrays."""
 
-    def __init__(self, graph, cfg: dict, noise_exit: bool = False):
+    def __init__(self, graph, cfg: dict, noise_exit=False):
+        """noise_exit: False / 0 = g2o's full retry semantics; True = shortcut with eps 1e-13; a float = that eps."""
         self.g = graph
         self.dim = graph.dim
         self.meas_w = 3 if self.dim == 2 else 7
@@ -78,7 +79,7 @@ class OracleIPC:
         om, oi = _f64(graph.odom_meas), _f64(graph.odom_info)
         self._h = lib().orc_create(self.dim, graph.n_poses, _p(om), _p(oi), C.byref(c))
         if noise_exit:
-            lib().orc_set_noise_exit(self._h, 1)
+            lib().orc_set_noise_exit(self._h, 1e-13 if noise_exit is True else float(noise_exit))
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -1,0 +1,48 @@
+// Host emulation of the CUDA check (TEST INFRASTRUCTURE): compiles ipc_b200/csrc/chain_se2.cuh with NT = 1 for the
+// CPU so the arithmetic and the Dogleg control flow of the kernel can be validated against the oracle on a box without
+// a GPU. Never part of the product library.
+#include <atomic>
+#include <thread>
+#include <vector>
+
+#include "../../ipc_b200/csrc/chain_se2.cuh"
+#include "../../ipc_b200/csrc/host_state.hpp"
+
+using namespace ipcb;
+
+extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
+                                const int* lto, const double* lmeas, const double* linfo, int n_checks, const int* member, const int* cand,
+                                double fast_th, double slow_th, int fast_iter, int slow_iter, double noise_eps, int speculate, int early_accept,
+                                int want_info, int use_uni, int n_threads, unsigned char* verdict, ipc_check_info* info, int* sweeps) {
+    HostState hs; std::string err;
+    if (!hs.init(2, n_poses, odom_meas, odom_info, s_factor, err)) return -1;
+    const int n_pad = (n_poses + 3) & ~1;
+    std::vector<double> soa; hs.build_odom_soa(n_pad, soa);
+    std::vector<LoopRec2> recs(n_loops);
+    for (int i = 0; i < n_loops; ++i) { recs[i].from = lfrom[i]; recs[i].to = lto[i]; HostState::se2_edge_record(lmeas + 3 * i, linfo + 9 * i, 1.0, recs[i].meas, recs[i].D); }
+    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept};
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        const int capv = n_poses + 2;
+        std::vector<double> buf((size_t)(CHAIN_STATE_ARRAYS + CHAIN_SCRATCH_ARRAYS) * capv + CHAIN_SMALL_DOUBLES, 0.0);
+        ChainMem M; double* p = buf.data();
+        chain_mem_small(M, p); p += CHAIN_SMALL_DOUBLES;
+        M.X = p; M.Y = p + capv; M.TH = p + 2 * capv; for (int m = 0; m < NPRE; ++m) M.P[m] = p + (3 + m) * (size_t)capv; p += (size_t)CHAIN_STATE_ARRAYS * capv;
+        M.BX = p; M.BY = p + capv; M.BT = p + 2 * capv; for (int q = 0; q < 3; ++q) { M.GB[q] = p + (3 + q) * (size_t)capv; M.GH[q] = p + (6 + q) * (size_t)capv; }
+        for (;;) {
+            int c = next.fetch_add(1);
+            if (c >= n_checks) break;
+            CheckResult r;
+            if (hs.uniform_iso && use_uni) run_check<1, true>(M, soa.data(), (size_t)n_pad, hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+            else run_check<1, false>(M, soa.data(), (size_t)n_pad, hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+            verdict[c] = (unsigned char)r.verdict;
+            if (info) { info[c].max_chi2 = r.max_chi2; info[c].cand_chi2 = r.cand_chi2; info[c].sum_chi2 = r.sum_chi2; info[c].iterations = r.iterations;
+                        info[c].evals = r.evals; info[c].window_len = r.window_len; info[c].n_loops = r.n_loops; }
+            if (sweeps) sweeps[c] = r.n_sweeps;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < (n_threads < 1 ? 1 : n_threads); ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+    return 0;
+}
