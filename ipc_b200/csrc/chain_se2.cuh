@@ -11,9 +11,10 @@
 // interval of edges, so the exact GN step is
 //   Xi_j = Pm_j - PM_j z_rho(j) - C_rho(j),     PM_j = sum_{k<j} Q_k V_k Q_k^T,  Pm_j = -sum_{k<j} Q_k d_k
 // where the per-region "forces" z come from a 3x3 (K = 1) or 6x6 (K = 2) capacitance solve on interval sums of PM, Pm.
-// One sweep over the window therefore (i) applies the step of the previous linearisation to every pose,
-// (ii) re-linearises every edge at the new pose (one sincos per pose), (iii) accumulates chi2 / max chi2 of the trial
-// state and (iv) produces the prefix sums PM, Pm of the NEW linearisation, i.e. everything the next step needs.
+// One sweep over the window therefore (i) re-derives the prefix sums of the OLD linearisation on the fly (cheap: the
+// cos / sin of every pose are part of the state), (ii) applies the step to every pose, (iii) re-linearises every edge at the
+// new pose (one sincos per pose), (iv) accumulates chi2 / max chi2 of the trial state and (v) produces the interval sums
+// of PM, Pm of the NEW linearisation, i.e. everything the next capacitance solve needs. State: 5 doubles per vertex.
 // The predicted gain of a GN step is chi2 - model(h_gn) with model = sum_r z_r^T P_r z_r + loop terms (O(1)).
 // Trust-region-limited steps (steepest-descent / dog-leg blends) need the gradient in g2o's vertex coordinates:
 // two extra sweeps (b, b^T H b) into a per-CTA scratch, then the same trial sweep reading h = c1 b + c2 h_gn.
@@ -119,95 +120,19 @@ IPC_HD void inv_sym3(const double* D, double* V) {
     V[4] = (D[1] * D[2] - D[0] * D[4]) * id;
     V[5] = (D[0] * D[3] - D[1] * D[1]) * id;
 }
-// dense n x n solve with partial pivoting (n <= 6), A row-major, b overwritten by the solution
-template <int N> IPC_HD void solve_small(double* A, double* b) {
-#pragma unroll
-    for (int c = 0; c < N; ++c) {
-        int p = c; double best = fabs(A[c * N + c]);
-#pragma unroll
-        for (int r = c + 1; r < N; ++r) { double v = fabs(A[r * N + c]); if (v > best) { best = v; p = r; } }
-        if (p != c) {
-#pragma unroll
-            for (int r = 0; r < N; ++r) if (r == p) {
-#pragma unroll
-                for (int k = 0; k < N; ++k) { double t = A[c * N + k]; A[c * N + k] = A[r * N + k]; A[r * N + k] = t; }
-                double t = b[c]; b[c] = b[r]; b[r] = t;
-            }
-        }
-        double inv = 1.0 / A[c * N + c];
-#pragma unroll
-        for (int r = c + 1; r < N; ++r) {
-            double f = A[r * N + c] * inv;
-#pragma unroll
-            for (int k = c + 1; k < N; ++k) A[r * N + k] -= f * A[c * N + k];
-            b[r] -= f * b[c];
-        }
-    }
-#pragma unroll
-    for (int c = N - 1; c >= 0; --c) {
-        double s = b[c];
-#pragma unroll
-        for (int k = c + 1; k < N; ++k) s -= A[c * N + k] * b[k];
-        b[c] = s / A[c * N + c];
-    }
-}
 IPC_HD void sym3_mul(const double* S, const double* v, double* o) {
     o[0] = S[0] * v[0] + S[1] * v[1] + S[2] * v[2];
     o[1] = S[1] * v[0] + S[3] * v[1] + S[4] * v[2];
     o[2] = S[2] * v[0] + S[4] * v[1] + S[5] * v[2];
 }
-IPC_HD void sym3_sym3(const double* P, const double* L, double* A) {   // A (full) = P (sym) * L (sym)
-    const double Pf[9] = {P[0], P[1], P[2], P[1], P[3], P[4], P[2], P[4], P[5]};
-    const double Lf[9] = {L[0], L[1], L[2], L[1], L[3], L[4], L[2], L[4], L[5]};
+// C (full 3x3, row-major) = A (sym) * B (sym)
+IPC_HD void sym3_sym3(const double* A, const double* B, double* C) {
+    const double Af[9] = {A[0], A[1], A[2], A[1], A[3], A[4], A[2], A[4], A[5]};
+    const double Bf[9] = {B[0], B[1], B[2], B[1], B[3], B[4], B[2], B[4], B[5]};
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) A[r * 3 + c] = Pf[r * 3] * Lf[c] + Pf[r * 3 + 1] * Lf[3 + c] + Pf[r * 3 + 2] * Lf[6 + c];
-}
-
-// one loop edge at the current state
-struct LoopLin2 {
-    int jf, jt;          // local vertex indices of from / to
-    int a, b;            // local edge interval [a, b)
-    Lin2 e;
-    double G[9];         // d(residual) / d(total twist over the interval)
-    double g[3];         // G^T D d
-    double Lam[6];       // G^T D G (sym)
-};
-IPC_HD void loop_lin2(const LoopRec2& L, int lo, const P2& pf, const P2& pt, LoopLin2& o) {
-    o.jf = L.from - lo; o.jt = L.to - lo;
-    const bool hi_is_to = L.to > L.from;
-    o.a = o.jf < o.jt ? o.jf : o.jt; o.b = o.jf < o.jt ? o.jt : o.jf;
-    double s, c; ipc_sincos(pf.t, &s, &c);
-    lin2cs(c, s, pf, pt, L.meas[0], L.meas[1], L.meas[2], L.D, o.e);
-    const Lin2& e = o.e;
-    double* G = o.G;
-    if (hi_is_to) {   // G = [R_f^T, R_f^T S t_t; 0 1],  S t = (-y, x)
-        G[0] = e.c; G[1] = e.s; G[2] = e.c * (-pt.y) + e.s * pt.x;
-        G[3] = -e.s; G[4] = e.c; G[5] = -e.s * (-pt.y) + e.c * pt.x;
-        G[6] = 0; G[7] = 0; G[8] = 1;
-    } else {          // G = [-R_f^T, -R_f^T S t_f + (ry, -rx)^T; 0 -1]
-        G[0] = -e.c; G[1] = -e.s; G[2] = -(e.c * (-pf.y) + e.s * pf.x) + e.ry;
-        G[3] = e.s; G[4] = -e.c; G[5] = -(-e.s * (-pf.y) + e.c * pf.x) - e.rx;
-        G[6] = 0; G[7] = 0; G[8] = -1;
-    }
-    o.g[0] = G[0] * e.w0 + G[3] * e.w1 + G[6] * e.w2;
-    o.g[1] = G[1] * e.w0 + G[4] * e.w1 + G[7] * e.w2;
-    o.g[2] = G[2] * e.w0 + G[5] * e.w1 + G[8] * e.w2;
-    double DG[9];
-    const double* D = L.D;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        DG[0 + q] = D[0] * G[q] + D[1] * G[3 + q] + D[2] * G[6 + q];
-        DG[3 + q] = D[1] * G[q] + D[3] * G[3 + q] + D[4] * G[6 + q];
-        DG[6 + q] = D[2] * G[q] + D[4] * G[3 + q] + D[5] * G[6 + q];
-    }
-    o.Lam[0] = G[0] * DG[0] + G[3] * DG[3] + G[6] * DG[6];
-    o.Lam[1] = G[0] * DG[1] + G[3] * DG[4] + G[6] * DG[7];
-    o.Lam[2] = G[0] * DG[2] + G[3] * DG[5] + G[6] * DG[8];
-    o.Lam[3] = G[1] * DG[1] + G[4] * DG[4] + G[7] * DG[7];
-    o.Lam[4] = G[1] * DG[2] + G[4] * DG[5] + G[7] * DG[8];
-    o.Lam[5] = G[2] * DG[2] + G[5] * DG[5] + G[8] * DG[8];
+        for (int c = 0; c < 3; ++c) C[r * 3 + c] = Af[r * 3] * Bf[c] + Af[r * 3 + 1] * Bf[3 + c] + Af[r * 3 + 2] * Bf[6 + c];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -368,9 +293,8 @@ struct UniBlock {            // uniform per-check data (shared memory): read by 
 constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
 
 struct ChainMem {
-    // per-vertex state, index j in [0, L]. Shared memory (MODE 0) or per-CTA global scratch (MODE 1).
-    double *X, *Y, *TH;
-    double* P[NPRE];         // thread-LOCAL inclusive prefix of (PM, Pm) at vertex j (edges k0 .. j-1 of the owner thread)
+    // per-vertex state, index j in [0, L]: pose and cos / sin of its heading. Shared memory (MODE 0) or per-CTA global scratch (MODE 1).
+    double *X, *Y, *TH, *CS, *SN;
     // per-CTA global scratch (L2 resident)
     double *BX, *BY, *BT;    // pose backup: state before the last trial sweep
     double* GB[3];           // gradient b_j in g2o vertex coordinates (steepest-descent sweeps)
@@ -379,9 +303,9 @@ struct ChainMem {
     double* spec;            // special-vertex table, 2 buffers of NSPEC * SPECW
     UniBlock* U;
 };
-constexpr int RED_DOUBLES = 32 * (NPRE + 3);     // NW <= 32 warps x (NPRE + NS + 1), NS = 2
+constexpr int RED_DOUBLES = 16 * (NPRE + 3);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 2
 constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
-constexpr int CHAIN_STATE_ARRAYS = 3 + NPRE;     // per-vertex doubles in shared memory (MODE 0)
+constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
 constexpr int CHAIN_SCRATCH_ARRAYS = 9;          // per-vertex doubles in the global scratch (backup, b, h_gn)
 
 IPC_HD void chain_mem_small(ChainMem& M, double* small) {
@@ -405,7 +329,7 @@ struct OdomView {            // odometry records of the window, SoA in HBM/L2: z
 struct ThreadState {         // registers carried from sweep to sweep
     int k0, k1;              // owned edges [k0, k1); owned vertices k0+1 .. k1
     P2 pa; double ca, sa;    // pose (+ cos / sin) of vertex k0 at the current state
-    double base[NPRE];       // prefix (PM, Pm) at vertex k0 for the linearisation held in M.P
+    double base[NPRE];       // prefix (PM, Pm) at vertex k0 for the linearisation of the current state
 };
 
 // twist Xi_j = Pm_j - PM_j z_r - C_r of the GN step at vertex j (region r by position)
@@ -424,7 +348,7 @@ IPC_HD void gn_step_at(const StepSpec* sp, int j, const double* pre /* full pref
     h[2] = X[2];
 }
 
-// contribution of one linearised odometry edge to the prefix sums: M = Q V Q^T (6), m = -Q d (3); Q = [c -s yb; s c -xb; 0 0 1]
+// contribution of one linearised edge to the prefix sums: M = Q V Q^T (6), m = -Q d (3); Q = [c -s yb; s c -xb; 0 0 1]
 IPC_HD void edge_prefix_terms(const Lin2& e, const double* V, double xb, double yb, double* t) {
     const double q02 = yb, q12 = -xb;
     const double r00 = e.c * V[0] - e.s * V[1] + q02 * V[2], r01 = e.c * V[1] - e.s * V[3] + q02 * V[4], r02 = e.c * V[2] - e.s * V[4] + q02 * V[5];
@@ -439,22 +363,52 @@ IPC_HD void edge_prefix_terms(const Lin2& e, const double* V, double xb, double 
     t[7] = -(e.s * e.d0 + e.c * e.d1 + q12 * e.d2);
     t[8] = -e.d2;
 }
+// same for V = diag(va, va, vc) (uniform isotropic information): Q V Q^T no longer depends on the heading
+IPC_HD void edge_prefix_terms_iso(const Lin2& e, double va, double vc, double xb, double yb, double* t) {
+    const double vy = vc * yb, vx = vc * xb;
+    t[0] = fma(vy, yb, va);
+    t[1] = -vy * xb;
+    t[2] = vy;
+    t[3] = fma(vx, xb, va);
+    t[4] = -vx;
+    t[5] = vc;
+    t[6] = -(e.c * e.d0 - e.s * e.d1 + yb * e.d2);
+    t[7] = -(e.s * e.d0 + e.c * e.d1 - xb * e.d2);
+    t[8] = -e.d2;
+}
+template <bool UNI> IPC_HD void odom_terms(const OdomView& O, int k, double c, double s, const P2& a, const P2& b, Lin2& e, double* t) {
+    if (UNI) {
+        lin2cs(c, s, a, b, O.z(0, k), O.z(1, k), O.z(2, k), O.Du, e);
+        edge_prefix_terms_iso(e, O.Vu[0], O.Vu[5], b.x, b.y, t);
+    } else {
+        double D[6], V[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) D[q] = O.z(3 + q, k);
+        inv_sym3(D, V);
+        lin2cs(c, s, a, b, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+        edge_prefix_terms(e, V, b.x, b.y, t);
+    }
+}
 
 struct SweepOut { double chi, mx, hh; };   // odometry chi2 sum / max at the new state, |h|^2 of the applied step
 
-// The sweep: apply a step (none / GN of M.U->sol / blend c1 b + c2 h_gn from the scratch), re-linearise, new local
-// prefixes, chi2, and publish the special vertices. Writes the pose backup when a step is applied. Two block barriers.
-template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts, SweepOut& out,
-                                              int& buf, const int* spec_v) {
+// The sweep: apply a step (none / GN of M.U->sol / blend c1 b + c2 h_gn from the scratch), re-linearise, chi2, interval
+// sums of the new linearisation at the special vertices. The GN step at vertex j needs the prefix of the OLD linearisation at
+// j: it is rebuilt on the fly from the old poses (no sincos: cos / sin are stored). Writes the pose backup when a step is
+// applied. Two block barriers.
+template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
+                                                   SweepOut& out, int& buf, const int* spec_v) {
     const int k0 = ts.k0, k1 = ts.k1;
     const StepSpec* sp = &M.U->sol;
-    double b0[NPRE];
+    double* spec = M.spec + (size_t)buf * NSPEC * SPECW;
+    double pre[NPRE];        // running prefix of the OLD linearisation (GN mode)
 #pragma unroll
-    for (int m = 0; m < NPRE; ++m) b0[m] = ts.base[m];
-    P2 na = ts.pa; double nca = ts.ca, nsa = ts.sa;
-    if (mode != STEP_NONE && k0 > 0 && k0 < k1) {   // boundary vertex k0: same arithmetic as its owner => identical bits
+    for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
+    P2 oa = ts.pa; double oca = ts.ca, osa = ts.sa;      // old from-vertex
+    P2 na = oa; double nca = oca, nsa = osa;             // new from-vertex
+    if (mode != STEP_NONE && k0 > 0 && k0 < k1) {        // boundary vertex k0: same arithmetic as its owner => identical bits
         double h[3];
-        if (mode == STEP_GN) gn_step_at(sp, k0, b0, na.x, na.y, h);
+        if (mode == STEP_GN) gn_step_at(sp, k0, pre, oa.x, oa.y, h);
         else {
 #pragma unroll
             for (int q = 0; q < 3; ++q) h[q] = c1 * M.GB[q][k0] + c2 * M.GH[q][k0];
@@ -463,70 +417,79 @@ template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const Odom
         ipc_sincos(na.t, &nsa, &nca);
     }
     ts.pa = na; ts.ca = nca; ts.sa = nsa;
-    double run[NPRE];
+    double run[NPRE];        // local prefix of the NEW linearisation
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) run[m] = 0;
     double chi = 0, mx = 0, hh = 0;
     for (int k = k0; k < k1; ++k) {
         const int j = k + 1;
-        P2 nb{M.X[j], M.Y[j], M.TH[j]};
+        const P2 ob{M.X[j], M.Y[j], M.TH[j]};
+        P2 nb = ob;
+        double ocb = 0, osb = 0, ncb, nsb;
+        if (j < k1) { ocb = M.CS[j]; osb = M.SN[j]; }
+        ncb = ocb; nsb = osb;
         if (mode != STEP_NONE) {
             double h[3];
             if (mode == STEP_GN) {
-                double pre[NPRE];
+                Lin2 eo; double to[NPRE];
+                odom_terms<UNI>(O, k, oca, osa, oa, ob, eo, to);
 #pragma unroll
-                for (int m = 0; m < NPRE; ++m) pre[m] = b0[m] + M.P[m][j];
-                gn_step_at(sp, j, pre, nb.x, nb.y, h);
+                for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
+                gn_step_at(sp, j, pre, ob.x, ob.y, h);
             } else {
 #pragma unroll
                 for (int q = 0; q < 3; ++q) h[q] = c1 * M.GB[q][j] + c2 * M.GH[q][j];
             }
-            M.BX[j] = nb.x; M.BY[j] = nb.y; M.BT[j] = nb.t;
+            M.BX[j] = ob.x; M.BY[j] = ob.y; M.BT[j] = ob.t;
             nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
             hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
             M.X[j] = nb.x; M.Y[j] = nb.y; M.TH[j] = nb.t;
+            if (j < k1) { ipc_sincos(nb.t, &nsb, &ncb); M.CS[j] = ncb; M.SN[j] = nsb; }
         }
-        double D[6], V[6];
-        if (UNI) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) { D[c] = O.Du[c]; V[c] = O.Vu[c]; }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) D[c] = O.z(3 + c, k);
-            inv_sym3(D, V);
-        }
-        Lin2 e; lin2cs(nca, nsa, na, nb, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+        Lin2 e; double t[NPRE];
+        odom_terms<UNI>(O, k, nca, nsa, na, nb, e, t);
         chi += e.chi; mx = fmax(mx, e.chi);
-        double t[NPRE]; edge_prefix_terms(e, V, nb.x, nb.y, t);
 #pragma unroll
-        for (int m = 0; m < NPRE; ++m) { run[m] += t[m]; M.P[m][j] = run[m]; }
-        na = nb;
-        if (j < k1) ipc_sincos(nb.t, &nsa, &nca);
+        for (int m = 0; m < NPRE; ++m) run[m] += t[m];
+#pragma unroll
+        for (int q = 1; q < NSPEC; ++q) {
+            if (j == spec_v[q]) {        // local part now, the thread base is added after the scan
+                double* o = spec + q * SPECW;
+#pragma unroll
+                for (int m = 0; m < NPRE; ++m) o[m] = run[m];
+                o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+            }
+        }
+        oa = ob; oca = ocb; osa = osb;
+        na = nb; nca = ncb; nsa = nsb;
     }
     double s[2] = {chi, hh};
     ScanSumMax<NT, 2>::run(run, s, mx, M.red + (size_t)buf * RED_DOUBLES);
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) ts.base[m] = run[m];
     out.chi = s[0]; out.hh = s[1]; out.mx = mx;
-    double* spec = M.spec + (size_t)buf * NSPEC * SPECW;
 #pragma unroll
     for (int q = 1; q < NSPEC; ++q) {
         const int v = spec_v[q];
         if (v > k0 && v <= k1) {
             double* o = spec + q * SPECW;
 #pragma unroll
-            for (int m = 0; m < NPRE; ++m) o[m] = ts.base[m] + M.P[m][v];
-            o[NPRE] = M.X[v]; o[NPRE + 1] = M.Y[v]; o[NPRE + 2] = M.TH[v];
+            for (int m = 0; m < NPRE; ++m) o[m] += run[m];
         }
     }
     bsync<NT>();
     buf ^= 1;
 }
 
-// undo the last applied sweep: poses from the backup, boundary registers re-read. The prefix arrays / bases are NOT restored:
-// every caller re-linearises (GN rejection) or only runs blend sweeps (which do not read them) until a step is accepted.
+// undo the last applied sweep: poses from the backup, cos / sin recomputed, boundary registers re-read. Thread bases are NOT
+// restored: every caller re-linearises (GN rejection) or only runs blend sweeps (which do not read them) until a step is kept.
 template <int NT> IPC_HD_COLD void rollback(const ChainMem& M, ThreadState& ts) {
-    for (int k = ts.k0; k < ts.k1; ++k) { const int j = k + 1; M.X[j] = M.BX[j]; M.Y[j] = M.BY[j]; M.TH[j] = M.BT[j]; }
+    for (int k = ts.k0; k < ts.k1; ++k) {
+        const int j = k + 1;
+        const double t = M.BT[j];
+        M.X[j] = M.BX[j]; M.Y[j] = M.BY[j]; M.TH[j] = t;
+        if (j < ts.k1) { double s, c; ipc_sincos(t, &s, &c); M.CS[j] = c; M.SN[j] = s; }
+    }
     bsync<NT>();
     if (ts.k0 < ts.k1) {
         ts.pa.x = M.X[ts.k0]; ts.pa.y = M.Y[ts.k0]; ts.pa.t = M.TH[ts.k0];
@@ -559,83 +522,83 @@ IPC_HD void spec_load(const double* spec, const CheckGeom& g, SpecVals& sv) {
 }
 IPC_HD P2 sel_pose(bool c, const P2& a, const P2& b) { P2 r; r.x = c ? a.x : b.x; r.y = c ? a.y : b.y; r.t = c ? a.t : b.t; return r; }
 
-// loop edges linearised at the published state
-IPC_HD void loops_eval(const SpecVals& sv, const CheckGeom& g, const LoopRec2& Lc, const LoopRec2& Lm, LoopLin2& lc, LoopLin2& lm) {
+// A loop edge in twist coordinates is one more edge of the cycle: with Q_l = [c_f -s_f y_t; s_f c_f -x_t; 0 0 1] (from-vertex
+// heading, to-vertex position) its terms W_l = Q_l V_l Q_l^T and Q_l d_l are what edge_prefix_terms() computes for an
+// odometry edge, and d(residual)/d(interval twist) = sigma Q_l^-1 with sigma = +1 when `to` is the later vertex.
+struct LoopNow { Lin2 e; double t[NPRE]; double sigma; };
+IPC_HD void loop_now(const LoopRec2& L, const P2& pf, const P2& pt, LoopNow& o) {
+    double s, c; ipc_sincos(pf.t, &s, &c);
+    lin2cs(c, s, pf, pt, L.meas[0], L.meas[1], L.meas[2], L.D, o.e);
+    edge_prefix_terms(o.e, L.V, pt.x, pt.y, o.t);
+    o.sigma = L.to > L.from ? 1.0 : -1.0;
+}
+IPC_HD void loops_eval(const SpecVals& sv, const CheckGeom& g, const LoopRec2& Lc, const LoopRec2& Lm, LoopNow& lc, LoopNow& lm) {
     const P2 org{0, 0, 0};
     {
         const P2 pa = sel_pose(g.c_a_is_rs, sv.p1, org), pb = sel_pose(g.c_b_is_L, sv.p3, sv.p2);
         const bool to_hi = Lc.to > Lc.from;
-        loop_lin2(Lc, g.lo, sel_pose(to_hi, pa, pb), sel_pose(to_hi, pb, pa), lc);
+        loop_now(Lc, sel_pose(to_hi, pa, pb), sel_pose(to_hi, pb, pa), lc);
     }
     if (g.K == 2) {
         const P2 pa = sel_pose(g.m_a_is_rs, sv.p1, org), pb = sel_pose(g.m_b_is_L, sv.p3, sv.p2);
         const bool to_hi = Lm.to > Lm.from;
-        loop_lin2(Lm, g.lo, sel_pose(to_hi, pa, pb), sel_pose(to_hi, pb, pa), lm);
+        loop_now(Lm, sel_pose(to_hi, pa, pb), sel_pose(to_hi, pb, pa), lm);
     }
 }
 
-// GN solution of the published linearisation: capacitance solve on the interval sums, forces per region, model value
-IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopLin2& lc, const LoopLin2& lm, const double* Dc, const double* Dm, StepSpec* sp) {
+// GN solution of the published linearisation. Unknowns: the force z_l of every loop on its interval. Stationarity gives the
+// SPD system  (P_ll' + delta_ll' W_l) z_l' = q_l + sigma_l Q_l d_l  with P_ll' = sum of PM over the common interval and
+// q_l = sum of Pm over the interval of l: 3x3 for K = 1, 6x6 for K = 2 (solved by a 3x3 Schur complement).
+// After the step the linearised residual of an edge under force z is -V Q^T z, so
+//   model = sum_r z_r^T P_r z_r + sum_l z_l^T W_l z_l.
+IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopNow& lc, const LoopNow& lm, StepSpec* sp) {
     // region sums: region 0 = [0, rs), region 1 = [rs, re), region 2 = [re, L)
     double acc[3][NPRE];
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) { acc[0][m] = sv.pre1[m]; acc[1][m] = sv.pre2[m] - sv.pre1[m]; acc[2][m] = sv.pre3[m] - sv.pre2[m]; }
     double zc[3], zm[3] = {0, 0, 0};
     if (g.K == 1) {
-        double Amat[9], rhs[3], t[3];
-        const double* P = acc[1];
-        sym3_sym3(P, lc.Lam, Amat);
-        Amat[0] += 1; Amat[4] += 1; Amat[8] += 1;
-        sym3_mul(P, lc.g, t);
-        rhs[0] = acc[1][6] - t[0]; rhs[1] = acc[1][7] - t[1]; rhs[2] = acc[1][8] - t[2];
-        solve_small<3>(Amat, rhs);
-        sym3_mul(lc.Lam, rhs, t);
-        zc[0] = lc.g[0] + t[0]; zc[1] = lc.g[1] + t[1]; zc[2] = lc.g[2] + t[2];
+        double S[6], Si[6], r[3];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) S[q] = acc[1][q] + lc.t[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) r[q] = acc[1][6 + q] - lc.sigma * lc.t[6 + q];
+        inv_sym3(S, Si);
+        sym3_mul(Si, r, zc);
     } else {
-        double Pcc[6], Pmm[6], Pcm[6], qc[3], qm[3];
+        double A[6], B[6], Cm[6], rc[3], rm[3];
 #pragma unroll
         for (int q = 0; q < 6; ++q) {
-            Pcm[q] = acc[1][q];
-            Pcc[q] = acc[1][q] + (g.first_is_c ? acc[0][q] : 0.0) + (g.last_is_c ? acc[2][q] : 0.0);
-            Pmm[q] = acc[1][q] + (g.first_is_c ? 0.0 : acc[0][q]) + (g.last_is_c ? 0.0 : acc[2][q]);
+            B[q] = acc[1][q];
+            A[q] = acc[1][q] + (g.first_is_c ? acc[0][q] : 0.0) + (g.last_is_c ? acc[2][q] : 0.0) + lc.t[q];
+            Cm[q] = acc[1][q] + (g.first_is_c ? 0.0 : acc[0][q]) + (g.last_is_c ? 0.0 : acc[2][q]) + lm.t[q];
         }
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            qc[q] = acc[1][6 + q] + (g.first_is_c ? acc[0][6 + q] : 0.0) + (g.last_is_c ? acc[2][6 + q] : 0.0);
-            qm[q] = acc[1][6 + q] + (g.first_is_c ? 0.0 : acc[0][6 + q]) + (g.last_is_c ? 0.0 : acc[2][6 + q]);
+            rc[q] = acc[1][6 + q] + (g.first_is_c ? acc[0][6 + q] : 0.0) + (g.last_is_c ? acc[2][6 + q] : 0.0) - lc.sigma * lc.t[6 + q];
+            rm[q] = acc[1][6 + q] + (g.first_is_c ? 0.0 : acc[0][6 + q]) + (g.last_is_c ? 0.0 : acc[2][6 + q]) - lm.sigma * lm.t[6 + q];
         }
-        double Amat[36], rhs[6], B[9], t[3], t2[3];
-        sym3_sym3(Pcc, lc.Lam, B);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Amat[r * 6 + c] = B[r * 3 + c] + (r == c ? 1.0 : 0.0);
-        sym3_sym3(Pcm, lm.Lam, B);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Amat[r * 6 + 3 + c] = B[r * 3 + c];
-        sym3_sym3(Pcm, lc.Lam, B);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Amat[(3 + r) * 6 + c] = B[r * 3 + c];
-        sym3_sym3(Pmm, lm.Lam, B);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) Amat[(3 + r) * 6 + 3 + c] = B[r * 3 + c] + (r == c ? 1.0 : 0.0);
-        sym3_mul(Pcc, lc.g, t); sym3_mul(Pcm, lm.g, t2);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) rhs[q] = qc[q] - t[q] - t2[q];
-        sym3_mul(Pcm, lc.g, t); sym3_mul(Pmm, lm.g, t2);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) rhs[3 + q] = qm[q] - t[q] - t2[q];
-        solve_small<6>(Amat, rhs);
-        sym3_mul(lc.Lam, rhs, t);
-        sym3_mul(lm.Lam, rhs + 3, t2);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) { zc[q] = lc.g[q] + t[q]; zm[q] = lm.g[q] + t2[q]; }
+        // [A B; B Cm] [zc; zm] = [rc; rm]:  Sch = Cm - B A^-1 B,  zm = Sch^-1 (rm - B A^-1 rc),  zc = A^-1 (rc - B zm)
+        double Ai[6], AiB[9], t[3], u[3];
+        inv_sym3(A, Ai);
+        sym3_sym3(Ai, B, AiB);                                   // A^-1 B (full)
+        double Sch[6];
+        // B (A^-1 B): symmetric, upper triangle only
+        Sch[0] = Cm[0] - (B[0] * AiB[0] + B[1] * AiB[3] + B[2] * AiB[6]);
+        Sch[1] = Cm[1] - (B[0] * AiB[1] + B[1] * AiB[4] + B[2] * AiB[7]);
+        Sch[2] = Cm[2] - (B[0] * AiB[2] + B[1] * AiB[5] + B[2] * AiB[8]);
+        Sch[3] = Cm[3] - (B[1] * AiB[1] + B[3] * AiB[4] + B[4] * AiB[7]);
+        Sch[4] = Cm[4] - (B[1] * AiB[2] + B[3] * AiB[5] + B[4] * AiB[8]);
+        Sch[5] = Cm[5] - (B[2] * AiB[2] + B[4] * AiB[5] + B[5] * AiB[8]);
+        sym3_mul(Ai, rc, t);                                     // A^-1 rc
+        sym3_mul(B, t, u);
+        double rs2[3] = {rm[0] - u[0], rm[1] - u[1], rm[2] - u[2]};
+        double Schi[6];
+        inv_sym3(Sch, Schi);
+        sym3_mul(Schi, rs2, zm);
+        sym3_mul(B, zm, u);
+        double rc2[3] = {rc[0] - u[0], rc[1] - u[1], rc[2] - u[2]};
+        sym3_mul(Ai, rc2, zc);
     }
     sp->rs = g.rs; sp->re = g.re;
     double z[3][3], C[3][3];
@@ -664,45 +627,23 @@ IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopLin2& lc,
     for (int r = 0; r < 3; ++r)
 #pragma unroll
         for (int q = 0; q < 3; ++q) { sp->z[r][q] = z[r][q]; sp->C[r][q] = C[r][q]; }
-    // model value after the GN step: odometry edges sum_r z_r^T P_r z_r, loop edges (d + G dXi)^T D (d + G dXi)
-    double model = 0;
+    double model = quad3(lc.t, zc[0], zc[1], zc[2]);
+    if (g.K == 2) model += quad3(lm.t, zm[0], zm[1], zm[2]);
 #pragma unroll
     for (int r = 0; r < 3; ++r) model += quad3(acc[r], z[r][0], z[r][1], z[r][2]);
-    double X1[3], X2[3], X3[3];
-    twist_at(sp, g.rs, sv.pre1, X1); twist_at(sp, g.re, sv.pre2, X2); twist_at(sp, g.L, sv.pre3, X3);
-    {
-        double dX[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) dX[q] = (g.c_b_is_L ? X3[q] : X2[q]) - (g.c_a_is_rs ? X1[q] : 0.0);
-        const double* G = lc.G;
-        const double n0 = lc.e.d0 + G[0] * dX[0] + G[1] * dX[1] + G[2] * dX[2];
-        const double n1 = lc.e.d1 + G[3] * dX[0] + G[4] * dX[1] + G[5] * dX[2];
-        const double n2 = lc.e.d2 + G[6] * dX[0] + G[7] * dX[1] + G[8] * dX[2];
-        model += quad3(Dc, n0, n1, n2);
-    }
-    if (g.K == 2) {
-        double dX[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) dX[q] = (g.m_b_is_L ? X3[q] : X2[q]) - (g.m_a_is_rs ? X1[q] : 0.0);
-        const double* G = lm.G;
-        const double n0 = lm.e.d0 + G[0] * dX[0] + G[1] * dX[1] + G[2] * dX[2];
-        const double n1 = lm.e.d1 + G[3] * dX[0] + G[4] * dX[1] + G[5] * dX[2];
-        const double n2 = lm.e.d2 + G[6] * dX[0] + G[7] * dX[1] + G[8] * dX[2];
-        model += quad3(Dm, n0, n1, n2);
-    }
     sp->model = model;
 }
 
 // After a sweep: thread 0 evaluates the loop edges at the published state and, if the trial is going to be kept
 // (rho > 0, or `force`), solves the new linearisation into M.U->sol. One barrier; every thread gets the loop chi2.
 IPC_HD_COLD void eval_and_solve_t0(const ChainMem& M, const CheckGeom& g, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
-    SpecVals sv; LoopLin2 lc, lm;
+    SpecVals sv; LoopNow lc, lm;
     spec_load(M.spec + (size_t)(buf ^ 1) * NSPEC * SPECW, g, sv);
     loops_eval(sv, g, M.U->Lc, M.U->Lm, lc, lm);
     const double c = lc.e.chi, m = g.K == 2 ? lm.e.chi : 0.0;
     if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
     const double rho = (cur_chi - (odom_chi + c + m)) / linearGain;
-    if (force || rho > 0) gn_solve(sv, g, lc, lm, M.U->Lc.D, M.U->Lm.D, &M.U->sol);
+    if (force || rho > 0) gn_solve(sv, g, lc, lm, &M.U->sol);
     M.U->n_c = c; M.U->n_m = m;
 }
 template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, const CheckGeom& g, int buf, double odom_chi, double cur_chi, double linearGain,
@@ -713,16 +654,24 @@ template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, const CheckGeom&
 }
 
 // |h_gn|^2 of the current linearisation without applying it
-template <int NT> IPC_HD_COLD double gn_norm_sq(const ChainMem& M, const ThreadState& ts) {
+template <int NT, bool UNI> IPC_HD_COLD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
     double v[1] = {0};
     const StepSpec* sp = &M.U->sol;
+    double pre[NPRE];
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
+    P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
     for (int k = ts.k0; k < ts.k1; ++k) {
         const int j = k + 1;
-        double pre[NPRE], h[3];
+        const P2 pb{M.X[j], M.Y[j], M.TH[j]};
+        Lin2 e; double t[NPRE], h[3];
+        odom_terms<UNI>(O, k, ca, sa, pa, pb, e, t);
 #pragma unroll
-        for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m] + M.P[m][j];
-        gn_step_at(sp, j, pre, M.X[j], M.Y[j], h);
+        for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
+        gn_step_at(sp, j, pre, pb.x, pb.y, h);
         v[0] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+        pa = pb;
+        if (j < ts.k1) { ca = M.CS[j]; sa = M.SN[j]; }
     }
     hd_block_sum<NT, 1>(v, M.red);
     return v[0];
@@ -752,15 +701,16 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
         grad2(em, gmi, gmj);
     }
     double v[3] = {0, 0, 0};
+    double pre[NPRE];        // running prefix of the current linearisation at the vertex being finished
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
     auto finish_vertex = [&](int j, const double* gsum, double x, double y) {   // b_j = -(odometry terms) - loop terms
         double b[3] = {-gsum[0], -gsum[1], -gsum[2]};
         if (j == cjf) { b[0] -= gci[0]; b[1] -= gci[1]; b[2] -= gci[2]; }
         if (j == cjt) { b[0] -= gcj[0]; b[1] -= gcj[1]; b[2] -= gcj[2]; }
         if (j == mjf) { b[0] -= gmi[0]; b[1] -= gmi[1]; b[2] -= gmi[2]; }
         if (j == mjt) { b[0] -= gmj[0]; b[1] -= gmj[1]; b[2] -= gmj[2]; }
-        double pre[NPRE], h[3];
-#pragma unroll
-        for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m] + M.P[m][j];
+        double h[3];
         gn_step_at(sp, j, pre, x, y, h);
 #pragma unroll
         for (int q = 0; q < 3; ++q) { M.GB[q][j] = b[q]; M.GH[q][j] = h[q]; }
@@ -773,15 +723,15 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
         double gprev[3] = {0, 0, 0};   // gj of the edge that ends at the current vertex
         for (int k = k0; k <= k1 && k < L; ++k) {      // one extra edge (k1) for the gradient at the last owned vertex
             P2 pb{M.X[k + 1], M.Y[k + 1], M.TH[k + 1]};
-            double D[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : O.z(3 + c, k);
-            Lin2 e; lin2cs(ca, sa, pa, pb, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+            Lin2 e; double t[NPRE];
+            odom_terms<UNI>(O, k, ca, sa, pa, pb, e, t);
             double gi[3], gj[3]; grad2(e, gi, gj);
             if (k > k0) {   // vertex j = k is complete: gj(edge j-1) + gi(edge j)
                 const double gs[3] = {gprev[0] + gi[0], gprev[1] + gi[1], gprev[2] + gi[2]};
                 finish_vertex(k, gs, pa.x, pa.y);
             }
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
             gprev[0] = gj[0]; gprev[1] = gj[1]; gprev[2] = gj[2];
             pa = pb; ipc_sincos(pb.t, &sa, &ca);
         }
@@ -907,6 +857,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             double s, c; ipc_sincos(thk, &s, &c);
             ax += c * O.z(0, k) - s * O.z(1, k); ay += s * O.z(0, k) + c * O.z(1, k);
             M.X[k + 1] = ax; M.Y[k + 1] = ay; thk = M.TH[k + 1];
+            if (k + 1 < k1) { double s1, c1; ipc_sincos(thk, &s1, &c1); M.CS[k + 1] = c1; M.SN[k + 1] = s1; }
         }
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) ts.base[m] = 0;
@@ -945,7 +896,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
                         sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps;
                     }
                 } else {
-                    hgnNorm = sqrt(gn_norm_sq<NT>(M, ts)); have_norm = true;
+                    hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); have_norm = true;
                 }
             }
             if (!trial_done) {

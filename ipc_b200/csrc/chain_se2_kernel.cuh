@@ -1,5 +1,5 @@
 // chain_se2_kernel.cuh — CUDA entry of the SE(2) window check (see chain_se2.cuh for the algorithm).
-// MODE 0: per-vertex state (pose + prefix sums, 12 doubles / vertex) in shared memory;
+// MODE 0: per-vertex state (pose + cos / sin of the heading: 5 doubles / vertex) in shared memory;
 // MODE 1: state in the per-CTA global scratch (windows longer than shared memory holds).
 #pragma once
 #include "chain_se2.cuh"
@@ -7,7 +7,7 @@
 namespace ipcb {
 
 template <int NT, int MODE, bool UNI>
-__global__ void __launch_bounds__(NT) chain_check_se2(BatchArgs A) {
+__global__ void __launch_bounds__(NT, 512 / NT) chain_check_se2(BatchArgs A) {
     extern __shared__ __align__(16) double sm[];
     const int capv = A.Lcap + 2;
     ChainMem M;
@@ -17,9 +17,7 @@ __global__ void __launch_bounds__(NT) chain_check_se2(BatchArgs A) {
 #pragma unroll
     for (int q = 0; q < 3; ++q) { M.GB[q] = scr + (size_t)(3 + q) * capv; M.GH[q] = scr + (size_t)(6 + q) * capv; }
     double* st = (MODE == 0) ? sm + CHAIN_SMALL_DOUBLES : scr + (size_t)CHAIN_SCRATCH_ARRAYS * capv;
-    M.X = st; M.Y = st + capv; M.TH = st + 2 * (size_t)capv;
-#pragma unroll
-    for (int m = 0; m < NPRE; ++m) M.P[m] = st + (size_t)(3 + m) * capv;
+    M.X = st; M.Y = st + capv; M.TH = st + 2 * (size_t)capv; M.CS = st + 3 * (size_t)capv; M.SN = st + 4 * (size_t)capv;
     const LoopRec2* loops = static_cast<const LoopRec2*>(A.loops);
     CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept};
     const int n_work = *A.n_work;

@@ -7,12 +7,13 @@
 
 namespace ipcb {
 
-// ---- loop-candidate record in HBM (80 B SE2 / 240 B SE3), information already moved into the
+// ---- loop-candidate record in HBM (128 B SE2), information already moved into the
 // ---- "relative-pose" frame of the edge (see DESIGN.md "Edge frames") ---------------------------
 struct LoopRec2 {
     int from, to;
     double meas[3];       // x y theta
     double D[6];          // E^T Omega E upper triangle (00 01 02 11 12 22)
+    double V[6];          // D^-1
 };
 
 struct BatchArgs {

@@ -69,6 +69,12 @@ struct HostState {
         D_out[0] = Dm[0]; D_out[1] = 0.5 * (Dm[1] + Dm[3]); D_out[2] = 0.5 * (Dm[2] + Dm[6]);
         D_out[3] = Dm[4]; D_out[4] = 0.5 * (Dm[5] + Dm[7]); D_out[5] = Dm[8];
     }
+    static void inv_sym3_host(const double* D, double* V) {
+        double c00 = D[3] * D[5] - D[4] * D[4], c01 = D[2] * D[4] - D[1] * D[5], c02 = D[1] * D[4] - D[2] * D[3];
+        double id = 1.0 / (D[0] * c00 + D[1] * c01 + D[2] * c02);
+        V[0] = c00 * id; V[1] = c01 * id; V[2] = c02 * id;
+        V[3] = (D[0] * D[5] - D[2] * D[2]) * id; V[4] = (D[1] * D[2] - D[0] * D[4]) * id; V[5] = (D[0] * D[3] - D[1] * D[1]) * id;
+    }
 
     // SoA layout in HBM: component c of edge k at soa[c * n_pad + k]; SE2: zx zy zt d00 d01 d02 d11 d12 d22
     void build_odom_soa(int n_pad, std::vector<double>& soa) const {

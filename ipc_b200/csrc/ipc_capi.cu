@@ -72,9 +72,11 @@ namespace {
 
 constexpr int NB = 6;   // launch buckets
 struct Bucket { int cap; int nt; int mode; };
-// window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh). MODE 0 keeps 12 doubles per
-// vertex in shared memory: 227 KB holds windows up to ~2300 edges; longer windows run from the global scratch.
-const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 128, 0}, {800, 256, 0}, {1400, 512, 0}, {2100, 512, 0}, {1 << 30, 512, 1}};
+// window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh). Every kernel is compiled for
+// 512 resident threads per SM (<= 128 registers): 16 x 32, 8 x 64, 4 x 128, 2 x 256 or 1 x 512 CTAs, so the serial part of
+// one check (capacitance solve by thread 0) overlaps with the sweeps of the CTAs sharing its SM. MODE 0 keeps 5 doubles per
+// vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
+const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 64, 0}, {800, 128, 0}, {2600, 256, 0}, {5400, 512, 0}, {1 << 30, 512, 1}};
 
 size_t smem_bytes(int mode, int cap) {
     size_t capv = cap + 2;
@@ -181,12 +183,13 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap);
         size_t sm = smem_bytes(bk.mode, a.Lcap);
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-        per_sm = std::min(per_sm, 2048 / bk.nt);
+        per_sm = std::min(per_sm, 512 / bk.nt);
         int grid = std::min(n_checks, h->n_sm * per_sm);
         grid = (int)std::min<size_t>(grid, h->scratch_doubles / a.scratch_stride);
         int rc = IPC_OK;
         if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st, uni);
         else if (bk.nt == 32) rc = launch_se2<32, 0>(a, grid, st, uni);
+        else if (bk.nt == 64) rc = launch_se2<64, 0>(a, grid, st, uni);
         else if (bk.nt == 128) rc = launch_se2<128, 0>(a, grid, st, uni);
         else if (bk.nt == 256) rc = launch_se2<256, 0>(a, grid, st, uni);
         else rc = launch_se2<512, 0>(a, grid, st, uni);
@@ -252,7 +255,7 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
             int Lcap = (std::min(kBuckets2[b].cap, n_poses - 1) + 1) & ~1;
             size_t sm = smem_bytes(kBuckets2[b].mode, Lcap);
             int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-            per_sm = std::min(per_sm, 2048 / kBuckets2[b].nt);
+            per_sm = std::min(per_sm, 512 / kBuckets2[b].nt);
             need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kBuckets2[b].mode, Lcap));
         }
         h->scratch_doubles = need;
@@ -300,7 +303,7 @@ int ipc_set_candidates(ipc_handle* h, int n_loops, const int* from, const int* t
         std::vector<LoopRec2> recs(n_loops);
         for (int i = 0; i < n_loops; ++i) {
             recs[i].from = from[i]; recs[i].to = to[i];
-            HostState::se2_edge_record(meas + 3 * i, info + 9 * i, 1.0, recs[i].meas, recs[i].D);
+            HostState::se2_edge_record(meas + 3 * i, info + 9 * i, 1.0, recs[i].meas, recs[i].D); HostState::inv_sym3_host(recs[i].D, recs[i].V);
         }
         if (n_loops) {
             CUDA_TRY(cudaMalloc(&h->d_loops, sizeof(LoopRec2) * n_loops));

@@ -10,7 +10,7 @@
 
 using namespace ipcb;
 
-extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
+template <class PT> static int emul_impl(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
                                 const int* lto, const double* lmeas, const double* linfo, int n_checks, const int* member, const int* cand,
                                 double fast_th, double slow_th, int fast_iter, int slow_iter, double noise_eps, int speculate, int early_accept,
                                 int want_info, int use_uni, int n_threads, unsigned char* verdict, ipc_check_info* info, int* sweeps) {
@@ -19,7 +19,7 @@ extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const doub
     const int n_pad = (n_poses + 3) & ~1;
     std::vector<double> soa; hs.build_odom_soa(n_pad, soa);
     std::vector<LoopRec2> recs(n_loops);
-    for (int i = 0; i < n_loops; ++i) { recs[i].from = lfrom[i]; recs[i].to = lto[i]; HostState::se2_edge_record(lmeas + 3 * i, linfo + 9 * i, 1.0, recs[i].meas, recs[i].D); }
+    for (int i = 0; i < n_loops; ++i) { recs[i].from = lfrom[i]; recs[i].to = lto[i]; HostState::se2_edge_record(lmeas + 3 * i, linfo + 9 * i, 1.0, recs[i].meas, recs[i].D); HostState::inv_sym3_host(recs[i].D, recs[i].V); }
     CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept};
     std::atomic<int> next{0};
     auto work = [&]() {
@@ -27,7 +27,7 @@ extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const doub
         std::vector<double> buf((size_t)(CHAIN_STATE_ARRAYS + CHAIN_SCRATCH_ARRAYS) * capv + CHAIN_SMALL_DOUBLES, 0.0);
         ChainMem M; double* p = buf.data();
         chain_mem_small(M, p); p += CHAIN_SMALL_DOUBLES;
-        M.X = p; M.Y = p + capv; M.TH = p + 2 * capv; for (int m = 0; m < NPRE; ++m) M.P[m] = p + (3 + m) * (size_t)capv; p += (size_t)CHAIN_STATE_ARRAYS * capv;
+        M.X = p; M.Y = p + capv; M.TH = p + 2 * capv; M.CS = p + 3 * capv; M.SN = p + 4 * capv; p += (size_t)CHAIN_STATE_ARRAYS * capv;
         M.BX = p; M.BY = p + capv; M.BT = p + 2 * capv; for (int q = 0; q < 3; ++q) { M.GB[q] = p + (3 + q) * (size_t)capv; M.GH[q] = p + (6 + q) * (size_t)capv; }
         for (;;) {
             int c = next.fetch_add(1);
@@ -45,4 +45,14 @@ extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const doub
     for (int t = 0; t < (n_threads < 1 ? 1 : n_threads); ++t) th.emplace_back(work);
     for (auto& t : th) t.join();
     return 0;
+}
+
+extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
+                                const int* lto, const double* lmeas, const double* linfo, int n_checks, const int* member, const int* cand,
+                                double fast_th, double slow_th, int fast_iter, int slow_iter, double noise_eps, int speculate, int early_accept,
+                                int want_info, int use_uni, int n_threads, unsigned char* verdict, ipc_check_info* info, int* sweeps, int prefix_f32) {
+    if (prefix_f32) return emul_impl<float>(n_poses, odom_meas, odom_info, s_factor, n_loops, lfrom, lto, lmeas, linfo, n_checks, member, cand, fast_th, slow_th,
+                                            fast_iter, slow_iter, noise_eps, speculate, early_accept, want_info, use_uni, n_threads, verdict, info, sweeps);
+    return emul_impl<double>(n_poses, odom_meas, odom_info, s_factor, n_loops, lfrom, lto, lmeas, linfo, n_checks, member, cand, fast_th, slow_th,
+                             fast_iter, slow_iter, noise_eps, speculate, early_accept, want_info, use_uni, n_threads, verdict, info, sweeps);
 }

@@ -22,7 +22,7 @@ def lib():
     return _LIB
 
 
-def check_batch(g, cfg, member, cand, noise_eps=1e-13, speculate=1, early_accept=0, want_info=1, use_uni=1, n_threads=None):
+def check_batch(g, cfg, member, cand, noise_eps=1e-13, speculate=1, early_accept=0, want_info=1, use_uni=1, n_threads=None, prefix_f32=0):
     p = lambda a: a.ctypes.data_as(C.c_void_p)
     f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
@@ -35,6 +35,6 @@ def check_batch(g, cfg, member, cand, noise_eps=1e-13, speculate=1, early_accept
     rc = lib().emul_check_batch(g.n_poses, p(om), p(oi), C.c_double(cfg["s_factor"]), g.n_loops, p(lf), p(lt), p(lm), p(li), n, p(mb), p(cd),
                                 C.c_double(cfg["fast_reject_th"]), C.c_double(cfg["slow_reject_th"]), cfg["fast_reject_iter_base"],
                                 cfg["slow_reject_iter_base"], C.c_double(noise_eps), speculate, early_accept, want_info, use_uni, n_threads or os.cpu_count(),
-                                p(verdict), p(info), p(sweeps))
+                                p(verdict), p(info), p(sweeps), prefix_f32)
     assert rc == 0
     return verdict.astype(bool), info, sweeps
