@@ -37,26 +37,32 @@ namespace ipcb {
 
 // sin / cos for |t| <= pi + small (every angle here is normalised): Cody-Waite reduction by multiples of pi/2 and the
 // fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp each). The CUDA library sincos carries a Payne-Hanek slow path
-// (local-memory table) that this kernel never needs.
+// (local-memory table) that this kernel never needs. Coefficients sit in constant memory so the FMAs read them as operands.
+#ifdef __CUDACC__
+__constant__ double kSinCos[12] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+                                   -1.98412698298579493134e-04, 8.33333333332248946124e-03,  -1.66666666666666324348e-01,
+                                   -1.13596475577881948265e-11, 2.08757232129817482790e-09,  -2.75573143513906633035e-07,
+                                   2.48015872894767294178e-05,  -1.38888888888741095749e-03, 4.16666666666666019037e-02};
+#endif
 IPC_HD void ipc_sincos(double t, double* s, double* c) {
 #ifdef __CUDA_ARCH__
     const double q = rint(t * 0.63661977236758134308);            // 2 / pi
     double r = fma(-q, 1.57079632679489655800e+00, t);             // pi/2 hi
     r = fma(-q, 6.12323399573676603587e-17, r);                    // pi/2 lo
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kSinCos[0], kSinCos[1]);
+    ps = fma(z, ps, kSinCos[2]);
+    ps = fma(z, ps, kSinCos[3]);
+    ps = fma(z, ps, kSinCos[4]);
+    ps = fma(z, ps, kSinCos[5]);
     const double sr = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, kSinCos[6], kSinCos[7]);
+    pc = fma(z, pc, kSinCos[8]);
+    pc = fma(z, pc, kSinCos[9]);
+    pc = fma(z, pc, kSinCos[10]);
+    pc = fma(z, pc, kSinCos[11]);
     const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
-    const int n = (int)q & 3;
+    const int n = (int)q;
     const double ss = (n & 1) ? cr : sr, cc = (n & 1) ? sr : cr;
     *s = (n & 2) ? -ss : ss;
     *c = ((n + 1) & 2) ? -cc : cc;
@@ -64,14 +70,11 @@ IPC_HD void ipc_sincos(double t, double* s, double* c) {
     *s = sin(t); *c = cos(t);
 #endif
 }
-IPC_HD double wrap_pi_hd(double t) {   // g2o normalize_theta: [-pi, pi)
-    const double pi = 3.14159265358979323846;
-    if (t >= -pi && t < pi) return t;
-    double m = floor(t / (2 * pi));
-    t = t - m * 2 * pi;
-    if (t >= pi) t -= 2 * pi;
-    if (t < -pi) t += 2 * pi;
-    return t;
+// g2o normalize_theta maps to [-pi, pi). Branch-free form: subtract the nearest multiple of 2 pi (exact no-op for the
+// common in-range case; the two differ only for |t| = pi exactly, where the residual / heading is equivalent).
+IPC_HD double wrap_pi_hd(double t) {
+    const double k = rint(t * 0.15915494309189533577);             // 1 / (2 pi)
+    return fma(-k, 6.28318530717958647692, t);
 }
 
 struct P2 { double x, y, t; };
@@ -285,46 +288,55 @@ struct StepSpec {            // GN solution of one linearisation (uniform; lives
     int rs, re;              // region boundaries (local vertex / edge indices)
 };
 
+
+struct CheckGeom {           // geometry of one check (uniform; lives in the UniBlock)
+    int K, lo, L;
+    int rs, re, first_is_c, last_is_c;
+    int spec_v[NSPEC];       // 0, rs, re, L
+    // end points of the loop intervals: every start is 0 or rs, every end is re or L
+    int c_a_is_rs, c_b_is_L, m_a_is_rs, m_b_is_L;
+};
+
 struct UniBlock {            // uniform per-check data (shared memory): read by every thread, written by thread 0
     LoopRec2 Lc, Lm;
     StepSpec sol;
     double n_c, n_m;         // chi2 of the loop edges at the state of the last sweep
+    CheckGeom g;
 };
 constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
 
-struct ChainMem {
-    // per-vertex state, index j in [0, L]: pose and cos / sin of its heading. Shared memory (MODE 0) or per-CTA global scratch (MODE 1).
-    double *X, *Y, *TH, *CS, *SN;
-    // per-CTA global scratch (L2 resident)
-    double *BX, *BY, *BT;    // pose backup: state before the last trial sweep
-    double* GB[3];           // gradient b_j in g2o vertex coordinates (steepest-descent sweeps)
-    double* GH[3];           // h_gn,j in g2o vertex coordinates
-    double* red;             // collective staging, 2 buffers of RED_DOUBLES
-    double* spec;            // special-vertex table, 2 buffers of NSPEC * SPECW
-    UniBlock* U;
+constexpr int RED_DOUBLES_ = 16 * (NPRE + 3);
+struct ChainMem {            // three base pointers + a capacity: cheap to keep in registers and to pass by value
+    double* st;              // per-vertex state, AoS of 5 doubles: x, y, theta, cos, sin. Shared memory (MODE 0) or global scratch (MODE 1)
+    double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capv, then (b, h_gn) AoS[6] x capv
+    double* small;           // shared memory: collective staging (2 buffers), special-vertex table (2 buffers), UniBlock
+    int capv;
+    IPC_HD double* P(int j) const { return st + 5 * j; }                          // x y theta cos sin of vertex j
+    IPC_HD double* B(int j) const { return scr + 3 * j; }                         // pose backup: state before the last trial sweep
+    IPC_HD double* G(int j) const { return scr + 3 * (size_t)capv + 6 * j; }      // gradient b_j (3) and h_gn,j (3), g2o vertex coordinates
+    IPC_HD double* red() const { return small; }
+    IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_; }
+    IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + 2 * NSPEC * SPECW); }
 };
 constexpr int RED_DOUBLES = 16 * (NPRE + 3);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 2
 constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
 constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
 constexpr int CHAIN_SCRATCH_ARRAYS = 9;          // per-vertex doubles in the global scratch (backup, b, h_gn)
 
-IPC_HD void chain_mem_small(ChainMem& M, double* small) {
-    M.red = small; M.spec = small + 2 * RED_DOUBLES; M.U = reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES + 2 * NSPEC * SPECW);
-}
 
-struct OdomView {            // odometry records of the window, SoA in HBM/L2: zx zy zt d00 d01 d02 d11 d12 d22
-    const double* base;      // component c of local edge k at base[c * stride + k]
-    size_t stride;
-    const double* Du;        // UNI: the one information matrix every odometry edge shares (isotropic in x, y => frame independent)
-    const double* Vu;        //      and its inverse
-    IPC_HD double z(int c, int k) const {
-#ifdef __CUDA_ARCH__
-        return __ldg(base + (size_t)c * stride + k);
-#else
-        return base[(size_t)c * stride + k];
-#endif
-    }
+struct OdomView {            // odometry records of the window in HBM/L2, AoS: (zx zy zt) when every edge shares one isotropic
+    const double* rec;       // information (UNI, 24 B / edge), else (zx zy zt d00 d01 d02 d11 d12 d22) (72 B / edge)
+    const double* Du;        // UNI: the shared information matrix (frame independent) ...
+    const double* Vu;        //      ... and its inverse
 };
+template <bool UNI> IPC_HD const double* odom_rec(const OdomView& O, int k) { return O.rec + (UNI ? 3 : 9) * (size_t)k; }
+IPC_HD double ldg_d(const double* p) {
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 struct ThreadState {         // registers carried from sweep to sweep
     int k0, k1;              // owned edges [k0, k1); owned vertices k0+1 .. k1
@@ -376,31 +388,36 @@ IPC_HD void edge_prefix_terms_iso(const Lin2& e, double va, double vc, double xb
     t[7] = -(e.s * e.d0 + e.c * e.d1 - xb * e.d2);
     t[8] = -e.d2;
 }
-template <bool UNI> IPC_HD void odom_terms(const OdomView& O, int k, double c, double s, const P2& a, const P2& b, Lin2& e, double* t) {
+// z[0..2] (and D for the general case) of one odometry edge, loaded ahead of use
+template <bool UNI> struct OdomRec { double z[UNI ? 3 : 9]; };
+template <bool UNI> IPC_HD void odom_load(const OdomView& O, int k, OdomRec<UNI>& r) {
+    const double* p = odom_rec<UNI>(O, k);
+#pragma unroll
+    for (int q = 0; q < (UNI ? 3 : 9); ++q) r.z[q] = ldg_d(p + q);
+}
+template <bool UNI> IPC_HD void odom_terms(const OdomView& O, const OdomRec<UNI>& r, double c, double s, const P2& a, const P2& b, Lin2& e, double* t) {
     if (UNI) {
-        lin2cs(c, s, a, b, O.z(0, k), O.z(1, k), O.z(2, k), O.Du, e);
+        lin2cs(c, s, a, b, r.z[0], r.z[1], r.z[2], O.Du, e);
         edge_prefix_terms_iso(e, O.Vu[0], O.Vu[5], b.x, b.y, t);
     } else {
-        double D[6], V[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) D[q] = O.z(3 + q, k);
-        inv_sym3(D, V);
-        lin2cs(c, s, a, b, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
+        double V[6];
+        inv_sym3(r.z + 3, V);
+        lin2cs(c, s, a, b, r.z[0], r.z[1], r.z[2], r.z + 3, e);
         edge_prefix_terms(e, V, b.x, b.y, t);
     }
 }
 
 struct SweepOut { double chi, mx, hh; };   // odometry chi2 sum / max at the new state, |h|^2 of the applied step
 
-// The sweep: apply a step (none / GN of M.U->sol / blend c1 b + c2 h_gn from the scratch), re-linearise, chi2, interval
+// The sweep: apply a step (none / GN of M.U()->sol / blend c1 b + c2 h_gn from the scratch), re-linearise, chi2, interval
 // sums of the new linearisation at the special vertices. The GN step at vertex j needs the prefix of the OLD linearisation at
 // j: it is rebuilt on the fly from the old poses (no sincos: cos / sin are stored). Writes the pose backup when a step is
 // applied. Two block barriers.
-template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
-                                                   SweepOut& out, int& buf, const int* spec_v) {
+template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
+                                              SweepOut& out, int& buf, const int* spec_v) {
     const int k0 = ts.k0, k1 = ts.k1;
-    const StepSpec* sp = &M.U->sol;
-    double* spec = M.spec + (size_t)buf * NSPEC * SPECW;
+    const StepSpec* sp = &M.U()->sol;
+    double* spec = M.spec() + (size_t)buf * NSPEC * SPECW;
     double pre[NPRE];        // running prefix of the OLD linearisation (GN mode)
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
@@ -410,8 +427,9 @@ template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const Odom
         double h[3];
         if (mode == STEP_GN) gn_step_at(sp, k0, pre, oa.x, oa.y, h);
         else {
+            const double* gq = M.G(k0);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) h[q] = c1 * M.GB[q][k0] + c2 * M.GH[q][k0];
+            for (int q = 0; q < 3; ++q) h[q] = c1 * gq[q] + c2 * gq[3 + q];
         }
         na.x += h[0]; na.y += h[1]; na.t = wrap_pi_hd(na.t + h[2]);
         ipc_sincos(na.t, &nsa, &nca);
@@ -421,60 +439,96 @@ template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const Odom
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) run[m] = 0;
     double chi = 0, mx = 0, hh = 0;
+    bool has_spec = false;
+#pragma unroll
+    for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
+    // records and state of the next edge are fetched one iteration ahead (L2 latency of the odometry records)
+    OdomRec<UNI> rn; double sn[5] = {0, 0, 0, 0, 0}, gn[6] = {0, 0, 0, 0, 0, 0};
+    if (k0 < k1) {
+        odom_load<UNI>(O, k0, rn);
+        const double* pp = M.P(k0 + 1);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) sn[q] = pp[q];
+        if (mode == STEP_BLEND) {
+            const double* gq = M.G(k0 + 1);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) gn[q] = gq[q];
+        }
+    }
     for (int k = k0; k < k1; ++k) {
         const int j = k + 1;
-        const P2 ob{M.X[j], M.Y[j], M.TH[j]};
+        const OdomRec<UNI> r = rn;
+        const P2 ob{sn[0], sn[1], sn[2]};
+        const double ocb = sn[3], osb = sn[4];
+        double g6[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) g6[q] = gn[q];
+        if (j < k1) {
+            odom_load<UNI>(O, k + 1, rn);
+            const double* pp = M.P(j + 1);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) sn[q] = pp[q];
+            if (mode == STEP_BLEND) {
+                const double* gq = M.G(j + 1);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) gn[q] = gq[q];
+            }
+        }
         P2 nb = ob;
-        double ocb = 0, osb = 0, ncb, nsb;
-        if (j < k1) { ocb = M.CS[j]; osb = M.SN[j]; }
-        ncb = ocb; nsb = osb;
+        double ncb = ocb, nsb = osb;
         if (mode != STEP_NONE) {
             double h[3];
             if (mode == STEP_GN) {
                 Lin2 eo; double to[NPRE];
-                odom_terms<UNI>(O, k, oca, osa, oa, ob, eo, to);
+                odom_terms<UNI>(O, r, oca, osa, oa, ob, eo, to);
 #pragma unroll
                 for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
                 gn_step_at(sp, j, pre, ob.x, ob.y, h);
             } else {
 #pragma unroll
-                for (int q = 0; q < 3; ++q) h[q] = c1 * M.GB[q][j] + c2 * M.GH[q][j];
+                for (int q = 0; q < 3; ++q) h[q] = c1 * g6[q] + c2 * g6[3 + q];
             }
-            M.BX[j] = ob.x; M.BY[j] = ob.y; M.BT[j] = ob.t;
+            double* bq = M.B(j);
+            bq[0] = ob.x; bq[1] = ob.y; bq[2] = ob.t;
             nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
             hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
-            M.X[j] = nb.x; M.Y[j] = nb.y; M.TH[j] = nb.t;
-            if (j < k1) { ipc_sincos(nb.t, &nsb, &ncb); M.CS[j] = ncb; M.SN[j] = nsb; }
+            ipc_sincos(nb.t, &nsb, &ncb);
+            double* pq = M.P(j);
+            pq[0] = nb.x; pq[1] = nb.y; pq[2] = nb.t; pq[3] = ncb; pq[4] = nsb;
         }
         Lin2 e; double t[NPRE];
-        odom_terms<UNI>(O, k, nca, nsa, na, nb, e, t);
+        odom_terms<UNI>(O, r, nca, nsa, na, nb, e, t);
         chi += e.chi; mx = fmax(mx, e.chi);
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) run[m] += t[m];
+        if (has_spec) {
 #pragma unroll
-        for (int q = 1; q < NSPEC; ++q) {
-            if (j == spec_v[q]) {        // local part now, the thread base is added after the scan
-                double* o = spec + q * SPECW;
+            for (int q = 1; q < NSPEC; ++q) {
+                if (j == spec_v[q]) {        // local part now, the thread base is added after the scan
+                    double* o = spec + q * SPECW;
 #pragma unroll
-                for (int m = 0; m < NPRE; ++m) o[m] = run[m];
-                o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+                    for (int m = 0; m < NPRE; ++m) o[m] = run[m];
+                    o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+                }
             }
         }
         oa = ob; oca = ocb; osa = osb;
         na = nb; nca = ncb; nsa = nsb;
     }
     double s[2] = {chi, hh};
-    ScanSumMax<NT, 2>::run(run, s, mx, M.red + (size_t)buf * RED_DOUBLES);
+    ScanSumMax<NT, 2>::run(run, s, mx, M.red() + (size_t)buf * RED_DOUBLES);
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) ts.base[m] = run[m];
     out.chi = s[0]; out.hh = s[1]; out.mx = mx;
+    if (has_spec) {
 #pragma unroll
-    for (int q = 1; q < NSPEC; ++q) {
-        const int v = spec_v[q];
-        if (v > k0 && v <= k1) {
-            double* o = spec + q * SPECW;
+        for (int q = 1; q < NSPEC; ++q) {
+            const int v = spec_v[q];
+            if (v > k0 && v <= k1) {
+                double* o = spec + q * SPECW;
 #pragma unroll
-            for (int m = 0; m < NPRE; ++m) o[m] += run[m];
+                for (int m = 0; m < NPRE; ++m) o[m] += run[m];
+            }
         }
     }
     bsync<NT>();
@@ -483,29 +537,22 @@ template <int NT, bool UNI> IPC_HD_COLD void sweep(const ChainMem& M, const Odom
 
 // undo the last applied sweep: poses from the backup, cos / sin recomputed, boundary registers re-read. Thread bases are NOT
 // restored: every caller re-linearises (GN rejection) or only runs blend sweeps (which do not read them) until a step is kept.
-template <int NT> IPC_HD_COLD void rollback(const ChainMem& M, ThreadState& ts) {
+template <int NT> IPC_HD void rollback(const ChainMem& M, ThreadState& ts) {
     for (int k = ts.k0; k < ts.k1; ++k) {
         const int j = k + 1;
-        const double t = M.BT[j];
-        M.X[j] = M.BX[j]; M.Y[j] = M.BY[j]; M.TH[j] = t;
-        if (j < ts.k1) { double s, c; ipc_sincos(t, &s, &c); M.CS[j] = c; M.SN[j] = s; }
+        const double t = M.B(j)[2];
+        double s, c; ipc_sincos(t, &s, &c);
+        double* pq = M.P(j);
+        pq[0] = M.B(j)[0]; pq[1] = M.B(j)[1]; pq[2] = t; pq[3] = c; pq[4] = s;
     }
     bsync<NT>();
-    if (ts.k0 < ts.k1) {
-        ts.pa.x = M.X[ts.k0]; ts.pa.y = M.Y[ts.k0]; ts.pa.t = M.TH[ts.k0];
-        ipc_sincos(ts.pa.t, &ts.sa, &ts.ca);
+    if (ts.k0 < ts.k1 && ts.k0 > 0) {
+        const double* pq = M.P(ts.k0);
+        ts.pa.x = pq[0]; ts.pa.y = pq[1]; ts.pa.t = pq[2]; ts.ca = pq[3]; ts.sa = pq[4];
     }
     bsync<NT>();
 }
 
-// what the uniform part needs about one check
-struct CheckGeom {
-    int K, lo, L;
-    int rs, re, first_is_c, last_is_c;
-    int spec_v[NSPEC];       // 0, rs, re, L
-    // end points of the loop intervals: every start is 0 or rs, every end is re or L
-    int c_a_is_rs, c_b_is_L, m_a_is_rs, m_b_is_L;
-};
 
 struct SpecVals {            // prefix (PM, Pm) and pose at the special vertices rs, re, L (vertex 0: zeros / origin)
     double pre1[NPRE], pre2[NPRE], pre3[NPRE];
@@ -635,59 +682,63 @@ IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopNow& lc, 
 }
 
 // After a sweep: thread 0 evaluates the loop edges at the published state and, if the trial is going to be kept
-// (rho > 0, or `force`), solves the new linearisation into M.U->sol. One barrier; every thread gets the loop chi2.
-IPC_HD_COLD void eval_and_solve_t0(const ChainMem& M, const CheckGeom& g, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
+// (rho > 0, or `force`), solves the new linearisation into M.U()->sol. One barrier; every thread gets the loop chi2.
+IPC_HD_COLD void eval_and_solve_t0(ChainMem M, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
+    UniBlock* U = M.U();
+    const CheckGeom& g = U->g;
     SpecVals sv; LoopNow lc, lm;
-    spec_load(M.spec + (size_t)(buf ^ 1) * NSPEC * SPECW, g, sv);
-    loops_eval(sv, g, M.U->Lc, M.U->Lm, lc, lm);
+    spec_load(M.spec() + (size_t)(buf ^ 1) * NSPEC * SPECW, g, sv);
+    loops_eval(sv, g, U->Lc, U->Lm, lc, lm);
     const double c = lc.e.chi, m = g.K == 2 ? lm.e.chi : 0.0;
     if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
     const double rho = (cur_chi - (odom_chi + c + m)) / linearGain;
-    if (force || rho > 0) gn_solve(sv, g, lc, lm, &M.U->sol);
-    M.U->n_c = c; M.U->n_m = m;
+    if (force || rho > 0) gn_solve(sv, g, lc, lm, &U->sol);
+    U->n_c = c; U->n_m = m;
 }
-template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, const CheckGeom& g, int buf, double odom_chi, double cur_chi, double linearGain,
-                                             bool force, double& n_c, double& n_m) {
-    if (hd_tid() == 0) eval_and_solve_t0(M, g, buf, odom_chi, cur_chi, linearGain, force);
+template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, int buf, double odom_chi, double cur_chi, double linearGain, bool force, double& n_c,
+                                             double& n_m) {
+    if (hd_tid() == 0) eval_and_solve_t0(M, buf, odom_chi, cur_chi, linearGain, force);
     bsync<NT>();
-    n_c = M.U->n_c; n_m = M.U->n_m;
+    n_c = M.U()->n_c; n_m = M.U()->n_m;
 }
 
 // |h_gn|^2 of the current linearisation without applying it
-template <int NT, bool UNI> IPC_HD_COLD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
+template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
     double v[1] = {0};
-    const StepSpec* sp = &M.U->sol;
+    const StepSpec* sp = &M.U()->sol;
     double pre[NPRE];
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
     P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
     for (int k = ts.k0; k < ts.k1; ++k) {
         const int j = k + 1;
-        const P2 pb{M.X[j], M.Y[j], M.TH[j]};
+        const double* pq = M.P(j);
+        const P2 pb{pq[0], pq[1], pq[2]};
+        OdomRec<UNI> r; odom_load<UNI>(O, k, r);
         Lin2 e; double t[NPRE], h[3];
-        odom_terms<UNI>(O, k, ca, sa, pa, pb, e, t);
+        odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
         gn_step_at(sp, j, pre, pb.x, pb.y, h);
         v[0] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
-        pa = pb;
-        if (j < ts.k1) { ca = M.CS[j]; sa = M.SN[j]; }
+        pa = pb; ca = pq[3]; sa = pq[4];
     }
-    hd_block_sum<NT, 1>(v, M.red);
+    hd_block_sum<NT, 1>(v, M.red());
     return v[0];
 }
 
 // steepest-descent sweeps at the current state (poses + prefixes valid): gradient b and h_gn per vertex into the scratch,
 // bb = |b|^2, bh = b . h_gn, hh = |h_gn|^2, bHb = b^T H b.
-template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const OdomView& O, const CheckGeom& g, const ThreadState& ts, double& bb,
+template <int NT, bool UNI> IPC_HD void sd_sweeps(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
                                                   double& bh, double& hh, double& bHb) {
+    const CheckGeom& g = M.U()->g;
     const int k0 = ts.k0, k1 = ts.k1, L = g.L;
-    const StepSpec* sp = &M.U->sol;
-    const LoopRec2& Lc = M.U->Lc; const LoopRec2& Lm = M.U->Lm;
+    const StepSpec* sp = &M.U()->sol;
+    const LoopRec2& Lc = M.U()->Lc; const LoopRec2& Lm = M.U()->Lm;
     // loop edges at the current state (poses are stable in M.X: nobody writes them during these sweeps)
     Lin2 ec, em; const int cjf = Lc.from - g.lo, cjt = Lc.to - g.lo; int mjf = -1, mjt = -1;
     {
-        P2 pf{M.X[cjf], M.Y[cjf], M.TH[cjf]}, pt{M.X[cjt], M.Y[cjt], M.TH[cjt]};
+        P2 pf{M.P(cjf)[0], M.P(cjf)[1], M.P(cjf)[2]}, pt{M.P(cjt)[0], M.P(cjt)[1], M.P(cjt)[2]};
         double s, c; ipc_sincos(pf.t, &s, &c);
         lin2cs(c, s, pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
     }
@@ -695,7 +746,7 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
     grad2(ec, gci, gcj);
     if (g.K == 2) {
         mjf = Lm.from - g.lo; mjt = Lm.to - g.lo;
-        P2 pf{M.X[mjf], M.Y[mjf], M.TH[mjf]}, pt{M.X[mjt], M.Y[mjt], M.TH[mjt]};
+        P2 pf{M.P(mjf)[0], M.P(mjf)[1], M.P(mjf)[2]}, pt{M.P(mjt)[0], M.P(mjt)[1], M.P(mjt)[2]};
         double s, c; ipc_sincos(pf.t, &s, &c);
         lin2cs(c, s, pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
         grad2(em, gmi, gmj);
@@ -713,7 +764,7 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
         double h[3];
         gn_step_at(sp, j, pre, x, y, h);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { M.GB[q][j] = b[q]; M.GH[q][j] = h[q]; }
+        for (int q = 0; q < 3; ++q) { M.G(j)[q] = b[q]; M.G(j)[3 + q] = h[q]; }
         v[0] += b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
         v[1] += b[0] * h[0] + b[1] * h[1] + b[2] * h[2];
         v[2] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
@@ -722,9 +773,10 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
         P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
         double gprev[3] = {0, 0, 0};   // gj of the edge that ends at the current vertex
         for (int k = k0; k <= k1 && k < L; ++k) {      // one extra edge (k1) for the gradient at the last owned vertex
-            P2 pb{M.X[k + 1], M.Y[k + 1], M.TH[k + 1]};
+            P2 pb{M.P(k + 1)[0], M.P(k + 1)[1], M.P(k + 1)[2]};
             Lin2 e; double t[NPRE];
-            odom_terms<UNI>(O, k, ca, sa, pa, pb, e, t);
+            OdomRec<UNI> r; odom_load<UNI>(O, k, r);
+            odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
             double gi[3], gj[3]; grad2(e, gi, gj);
             if (k > k0) {   // vertex j = k is complete: gj(edge j-1) + gi(edge j)
                 const double gs[3] = {gprev[0] + gi[0], gprev[1] + gi[1], gprev[2] + gi[2]};
@@ -739,23 +791,24 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
     }
     if (hd_tid() == 0) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { M.GB[q][0] = 0; M.GH[q][0] = 0; }   // vertex 0 is fixed
+        for (int q = 0; q < 3; ++q) { M.G(0)[q] = 0; M.G(0)[3 + q] = 0; }   // vertex 0 is fixed
     }
-    hd_block_sum<NT, 3>(v, M.red);
+    hd_block_sum<NT, 3>(v, M.red());
     bsync<NT>();                        // GB / GH visible to the neighbours
     bb = v[0]; bh = v[1]; hh = v[2];
     // b^T H b = sum over edges |J b|^2_D
     double w[1] = {0};
     if (k0 < k1) {
         P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
-        double ba[3] = {M.GB[0][k0], M.GB[1][k0], M.GB[2][k0]};
+        double ba[3] = {M.G(k0)[0], M.G(k0)[1], M.G(k0)[2]};
         for (int k = k0; k < k1; ++k) {
-            P2 pb{M.X[k + 1], M.Y[k + 1], M.TH[k + 1]};
+            P2 pb{M.P(k + 1)[0], M.P(k + 1)[1], M.P(k + 1)[2]};
+            OdomRec<UNI> r; odom_load<UNI>(O, k, r);
             double D[6];
 #pragma unroll
-            for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : O.z(3 + c, k);
-            Lin2 e; lin2cs(ca, sa, pa, pb, O.z(0, k), O.z(1, k), O.z(2, k), D, e);
-            double bv[3] = {M.GB[0][k + 1], M.GB[1][k + 1], M.GB[2][k + 1]};
+            for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : r.z[UNI ? 0 : 3 + c];
+            Lin2 e; lin2cs(ca, sa, pa, pb, r.z[0], r.z[1], r.z[2], D, e);
+            double bv[3] = {M.G(k + 1)[0], M.G(k + 1)[1], M.G(k + 1)[2]};
             double q0, q1, q2; dlin2(e, ba, bv, q0, q1, q2);
             w[0] += quad3(D, q0, q1, q2);
             ba[0] = bv[0]; ba[1] = bv[1]; ba[2] = bv[2];
@@ -763,14 +816,14 @@ template <int NT, bool UNI> IPC_HD_COLD void sd_sweeps(const ChainMem& M, const 
         }
     }
     if (hd_tid() == 0) {
-        double bf[3] = {M.GB[0][cjf], M.GB[1][cjf], M.GB[2][cjf]}, bt[3] = {M.GB[0][cjt], M.GB[1][cjt], M.GB[2][cjt]}, q0, q1, q2;
+        double bf[3] = {M.G(cjf)[0], M.G(cjf)[1], M.G(cjf)[2]}, bt[3] = {M.G(cjt)[0], M.G(cjt)[1], M.G(cjt)[2]}, q0, q1, q2;
         dlin2(ec, bf, bt, q0, q1, q2); w[0] += quad3(Lc.D, q0, q1, q2);
         if (g.K == 2) {
-            double mf[3] = {M.GB[0][mjf], M.GB[1][mjf], M.GB[2][mjf]}, mt[3] = {M.GB[0][mjt], M.GB[1][mjt], M.GB[2][mjt]};
+            double mf[3] = {M.G(mjf)[0], M.G(mjf)[1], M.G(mjf)[2]}, mt[3] = {M.G(mjt)[0], M.G(mjt)[1], M.G(mjt)[2]};
             dlin2(em, mf, mt, q0, q1, q2); w[0] += quad3(Lm.D, q0, q1, q2);
         }
     }
-    hd_block_sum<NT, 1>(w, M.red);
+    hd_block_sum<NT, 1>(w, M.red());
     bHb = w[0];
 }
 
@@ -789,21 +842,24 @@ struct CheckResult {
 };
 
 // One check, executed cooperatively by NT threads (device) or by the calling thread (host, NT = 1).
-template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const double* odom, size_t odom_stride, const double* Du, const double* Vu,
+// The Dogleg of g2o (OptimizationAlgorithmDogleg::solve inside SparseOptimizer::optimize) is written as a state machine
+// around ONE sweep call site, so the sweep is inlined exactly once and nothing lives in local memory.
+enum { P_INIT = 0, P_TRIAL_SPEC, P_TRIAL_GN, P_TRIAL_BLEND, P_RELIN_SPECFAIL, P_RELIN_REJECT };
+
+template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
                                                   const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res) {
     const int tid = hd_tid();
-    bsync<NT>();                                            // previous check is done with every array and with M.U
-    if (tid == 0) { M.U->Lc = *Lc_in; M.U->Lm = Lm_in ? *Lm_in : *Lc_in; }
-    bsync<NT>();
-    CheckGeom g;
-    int ma_l = 0, mb_l = 0;
-    {
-        const int cf = M.U->Lc.from, ct = M.U->Lc.to;
+    bsync<NT>();                                            // previous check is done with every array and with the UniBlock
+    if (tid == 0) {
+        UniBlock* U = M.U();
+        U->Lc = *Lc_in; U->Lm = Lm_in ? *Lm_in : *Lc_in;
+        CheckGeom g;
+        const int cf = U->Lc.from, ct = U->Lc.to;
         const int ca = cf < ct ? cf : ct, cb = cf < ct ? ct : cf;
         int lo = ca, hi = cb; g.K = 1;
         int ma = 0, mb = 0;
         if (Lm_in) {
-            const int mf = M.U->Lm.from, mt = M.U->Lm.to;
+            const int mf = U->Lm.from, mt = U->Lm.to;
             ma = mf < mt ? mf : mt; mb = mf < mt ? mt : mf;
             // src/consensus.cpp:157-159: positive-length overlap pulls the member into the cluster
             if ((mb < cb ? mb : cb) - (ma > ca ? ma : ca) > 0) { g.K = 2; lo = ca < ma ? ca : ma; hi = cb > mb ? cb : mb; }
@@ -812,7 +868,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         g.lo = lo; g.L = L;
         const int ca_l = ca - lo, cb_l = cb - lo;
         g.rs = 0; g.re = L; g.first_is_c = 1; g.last_is_c = 1;
-        ma_l = 0; mb_l = L;
+        int ma_l = 0, mb_l = L;
         if (g.K == 2) {
             ma_l = ma - lo; mb_l = mb - lo;
             g.rs = ca_l > ma_l ? ca_l : ma_l; g.re = cb_l < mb_l ? cb_l : mb_l;
@@ -820,12 +876,15 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         }
         g.spec_v[0] = 0; g.spec_v[1] = g.rs; g.spec_v[2] = g.re; g.spec_v[3] = L;
         g.c_a_is_rs = ca_l != 0; g.c_b_is_L = cb_l == L; g.m_a_is_rs = ma_l != 0; g.m_b_is_L = mb_l == L;
+        U->g = g;
     }
-    const int L = g.L;
-    const double th = (g.K == 2) ? prm.slow_th : prm.fast_th;
-    int max_iter = (g.K == 2) ? prm.slow_iter : prm.fast_iter;
-    if (L + g.K > 100) max_iter *= 5;                      // src/consensus_utils.cpp:12-13
-    OdomView O{odom + g.lo, odom_stride, Du, Vu};
+    bsync<NT>();
+    const int K = M.U()->g.K, L = M.U()->g.L;
+    const int spec_v[NSPEC] = {0, M.U()->g.rs, M.U()->g.re, L};
+    const double th = (K == 2) ? prm.slow_th : prm.fast_th;
+    int max_iter = (K == 2) ? prm.slow_iter : prm.fast_iter;
+    if (L + K > 100) max_iter *= 5;                        // src/consensus_utils.cpp:12-13
+    OdomView O{odom + (UNI ? 3 : 9) * (size_t)M.U()->g.lo, Du, Vu};
 
     ThreadState ts;
     int S = (L + NT - 1) / NT; if (S < 1) S = 1; S |= 1;   // odd segment length: conflict-free strided shared-memory access
@@ -835,130 +894,155 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     // ---- dead-reckoning (propagateGuess, src/consensus_utils.cpp:98-116) as two block scans --------------
     {
         double v[1] = {0};
-        for (int k = k0; k < k1; ++k) v[0] += O.z(2, k);
-        hd_block_excl_scan<NT, 1>(v, M.red);
+        for (int k = k0; k < k1; ++k) v[0] += ldg_d(odom_rec<UNI>(O, k) + 2);
+        hd_block_excl_scan<NT, 1>(v, M.red());
         double acc = v[0];
         const double th0 = wrap_pi_hd(acc);                 // heading of vertex k0
-        if (tid == 0) { M.X[0] = 0; M.Y[0] = 0; M.TH[0] = 0; }
+        if (tid == 0) { double* p0 = M.P(0); p0[0] = 0; p0[1] = 0; p0[2] = 0; p0[3] = 1; p0[4] = 0; }
         double p[2] = {0, 0};
-        double thk = th0;
+        double s, c; ipc_sincos(th0, &s, &c);
+        ts.pa.t = th0; ts.ca = c; ts.sa = s;
         for (int k = k0; k < k1; ++k) {
-            double s, c; ipc_sincos(thk, &s, &c);
-            p[0] += c * O.z(0, k) - s * O.z(1, k); p[1] += s * O.z(0, k) + c * O.z(1, k);
-            acc += O.z(2, k); thk = wrap_pi_hd(acc); M.TH[k + 1] = thk;
+            const double* zr = odom_rec<UNI>(O, k);
+            const double zx = ldg_d(zr), zy = ldg_d(zr + 1), zt = ldg_d(zr + 2);
+            p[0] += c * zx - s * zy; p[1] += s * zx + c * zy;
+            acc += zt;
+            const double thk = wrap_pi_hd(acc);
+            ipc_sincos(thk, &s, &c);
+            double* pq = M.P(k + 1);
+            pq[2] = thk; pq[3] = c; pq[4] = s;
         }
         bsync<NT>();
-        hd_block_excl_scan<NT, 2>(p, M.red);
+        hd_block_excl_scan<NT, 2>(p, M.red());
         double ax = p[0], ay = p[1];
-        ts.pa.x = ax; ts.pa.y = ay; ts.pa.t = th0;
-        ipc_sincos(th0, &ts.sa, &ts.ca);
-        thk = th0;
+        ts.pa.x = ax; ts.pa.y = ay;
+        c = ts.ca; s = ts.sa;
         for (int k = k0; k < k1; ++k) {
-            double s, c; ipc_sincos(thk, &s, &c);
-            ax += c * O.z(0, k) - s * O.z(1, k); ay += s * O.z(0, k) + c * O.z(1, k);
-            M.X[k + 1] = ax; M.Y[k + 1] = ay; thk = M.TH[k + 1];
-            if (k + 1 < k1) { double s1, c1; ipc_sincos(thk, &s1, &c1); M.CS[k + 1] = c1; M.SN[k + 1] = s1; }
+            const double* zr = odom_rec<UNI>(O, k);
+            const double zx = ldg_d(zr), zy = ldg_d(zr + 1);
+            ax += c * zx - s * zy; ay += s * zx + c * zy;
+            double* pq = M.P(k + 1);
+            pq[0] = ax; pq[1] = ay; c = pq[3]; s = pq[4];
         }
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) ts.base[m] = 0;
     }
+
     int buf = 0, n_sweeps = 0;
     SweepOut so;
-    double n_c, n_m;
-    sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps;
-    eval_and_solve<NT>(M, g, buf, so.chi, 0, 1, true, n_c, n_m);
-    double cur_chi = so.chi + n_c + n_m;
-    double cur_max = fmax(so.mx, fmax(n_c, n_m));
-    double cand_chi = n_c;
-
-    // ---- Dogleg (OptimizationAlgorithmDogleg::solve + SparseOptimizer::optimize) --------------------------
+    double cur_chi = 0, cur_max = 0, cand_chi = 0;
     double delta = 1e4;
-    int iterations = 0, evals = 0;
-    bool ok = true;
+    int iterations = 0, evals = 0, it = 0, tries = 0;
     double prev_hnorm = -1;      // norm of the last accepted step (speculation heuristic)
-    for (int it = 0; it < max_iter && ok; ++it) {
-        if (prm.early_accept && !want_info && cur_chi <= th) break;     // every edge chi2 <= sum <= th, and the sum only decreases
-        bool have_norm = false, have_sd = false, good = false;
-        double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0;
-        int tries = 0;
-        do {
-            ++tries;
-            bool trial_done = false, trial_gn = false;
-            double linearGain = 0;
-            const double gn_gain = cur_chi - M.U->sol.model;     // predicted gain of the GN step of the current linearisation
-            if (!have_norm) {
-                if (prm.speculate && prev_hnorm >= 0 && 4 * prev_hnorm < delta) {
-                    sweep<NT, UNI>(M, O, STEP_GN, 0, 1, ts, so, buf, g.spec_v); ++n_sweeps;
-                    hgnNorm = sqrt(so.hh); have_norm = true;
-                    if (hgnNorm < delta) { trial_done = true; trial_gn = true; }
-                    else {   // the GN step does not fit the trust region after all: undo, restore the linearisation
-                        rollback<NT>(M, ts);
-                        sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps;
-                    }
-                } else {
-                    hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); have_norm = true;
-                }
+    bool have_norm = false, have_sd = false, need_rollback = false;
+    double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0, linearGain = 0;
+    int purpose = P_INIT, mode = STEP_NONE;
+    double c1 = 0, c2 = 0;
+    for (;;) {
+        if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; }
+        sweep<NT, UNI>(M, O, mode, c1, c2, ts, so, buf, spec_v); ++n_sweeps;
+        bool start_iter = false, after_reject = false, decide = false;
+        if (purpose == P_INIT) {
+            double n_c, n_m;
+            eval_and_solve<NT>(M, buf, so.chi, 0, 1, true, n_c, n_m);
+            cur_chi = so.chi + n_c + n_m; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
+            start_iter = true;
+        } else if (purpose == P_RELIN_SPECFAIL) {
+            decide = true;                                   // same try, the GN norm is known now
+        } else if (purpose == P_RELIN_REJECT) {
+            after_reject = true;
+        } else {
+            bool specfail = false;
+            if (purpose == P_TRIAL_SPEC) { hgnNorm = sqrt(so.hh); have_norm = true; specfail = !(hgnNorm < delta); }
+            if (specfail) {      // the GN step does not fit the trust region after all: undo, restore the linearisation
+                need_rollback = true; mode = STEP_NONE; purpose = P_RELIN_SPECFAIL;
+                continue;
             }
-            if (!trial_done) {
-                if (hgnNorm < delta) {
-                    sweep<NT, UNI>(M, O, STEP_GN, 0, 1, ts, so, buf, g.spec_v); ++n_sweeps;
-                    trial_gn = true;
-                } else {
-                    if (!have_sd) {
-                        sd_sweeps<NT, UNI>(M, O, g, ts, bb, bh, hh, bHb); n_sweeps += 2;
-                        alpha = bb / bHb;
-                        hsdNorm = alpha * sqrt(bb);
-                        have_sd = true;
-                    }
-                    double c1, c2;
-                    if (hsdNorm > delta) { c1 = delta / hsdNorm * alpha; c2 = 0; }
-                    else {
-                        const double hsdSq = alpha * alpha * bb;
-                        const double c = alpha * bh - hsdSq;                     // hsd . (hgn - hsd)
-                        const double bma = hh - 2 * alpha * bh + hsdSq;           // |hgn - hsd|^2
-                        double beta;
-                        if (c <= 0) beta = (-c + sqrt(c * c + bma * (delta * delta - hsdSq))) / bma;
-                        else beta = (delta * delta - hsdSq) / (c + sqrt(c * c + bma * (delta * delta - hsdSq)));
-                        c1 = alpha * (1 - beta); c2 = beta;
-                    }
-                    // H h_gn = b  =>  h^T H h = c1^2 bHb + 2 c1 c2 bb + c2^2 bh,  b^T h = c1 bb + c2 bh
-                    linearGain = -(c1 * c1 * bHb + 2 * c1 * c2 * bb + c2 * c2 * bh) + 2 * (c1 * bb + c2 * bh);
-                    sweep<NT, UNI>(M, O, STEP_BLEND, c1, c2, ts, so, buf, g.spec_v); ++n_sweeps;
-                }
-            }
-            if (trial_gn) linearGain = gn_gain;
+            const bool trial_gn = purpose != P_TRIAL_BLEND;
             const double hdlNorm = sqrt(so.hh);
             ++evals;
             // loop edges at the trial state; thread 0 also solves the new linearisation when the step is going to be kept
-            eval_and_solve<NT>(M, g, buf, so.chi, cur_chi, linearGain, false, n_c, n_m);
+            double n_c, n_m;
+            eval_and_solve<NT>(M, buf, so.chi, cur_chi, linearGain, false, n_c, n_m);
             const double newChi = so.chi + n_c + n_m;
             const double rawGain = linearGain;
-            if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
-            const double rho = (cur_chi - newChi) / linearGain;
-            if (rho > 0) {
-                good = true;
-                cur_chi = newChi; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
-                prev_hnorm = hdlNorm;
-            } else {
-                rollback<NT>(M, ts);
-                if (trial_gn) { sweep<NT, UNI>(M, O, STEP_NONE, 0, 0, ts, so, buf, g.spec_v); ++n_sweeps; }   // prefixes of the old state again
-                prev_hnorm = -1;
-            }
+            double lg = linearGain;
+            if (fabs(lg) < 1e-12) lg = 1e-12;
+            const double rho = (cur_chi - newChi) / lg;
             if (rho > 0.75) delta = fmax(delta, 3 * hdlNorm);
             else if (rho < 0.25) delta *= 0.5;
-            if (!good) {
+            if (rho > 0) {
+                cur_chi = newChi; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
+                prev_hnorm = hdlNorm;
+                ++iterations; ++it;
+                start_iter = true;
+            } else {
+                need_rollback = true;
+                prev_hnorm = -1;
                 // a rejected Gauss-Newton step is retried verbatim while it still fits the trust region: every such retry
                 // reproduces the same rho (<= 0), so only the halving of delta and the try counter advance
                 if (trial_gn) while (tries < prm.max_tries && hgnNorm < delta) { ++tries; ++evals; delta *= 0.5; }
                 if (prm.noise_eps > 0 && rawGain <= prm.noise_eps * cur_chi + 1e-300) tries = prm.max_tries;
+                if (trial_gn && tries < prm.max_tries) {     // prefixes of the old state are needed again (gradient sweeps)
+                    mode = STEP_NONE; purpose = P_RELIN_REJECT;
+                    continue;
+                }
+                after_reject = true;
             }
-        } while (!good && tries < prm.max_tries);
-        ++iterations;
-        if (tries >= prm.max_tries || !good) ok = false;       // Terminate
+        }
+        if (after_reject) {
+            if (tries < prm.max_tries) decide = true;
+            else { ++iterations; break; }                    // Terminate: no good step in max_tries tries
+            ++tries;
+        }
+        if (start_iter) {
+            if (it >= max_iter) break;
+            if (prm.early_accept && !want_info && cur_chi <= th) break;   // every edge chi2 <= sum <= th, and the sum only decreases
+            have_norm = false; have_sd = false; tries = 1;
+            decide = true;
+        }
+        if (decide) {
+            if (!have_norm) {
+                if (prm.speculate && prev_hnorm >= 0 && 4 * prev_hnorm < delta) {
+                    linearGain = cur_chi - M.U()->sol.model;
+                    mode = STEP_GN; purpose = P_TRIAL_SPEC; c1 = 0; c2 = 1;
+                    continue;
+                }
+                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; }
+                hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); have_norm = true;
+            }
+            if (hgnNorm < delta) {
+                linearGain = cur_chi - M.U()->sol.model;     // predicted gain of the GN step of the current linearisation
+                mode = STEP_GN; purpose = P_TRIAL_GN; c1 = 0; c2 = 1;
+                continue;
+            }
+            if (!have_sd) {
+                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; }
+                sd_sweeps<NT, UNI>(M, O, ts, bb, bh, hh, bHb); n_sweeps += 2;
+                alpha = bb / bHb;
+                hsdNorm = alpha * sqrt(bb);
+                have_sd = true;
+            }
+            if (hsdNorm > delta) { c1 = delta / hsdNorm * alpha; c2 = 0; }
+            else {
+                const double hsdSq = alpha * alpha * bb;
+                const double c = alpha * bh - hsdSq;                     // hsd . (hgn - hsd)
+                const double bma = hh - 2 * alpha * bh + hsdSq;           // |hgn - hsd|^2
+                double beta;
+                if (c <= 0) beta = (-c + sqrt(c * c + bma * (delta * delta - hsdSq))) / bma;
+                else beta = (delta * delta - hsdSq) / (c + sqrt(c * c + bma * (delta * delta - hsdSq)));
+                c1 = alpha * (1 - beta); c2 = beta;
+            }
+            // H h_gn = b  =>  h^T H h = c1^2 bHb + 2 c1 c2 bb + c2^2 bh,  b^T h = c1 bb + c2 bh
+            linearGain = -(c1 * c1 * bHb + 2 * c1 * c2 * bb + c2 * c2 * bh) + 2 * (c1 * bb + c2 * bh);
+            mode = STEP_BLEND; purpose = P_TRIAL_BLEND;
+            continue;
+        }
+        break;
     }
     res.verdict = (cur_max > th) ? 0 : 1;                      // every edge chi2 <= th (src/consensus_utils.cpp:17-19)
     res.max_chi2 = cur_max; res.cand_chi2 = cand_chi; res.sum_chi2 = cur_chi;
-    res.iterations = iterations; res.evals = evals; res.window_len = L; res.n_loops = g.K; res.n_sweeps = n_sweeps;
+    res.iterations = iterations; res.evals = evals; res.window_len = L; res.n_loops = K; res.n_sweeps = n_sweeps;
 }
 
 }  // namespace ipcb

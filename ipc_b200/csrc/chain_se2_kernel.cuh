@@ -10,14 +10,10 @@ template <int NT, int MODE, bool UNI>
 __global__ void __launch_bounds__(NT, 512 / NT) chain_check_se2(BatchArgs A) {
     extern __shared__ __align__(16) double sm[];
     const int capv = A.Lcap + 2;
-    ChainMem M;
-    chain_mem_small(M, sm);
     double* scr = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
-    M.BX = scr; M.BY = scr + capv; M.BT = scr + 2 * (size_t)capv;
-#pragma unroll
-    for (int q = 0; q < 3; ++q) { M.GB[q] = scr + (size_t)(3 + q) * capv; M.GH[q] = scr + (size_t)(6 + q) * capv; }
-    double* st = (MODE == 0) ? sm + CHAIN_SMALL_DOUBLES : scr + (size_t)CHAIN_SCRATCH_ARRAYS * capv;
-    M.X = st; M.Y = st + capv; M.TH = st + 2 * (size_t)capv; M.CS = st + 3 * (size_t)capv; M.SN = st + 4 * (size_t)capv;
+    ChainMem M;
+    M.small = sm; M.scr = scr; M.capv = capv;
+    M.st = (MODE == 0) ? sm + CHAIN_SMALL_DOUBLES : scr + (size_t)CHAIN_SCRATCH_ARRAYS * capv;
     const LoopRec2* loops = static_cast<const LoopRec2*>(A.loops);
     CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept};
     const int n_work = *A.n_work;
@@ -25,7 +21,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) chain_check_se2(BatchArgs A) {
         const int chk = A.work[wi];
         const int midx = A.member[chk];
         CheckResult r;
-        run_check<NT, UNI>(M, A.odom, (size_t)A.n_pad, A.Du, A.Vu, loops + A.cand[chk], midx >= 0 ? loops + midx : nullptr, prm, A.info != nullptr, r);
+        run_check<NT, UNI>(M, A.odom, A.Du, A.Vu, loops + A.cand[chk], midx >= 0 ? loops + midx : nullptr, prm, A.info != nullptr, r);
         if (threadIdx.x == 0) {
             A.verdict[chk] = (unsigned char)r.verdict;
             if (A.info) {

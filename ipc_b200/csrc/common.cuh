@@ -17,7 +17,7 @@ struct LoopRec2 {
 };
 
 struct BatchArgs {
-    const double* odom;        // SoA: NCOMP component arrays of length n_pad
+    const double* odom;        // AoS odometry records: 3 doubles / edge (UNI kernels) or 9 doubles / edge
     int n_pad;
     double Du[6], Vu[6];       // uniform-information specialisation (kernels instantiated with UNI = true)
     const void* loops;         // LoopRec2 / LoopRec3

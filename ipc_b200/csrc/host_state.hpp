@@ -76,21 +76,20 @@ struct HostState {
         V[3] = (D[0] * D[5] - D[2] * D[2]) * id; V[4] = (D[1] * D[2] - D[0] * D[4]) * id; V[5] = (D[0] * D[3] - D[1] * D[1]) * id;
     }
 
-    // SoA layout in HBM: component c of edge k at soa[c * n_pad + k]; SE2: zx zy zt d00 d01 d02 d11 d12 d22
-    void build_odom_soa(int n_pad, std::vector<double>& soa) const {
-        if (dim == 2) {
-            soa.assign((size_t)9 * n_pad, 0.0);
-            for (int k = 0; k + 1 < n; ++k) {
+    // AoS layout in HBM: (zx zy zt) per edge when uniform_iso (24 B), else (zx zy zt d00 d01 d02 d11 d12 d22) (72 B)
+    int odom_rec_doubles(bool uni) const { return uni ? 3 : 9; }
+    void build_odom_aos(bool uni, int n_pad, std::vector<double>& rec) const {
+        const int w = odom_rec_doubles(uni);
+        rec.assign((size_t)w * n_pad, 0.0);
+        if (dim != 2) { rec.clear(); return; }
+        for (int k = 0; k < n_pad; ++k) {
+            double* r = &rec[(size_t)k * w];
+            if (k + 1 < n) {
                 double z[3], D[6];
                 se2_edge_record(&odom_meas[(size_t)k * 3], &odom_info[(size_t)k * 9], 1.0, z, D);
-                if (uniform_iso) for (int c = 0; c < 6; ++c) D[c] = Du[c];
-                for (int c = 0; c < 3; ++c) soa[(size_t)c * n_pad + k] = z[c];
-                for (int c = 0; c < 6; ++c) soa[(size_t)(3 + c) * n_pad + k] = D[c];
-            }
-            // padding entries keep D = identity so stray reads stay finite
-            for (int k = n - 1; k < n_pad; ++k) { soa[(size_t)3 * n_pad + k] = 1; soa[(size_t)6 * n_pad + k] = 1; soa[(size_t)8 * n_pad + k] = 1; }
-        } else {
-            soa.clear();
+                for (int c = 0; c < 3; ++c) r[c] = z[c];
+                if (!uni) for (int c = 0; c < 6; ++c) r[3 + c] = D[c];
+            } else if (!uni) { r[3] = 1; r[6] = 1; r[8] = 1; }   // padding entries keep D = identity so stray reads stay finite
         }
     }
 

@@ -118,7 +118,8 @@ struct ipc_handle {
     int use_uniform = 1;              // allow the uniform-information kernels when the graph qualifies
     HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
     // device graph
-    double* d_odom = nullptr;         // SoA components
+    double* d_odom9 = nullptr;        // AoS odometry records, general (9 doubles / edge)
+    double* d_odom3 = nullptr;        // AoS odometry records, uniform isotropic information (3 doubles / edge); null if not applicable
     void* d_loops = nullptr;  int n_loops = 0;
     std::vector<int> h_lfrom, h_lto;  // host copy of candidate endpoints
     std::vector<double> h_lmeas, h_linfo;
@@ -172,8 +173,8 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         if (lo_cap >= h->n - 1) break;                 // no window can be this long
         BatchArgs a{};
         for (int c = 0; c < 6; ++c) { a.Du[c] = h->hs.Du[c]; a.Vu[c] = h->hs.Vu[c]; }
-        const bool uni = h->hs.uniform_iso && h->use_uniform;
-        a.odom = h->d_odom; a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
+        const bool uni = h->hs.uniform_iso && h->use_uniform && h->d_odom3;
+        a.odom = uni ? h->d_odom3 : h->d_odom9; a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
         a.work = work_dev + (size_t)b * work_stride; a.n_work = h->d_counts + b;
         a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
@@ -236,11 +237,16 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     h->n_sm = prop.multiProcessorCount;
     std::string err;
     if (!h->hs.init(dim, n_poses, odom_meas, odom_info, cfg->s_factor, err)) { delete h; return fail(IPC_ERR_ARG, err); }
-    // device SoA odometry records
-    std::vector<double> soa;
-    h->hs.build_odom_soa(h->n_pad, soa);
-    CUDA_TRY(cudaMalloc(&h->d_odom, soa.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(h->d_odom, soa.data(), soa.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // device odometry records
+    std::vector<double> rec;
+    h->hs.build_odom_aos(false, h->n_pad, rec);
+    CUDA_TRY(cudaMalloc(&h->d_odom9, rec.size() * sizeof(double)));
+    CUDA_TRY(cudaMemcpy(h->d_odom9, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (h->hs.uniform_iso) {
+        h->hs.build_odom_aos(true, h->n_pad, rec);
+        CUDA_TRY(cudaMalloc(&h->d_odom3, rec.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(h->d_odom3, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY(cudaMalloc(&h->d_counts, sizeof(int) * NB));
     CUDA_TRY(cudaMalloc(&h->d_bucket_cap, sizeof(int) * NB));
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * 2));
@@ -271,7 +277,7 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
 void ipc_destroy(ipc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_odom); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
+    cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ev_k0) cudaEventDestroy(h->ev_k0);

@@ -17,7 +17,8 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
     HostState hs; std::string err;
     if (!hs.init(2, n_poses, odom_meas, odom_info, s_factor, err)) return -1;
     const int n_pad = (n_poses + 3) & ~1;
-    std::vector<double> soa; hs.build_odom_soa(n_pad, soa);
+    const bool uni = hs.uniform_iso && use_uni;
+    std::vector<double> soa; hs.build_odom_aos(uni, n_pad, soa);
     std::vector<LoopRec2> recs(n_loops);
     for (int i = 0; i < n_loops; ++i) { recs[i].from = lfrom[i]; recs[i].to = lto[i]; HostState::se2_edge_record(lmeas + 3 * i, linfo + 9 * i, 1.0, recs[i].meas, recs[i].D); HostState::inv_sym3_host(recs[i].D, recs[i].V); }
     CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept};
@@ -26,15 +27,13 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
         const int capv = n_poses + 2;
         std::vector<double> buf((size_t)(CHAIN_STATE_ARRAYS + CHAIN_SCRATCH_ARRAYS) * capv + CHAIN_SMALL_DOUBLES, 0.0);
         ChainMem M; double* p = buf.data();
-        chain_mem_small(M, p); p += CHAIN_SMALL_DOUBLES;
-        M.X = p; M.Y = p + capv; M.TH = p + 2 * capv; M.CS = p + 3 * capv; M.SN = p + 4 * capv; p += (size_t)CHAIN_STATE_ARRAYS * capv;
-        M.BX = p; M.BY = p + capv; M.BT = p + 2 * capv; for (int q = 0; q < 3; ++q) { M.GB[q] = p + (3 + q) * (size_t)capv; M.GH[q] = p + (6 + q) * (size_t)capv; }
+        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN_STATE_ARRAYS * capv; M.capv = capv;
         for (;;) {
             int c = next.fetch_add(1);
             if (c >= n_checks) break;
             CheckResult r;
-            if (hs.uniform_iso && use_uni) run_check<1, true>(M, soa.data(), (size_t)n_pad, hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
-            else run_check<1, false>(M, soa.data(), (size_t)n_pad, hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+            if (uni) run_check<1, true>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+            else run_check<1, false>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
             verdict[c] = (unsigned char)r.verdict;
             if (info) { info[c].max_chi2 = r.max_chi2; info[c].cand_chi2 = r.cand_chi2; info[c].sum_chi2 = r.sum_chi2; info[c].iterations = r.iterations;
                         info[c].evals = r.evals; info[c].window_len = r.window_len; info[c].n_loops = r.n_loops; }
