@@ -17,7 +17,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) chain_check_se2(BatchArgs A) {
     const LoopRec2* loops = static_cast<const LoopRec2*>(A.loops);
     CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept};
     const int n_work = *A.n_work;
-    for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    __shared__ int s_wi;
+    for (;;) {
+        // dynamic claim: checks differ by 30x in cost (window length x Dogleg iterations), a static split leaves SMs idle
+        if (threadIdx.x == 0) s_wi = atomicAdd(A.next, 1);
+        if (NT <= 32) __syncwarp(); else __syncthreads();
+        const int wi = s_wi;
+        if (wi >= n_work) break;
         const int chk = A.work[wi];
         const int midx = A.member[chk];
         CheckResult r;

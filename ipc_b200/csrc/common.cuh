@@ -25,6 +25,7 @@ struct BatchArgs {
     const int* cand;           // per check: candidate loop index
     const int* work;           // check ids handled by this launch (sorted by window length, longest first)
     const int* n_work;         // device counter: number of entries in `work`
+    int* next;                 // device counter: next unclaimed entry of `work` (CTAs claim checks dynamically)
     double* scratch;           // per-CTA global scratch (pose backup, gradient, h_gn; MODE 1: the state arrays too)
     size_t scratch_stride;     // doubles per CTA
     int Lcap;                  // capacity (edges) of the per-vertex arrays, even

@@ -10,6 +10,7 @@
 
 #include "chain_se2_kernel.cuh"
 #include "host_state.hpp"
+#include "matrix.cuh"
 
 using namespace ipcb;
 
@@ -92,7 +93,7 @@ template <int NT, int MODE, bool UNI> int launch_se2u(const BatchArgs& a, int gr
     size_t sm = smem_bytes(MODE, a.Lcap);
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_done = true;
     }
     chain_check_se2<NT, MODE, UNI><<<grid, NT, sm, st>>>(a);
@@ -159,7 +160,7 @@ int ensure_batch_buffers(ipc_handle* h, int n_checks) {
 int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev, int* work_dev, int work_stride,
                   unsigned char* verdict_dev, uint32_t* bits_dev, ipc_check_info* info_dev, cudaStream_t st) {
     if (h->dim != 2) return fail(IPC_ERR_UNSUPPORTED, "SE(3) batch kernel not built in this revision");
-    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, sizeof(int) * NB, st));
+    CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * NB, st));
     CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * 2, st));
     const int loop_stride_ints = (int)(sizeof(LoopRec2) / sizeof(int));
     plan_checks<<<(n_checks + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int*>(h->d_loops), loop_stride_ints, n_checks, member_dev, cand_dev,
@@ -175,7 +176,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         for (int c = 0; c < 6; ++c) { a.Du[c] = h->hs.Du[c]; a.Vu[c] = h->hs.Vu[c]; }
         const bool uni = h->hs.uniform_iso && h->use_uniform && h->d_odom3;
         a.odom = uni ? h->d_odom3 : h->d_odom9; a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
-        a.work = work_dev + (size_t)b * work_stride; a.n_work = h->d_counts + b;
+        a.work = work_dev + (size_t)b * work_stride; a.n_work = h->d_counts + b; a.next = h->d_counts + NB + b;
         a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
         a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
@@ -247,7 +248,7 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
         CUDA_TRY(cudaMalloc(&h->d_odom3, rec.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(h->d_odom3, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMalloc(&h->d_counts, sizeof(int) * NB));
+    CUDA_TRY(cudaMalloc(&h->d_counts, sizeof(int) * 2 * NB));
     CUDA_TRY(cudaMalloc(&h->d_bucket_cap, sizeof(int) * NB));
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * 2));
     int caps[NB];
@@ -403,7 +404,77 @@ int ipc_agreement_check(ipc_handle*, int, int, const double*, const double*, int
     return fail(IPC_ERR_UNSUPPORTED, "stateful agreementCheck not built in this revision");
 }
 int ipc_get_poses(ipc_handle*, double*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
-int ipc_consistency_matrix(ipc_handle*, uint32_t*, int*, int64_t*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
-int ipc_greedy_consensus(ipc_handle*, const uint32_t*, int, unsigned char*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
+int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved) {
+    if (!h || !rows_bits) return fail(IPC_ERR_ARG, "null argument");
+    if (!h->d_loops || h->n_loops <= 0) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int n = h->n_loops, words = (n + 31) / 32;
+    // candidate order of src/simulation.cpp:26 (cmpTime), stable over file order
+    std::vector<int> order(n), lo(n), hi(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::max(h->h_lfrom[a], h->h_lto[a]) < std::max(h->h_lfrom[b], h->h_lto[b]); });
+    for (int i = 0; i < n; ++i) { lo[i] = std::min(h->h_lfrom[order[i]], h->h_lto[order[i]]); hi[i] = std::max(h->h_lfrom[order[i]], h->h_lto[order[i]]); }
+    cudaStream_t st = h->stream;
+    int *d_lo = nullptr, *d_hi = nullptr, *d_order = nullptr, *d_cnt = nullptr, *d_rowptr = nullptr, *d_total = nullptr;
+    int *d_member = nullptr, *d_cand = nullptr, *d_pi = nullptr, *d_pj = nullptr, *d_work = nullptr;
+    unsigned char* d_verdict = nullptr; uint32_t* d_rows = nullptr;
+    auto cleanup = [&]() { cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_order); cudaFree(d_cnt); cudaFree(d_rowptr); cudaFree(d_total); cudaFree(d_member);
+                           cudaFree(d_cand); cudaFree(d_pi); cudaFree(d_pj); cudaFree(d_work); cudaFree(d_verdict); cudaFree(d_rows); };
+#define MTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return fail(IPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } } while (0)
+    MTRY(cudaMalloc(&d_lo, sizeof(int) * n)); MTRY(cudaMalloc(&d_hi, sizeof(int) * n)); MTRY(cudaMalloc(&d_order, sizeof(int) * n));
+    MTRY(cudaMalloc(&d_cnt, sizeof(int) * n)); MTRY(cudaMalloc(&d_rowptr, sizeof(int) * n)); MTRY(cudaMalloc(&d_total, sizeof(int)));
+    MTRY(cudaMemcpyAsync(d_lo, lo.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    MTRY(cudaMemcpyAsync(d_hi, hi.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    MTRY(cudaMemcpyAsync(d_order, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    overlap_count<<<n, 256, 0, st>>>(d_lo, d_hi, n, d_cnt);
+    row_offsets<<<1, 1024, 0, st>>>(d_cnt, n, n, d_rowptr, d_total);
+    int total = 0;
+    MTRY(cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MTRY(cudaStreamSynchronize(st));
+    const int n_checks = total;           // n diagonal checks + overlapping pairs
+    MTRY(cudaMalloc(&d_member, sizeof(int) * n_checks)); MTRY(cudaMalloc(&d_cand, sizeof(int) * n_checks));
+    MTRY(cudaMalloc(&d_pi, sizeof(int) * n_checks)); MTRY(cudaMalloc(&d_pj, sizeof(int) * n_checks));
+    MTRY(cudaMalloc(&d_work, sizeof(int) * (size_t)n_checks * NB)); MTRY(cudaMalloc(&d_verdict, n_checks));
+    MTRY(cudaMalloc(&d_rows, sizeof(uint32_t) * (size_t)n * words));
+    overlap_fill<<<n, 256, 0, st>>>(d_lo, d_hi, d_order, n, d_rowptr, d_member, d_cand, d_pi, d_pj);
+    MTRY(cudaGetLastError());
+    int rc = enqueue_batch(h, n_checks, d_member, d_cand, d_work, n_checks, d_verdict, nullptr, nullptr, st);
+    if (rc != IPC_OK) { cleanup(); return rc; }
+    {
+        const long long warps = (long long)n * words;
+        const int threads = 256;
+        const long long blocks = (warps * 32 + threads - 1) / threads;
+        matrix_init<<<(unsigned)blocks, threads, 0, st>>>(d_lo, d_hi, d_verdict, n, words, d_rows);
+        if (n_checks > n) matrix_scatter<<<(n_checks - n + 255) / 256, 256, 0, st>>>(d_verdict, d_pi, d_pj, n, n_checks, words, d_rows);
+        MTRY(cudaGetLastError());
+        h->last_launches += 5;
+    }
+    MTRY(cudaMemcpyAsync(rows_bits, d_rows, sizeof(uint32_t) * (size_t)n * words, cudaMemcpyDeviceToHost, st));
+    MTRY(cudaStreamSynchronize(st));
+#undef MTRY
+    cleanup();
+    if (order_out) std::copy(order.begin(), order.end(), order_out);
+    if (n_solved) *n_solved = n_checks;
+    return IPC_OK;
+}
+
+int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsigned char* in_set) {
+    if (!h || !rows_bits || !in_set || n < 0) return fail(IPC_ERR_ARG, "bad arguments");
+    if (n == 0) return IPC_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int words = (n + 31) / 32;
+    uint32_t *d_rows = nullptr, *d_S = nullptr; unsigned char* d_in = nullptr;
+    auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_S); cudaFree(d_in); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_rows, sizeof(uint32_t) * (size_t)n * words)) != cudaSuccess || (e = cudaMalloc(&d_S, sizeof(uint32_t) * words)) != cudaSuccess ||
+        (e = cudaMalloc(&d_in, n)) != cudaSuccess) { cleanup(); return fail(IPC_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpyAsync(d_rows, rows_bits, sizeof(uint32_t) * (size_t)n * words, cudaMemcpyHostToDevice, h->stream);
+    greedy_consensus<<<1, 512, 0, h->stream>>>(d_rows, n, words, d_S, d_in);
+    cudaMemcpyAsync(in_set, d_in, n, cudaMemcpyDeviceToHost, h->stream);
+    e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(IPC_ERR_CUDA, cudaGetErrorString(e));
+    return IPC_OK;
+}
 
 }  // extern "C"

@@ -107,3 +107,43 @@ def test_full_size_properties(gpu_lib):
     acc_p2, info_p2 = ipc2.check_batch(m, c)
     assert np.array_equal(acc_p, acc_p2) and np.array_equal(info_p["max_chi2"], info_p2["max_chi2"])
     ipc.close(); ipc2.close()
+
+
+def _unpack(rows, n):
+    return ((rows[:, np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(bool)
+
+
+def test_consistency_matrix_and_greedy_consensus(gpu_lib, oracle_lib):
+    """N_c x N_c matrix (diagonal = fast check, overlapping pairs = K = 2 check, others = AND of the diagonals) against the
+    oracle's verdicts for every solved check, and the row-AND + popcount greedy growth against a numpy restatement."""
+    g, cfg = synth.make_config("intel", scale=0.3)
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    rows, order, solved = ipc.consistency_matrix()
+    n = g.n_loops
+    assert np.array_equal(order, g.time_order())
+    mem, cnd = api.pair_checks(g)
+    assert solved == len(cnd)
+    ptr, idx = api.checks_to_csr(mem, cnd)
+    oacc, _ = oracle_lib.OracleIPC(g, cfg).check_batch(ptr, idx, n_threads=os.cpu_count())
+    pos = np.empty(n, dtype=np.int64); pos[order] = np.arange(n)
+    want = np.zeros((n, n), dtype=bool)
+    diag = np.zeros(n, dtype=bool)
+    for m, c, a in zip(mem, cnd, oacc):
+        if m < 0:
+            diag[pos[c]] = a
+    want = np.logical_and.outer(diag, diag)
+    for m, c, a in zip(mem, cnd, oacc):
+        if m >= 0:
+            want[pos[m], pos[c]] = want[pos[c], pos[m]] = a
+    want[np.arange(n), np.arange(n)] = diag
+    got = _unpack(rows, n)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got, got.T)
+    in_set = ipc.greedy_consensus(rows)
+    S = []
+    ref = np.zeros(n, dtype=bool)
+    for k in range(n):
+        if want[k, k] and all(want[k, s] for s in S):
+            S.append(k); ref[k] = True
+    assert np.array_equal(in_set, ref)
+    ipc.close()
