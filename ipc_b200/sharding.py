@@ -1,0 +1,85 @@
+"""Sharding of independent checks across the GPUs of one box.
+
+Fast and pair checks are independent units (each starts from the dead-reckoned state), so the check list is dealt to the
+ranks by estimated cost (window length, longest first, round robin) with NO data-path collective; the only exchange step is
+ONE all_gather of the packed verdict words (N_c^2 / 8 bytes in total for a whole consistency matrix: latency bound), after
+which every rank holds every verdict. One process per GPU, `torch.distributed` (nccl on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def window_lengths(graph, member, cand):
+    """L = hi - lo of every check (union window when the member overlaps, src/consensus.cpp:157-159)."""
+    a = np.minimum(graph.loop_from, graph.loop_to)
+    b = np.maximum(graph.loop_from, graph.loop_to)
+    member, cand = np.asarray(member), np.asarray(cand)
+    m = np.where(member >= 0, member, cand)
+    ov = (member >= 0) & ((np.minimum(b[m], b[cand]) - np.maximum(a[m], a[cand])) > 0)
+    lo = np.where(ov, np.minimum(a[m], a[cand]), a[cand])
+    hi = np.where(ov, np.maximum(b[m], b[cand]), b[cand])
+    return (hi - lo).astype(np.int64)
+
+
+def partition(cost, world: int, rank: int) -> np.ndarray:
+    """Indices of the checks owned by `rank`: sort by cost (descending, stable), deal round robin. Deterministic, and the
+    union over ranks is a permutation of range(len(cost))."""
+    order = np.argsort(-np.asarray(cost), kind="stable")
+    return np.sort(order[rank::world])
+
+
+def pack_bits(v: np.ndarray) -> np.ndarray:
+    n = len(v)
+    words = np.zeros((n + 31) // 32, dtype=np.uint32)
+    idx = np.nonzero(v)[0]
+    np.bitwise_or.at(words, idx >> 5, (np.uint32(1) << (idx & 31).astype(np.uint32)))
+    return words
+
+
+def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
+    i = np.arange(n)
+    return ((words[i >> 5] >> (i & 31).astype(np.uint32)) & 1).astype(bool)
+
+
+def sharded_verdicts(cost, compute_local, world: int, rank: int, dist=None, device=None):
+    """Run `compute_local(indices) -> bool verdicts` on this rank's shard and all_gather the packed words.
+    Returns the verdict of every check (same array on every rank)."""
+    n = len(cost)
+    mine = partition(cost, world, rank)
+    local = np.asarray(compute_local(mine), dtype=bool)
+    if world == 1 or dist is None:
+        out = np.zeros(n, dtype=bool)
+        out[mine] = local
+        return out
+    import torch
+    per = (n + world - 1) // world                       # every shard has per or per - 1 entries: pad to `per`
+    words = (per + 31) // 32
+    buf = torch.zeros(words, dtype=torch.int32, device=device)
+    buf[: (len(local) + 31) // 32] = torch.from_numpy(pack_bits(local).view(np.int32)).to(device)
+    gathered = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(gathered, buf)                       # the single collective of the path
+    out = np.zeros(n, dtype=bool)
+    for r in range(world):
+        idx = partition(cost, world, r)
+        out[idx] = unpack_bits(gathered[r].cpu().numpy().view(np.uint32), len(idx))
+    return out
+
+
+def matrix_from_verdicts(graph, member, cand, verdict, order=None):
+    """Dense boolean consistency matrix in time order from the verdicts of the solved checks (diagonal = fast check,
+    overlapping pair = its K = 2 check, anything else = AND of the two diagonals)."""
+    order = graph.time_order() if order is None else np.asarray(order)
+    n = len(order)
+    pos = np.empty(graph.n_loops, dtype=np.int64)
+    pos[order] = np.arange(n)
+    member, cand, verdict = np.asarray(member), np.asarray(cand), np.asarray(verdict, dtype=bool)
+    diag = np.zeros(n, dtype=bool)
+    d = member < 0
+    diag[pos[cand[d]]] = verdict[d]
+    M = np.logical_and.outer(diag, diag)
+    p = ~d
+    M[pos[member[p]], pos[cand[p]]] = verdict[p]
+    M[pos[cand[p]], pos[member[p]]] = verdict[p]
+    M[np.arange(n), np.arange(n)] = diag
+    return M
