@@ -152,6 +152,7 @@ def run_reference(args):
 
 
 def run_ours(args):
+    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
     from ipc_b200 import api

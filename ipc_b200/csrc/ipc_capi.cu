@@ -11,6 +11,8 @@
 #include "chain_se2_kernel.cuh"
 #include "host_state.hpp"
 #include "matrix.cuh"
+#include "cluster_se2.cuh"
+#include <cusolverDn.h>
 
 using namespace ipcb;
 
@@ -134,6 +136,15 @@ struct ipc_handle {
     double* d_scratch = nullptr; size_t scratch_doubles = 0;   // per-CTA scratch, shared by the (serialised) bucket launches
     int last_launches = 0;
     cudaStream_t stream = nullptr;
+    // ---- sequential stream (stateful agreementCheck): global pose state + cluster-solve work buffers
+    double* d_pose = nullptr;         // AoS[5] x n: x y theta cos sin — the vertex estimates of the IPC object
+    cusolverDnHandle_t solver = nullptr;
+    int cl_Lcap = 0, cl_Kcap = 0, cl_work_n = 0;
+    ClBuffers clB[2] = {};
+    double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_work = nullptr;
+    int* cl_info = nullptr;
+    ClLoop* cl_loops = nullptr;
+    double* cl_hres = nullptr;        // pinned
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
     bool ev_valid = false;
 };
@@ -269,6 +280,18 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
         CUDA_TRY(cudaMalloc(&h->d_scratch, need * sizeof(double)));
     }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    if (dim == 2) {   // IPC::IPC: vertex 0 at the origin, everything else dead-reckoned (propagateGuess, src/consensus_utils.cpp:98-116)
+        CUDA_TRY(cudaMalloc(&h->d_pose, sizeof(double) * 5 * (size_t)n_poses));
+        cl_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
+        cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, 0, n_poses, h->d_pose);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMallocHost(&h->cl_hres, sizeof(double) * CL_NRES));
+        CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES));
+        CUDA_TRY(cudaMalloc(&h->cl_info, sizeof(int)));
+        if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(IPC_ERR_CUDA, "cusolverDnCreate failed");
+        cusolverDnSetStream(h->solver, h->stream);
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
     CUDA_TRY(cudaEventCreate(&h->ev_k0));
     CUDA_TRY(cudaEventCreate(&h->ev_k1));
     *out = h;
@@ -280,6 +303,11 @@ void ipc_destroy(ipc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
+    cudaFree(h->d_pose); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
+    cudaFree(h->cl_info); cudaFree(h->cl_loops);
+    for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
+    if (h->cl_hres) cudaFreeHost(h->cl_hres);
+    if (h->solver) cusolverDnDestroy(h->solver);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ev_k0) cudaEventDestroy(h->ev_k0);
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
@@ -400,10 +428,190 @@ int ipc_get_consensus(ipc_handle* h, int* from_to, int capacity) {
     return IPC_OK;
 }
 
-int ipc_agreement_check(ipc_handle*, int, int, const double*, const double*, int*, ipc_check_info*) {
-    return fail(IPC_ERR_UNSUPPORTED, "stateful agreementCheck not built in this revision");
+namespace {
+
+int cl_ensure(ipc_handle* h, int L, int K) {
+    if (L > h->cl_Lcap) {
+        int cap = std::max(L, 256);
+        for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); h->clB[q].W = h->clB[q].T = h->clB[q].P = h->clB[q].chi_e = nullptr; }
+        cudaFree(h->cl_G); cudaFree(h->cl_H); h->cl_G = h->cl_H = nullptr; h->cl_Lcap = 0;
+        for (int q = 0; q < 2; ++q) {
+            CUDA_TRY(cudaMalloc(&h->clB[q].W, sizeof(double) * 5 * (size_t)(cap + 1)));
+            CUDA_TRY(cudaMalloc(&h->clB[q].T, sizeof(double) * NPRE * (size_t)cap));
+            CUDA_TRY(cudaMalloc(&h->clB[q].P, sizeof(double) * NPRE * (size_t)(cap + 1)));
+            CUDA_TRY(cudaMalloc(&h->clB[q].chi_e, sizeof(double) * (size_t)cap));
+        }
+        CUDA_TRY(cudaMalloc(&h->cl_G, sizeof(double) * 3 * (size_t)(cap + 1)));
+        CUDA_TRY(cudaMalloc(&h->cl_H, sizeof(double) * 3 * (size_t)(cap + 1)));
+        h->cl_Lcap = cap;
+    }
+    if (K > h->cl_Kcap) {
+        int cap = std::max(K + K / 2, 64);
+        for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].lt); h->clB[q].lt = nullptr; }
+        cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_loops); cudaFree(h->cl_work); h->cl_S = h->cl_z = h->cl_work = nullptr; h->cl_loops = nullptr; h->cl_Kcap = 0;
+        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&h->clB[q].lt, sizeof(double) * 12 * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&h->cl_S, sizeof(double) * 9 * (size_t)cap * cap));
+        CUDA_TRY(cudaMalloc(&h->cl_z, sizeof(double) * 3 * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&h->cl_loops, sizeof(ClLoop) * (size_t)cap));
+        int lwork = 0;
+        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, 3 * cap, h->cl_S, 3 * cap, &lwork) != CUSOLVER_STATUS_SUCCESS)
+            return fail(IPC_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
+        CUDA_TRY(cudaMalloc(&h->cl_work, sizeof(double) * (size_t)std::max(lwork, 1)));
+        h->cl_work_n = lwork; h->cl_Kcap = cap;
+    }
+    return IPC_OK;
 }
-int ipc_get_poses(ipc_handle*, double*) { return fail(IPC_ERR_UNSUPPORTED, "not built in this revision"); }
+
+int cl_read(ipc_handle* h) {   // device scalars -> pinned host buffer
+    CUDA_TRY(cudaMemcpyAsync(h->cl_hres, h->cl_res, sizeof(double) * CL_NRES, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return IPC_OK;
+}
+
+// isAgreeingWithCurrentState on the window [lo, hi] with the K loops already uploaded (the candidate is the last one)
+int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_base, bool* ok_out, ipc_check_info* info, int* cur_buf) {
+    const int L = hi - lo, Lcap = h->cl_Lcap;
+    cudaStream_t st = h->stream;
+    int cur = 0;
+    double* res = h->cl_res;
+    const double* hr = h->cl_hres;
+    cl_load_window<<<16, 256, 0, st>>>(h->d_pose, lo, L, h->clB[0].W);
+    cl_linearize<<<1, CL_NT, 0, st>>>(h->d_odom9, lo, L, Lcap, h->clB[cur], res);
+    cl_loops<<<1, 256, 0, st>>>(h->cl_loops, K, h->clB[cur], res);
+    CUDA_TRY(cudaGetLastError());
+    int rc = cl_read(h); if (rc != IPC_OK) return rc;
+    double cur_chi = hr[0] + hr[2], cur_max = std::max(hr[1], hr[3]), cand_chi = hr[4];
+    int max_iter = iter_base;
+    if (L + K > 100) max_iter *= 5;                        // src/consensus_utils.cpp:12-13
+    double delta = 1e4;
+    int iterations = 0, evals = 0;
+    bool ok = true;
+    const int n3 = 3 * K;
+    for (int it = 0; it < max_iter && ok; ++it) {
+        // ---- Gauss-Newton step of the current linearisation
+        {
+            const long long nb = ((long long)K * K + 255) / 256;
+            cl_assemble<<<(unsigned)nb, 256, 0, st>>>(h->cl_loops, K, Lcap, h->clB[cur], h->cl_S, h->cl_z);
+            if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, n3, h->cl_S, n3, h->cl_work, h->cl_work_n, h->cl_info) != CUSOLVER_STATUS_SUCCESS)
+                return fail(IPC_ERR_CUDA, "cusolverDnDpotrf failed");
+            if (cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, n3, 1, h->cl_S, n3, h->cl_z, n3, h->cl_info) != CUSOLVER_STATUS_SUCCESS)
+                return fail(IPC_ERR_CUDA, "cusolverDnDpotrs failed");
+            cl_gn_step<<<1, CL_NT, 0, st>>>(h->cl_loops, K, L, Lcap, h->clB[cur], h->cl_z, h->cl_H, res);
+            CUDA_TRY(cudaGetLastError());
+            rc = cl_read(h); if (rc != IPC_OK) return rc;
+        }
+        const double hh = hr[5], hgnNorm = std::sqrt(hh), gn_gain = cur_chi - hr[6];
+        if (!std::isfinite(hgnNorm)) { ok = false; ++iterations; break; }     // factorisation broke down (g2o: Fail)
+        bool have_sd = false, good = false;
+        double bb = 0, bh = 0, bHb = 0, alpha = 0, hsdNorm = 0;
+        int tries = 0;
+        do {
+            ++tries;
+            double c1 = 0, c2 = 1, linearGain = gn_gain;
+            const bool trial_gn = hgnNorm < delta;
+            if (!trial_gn) {
+                if (!have_sd) {
+                    cl_grad_odom<<<1, CL_NT, 0, st>>>(h->d_odom9, lo, L, h->clB[cur], h->cl_G);
+                    cl_grad_loops<<<1, 32, 0, st>>>(h->cl_loops, K, h->clB[cur], h->cl_G);
+                    cl_sd_scalars<<<1, CL_NT, 0, st>>>(h->d_odom9, h->cl_loops, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
+                    CUDA_TRY(cudaGetLastError());
+                    rc = cl_read(h); if (rc != IPC_OK) return rc;
+                    bb = hr[7]; bh = hr[8]; bHb = hr[9];
+                    alpha = bb / bHb; hsdNorm = alpha * std::sqrt(bb); have_sd = true;
+                }
+                if (hsdNorm > delta) { c1 = delta / hsdNorm * alpha; c2 = 0; }
+                else {
+                    const double hsdSq = alpha * alpha * bb;
+                    const double c = alpha * bh - hsdSq, bma = hh - 2 * alpha * bh + hsdSq;
+                    double beta;
+                    if (c <= 0) beta = (-c + std::sqrt(c * c + bma * (delta * delta - hsdSq))) / bma;
+                    else beta = (delta * delta - hsdSq) / (c + std::sqrt(c * c + bma * (delta * delta - hsdSq)));
+                    c1 = alpha * (1 - beta); c2 = beta;
+                }
+                linearGain = -(c1 * c1 * bHb + 2 * c1 * c2 * bb + c2 * c2 * bh) + 2 * (c1 * bb + c2 * bh);
+            }
+            const int nxt = cur ^ 1;
+            cl_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
+            cl_linearize<<<1, CL_NT, 0, st>>>(h->d_odom9, lo, L, Lcap, h->clB[nxt], res);
+            cl_loops<<<1, 256, 0, st>>>(h->cl_loops, K, h->clB[nxt], res);
+            CUDA_TRY(cudaGetLastError());
+            rc = cl_read(h); if (rc != IPC_OK) return rc;
+            ++evals;
+            const double newChi = hr[0] + hr[2], hdlNorm = std::sqrt(hr[10]);
+            const double rawGain = linearGain;
+            if (std::fabs(linearGain) < 1e-12) linearGain = 1e-12;
+            const double rho = (cur_chi - newChi) / linearGain;
+            if (rho > 0) { good = true; cur = nxt; cur_chi = newChi; cur_max = std::max(hr[1], hr[3]); cand_chi = hr[4]; }
+            if (rho > 0.75) delta = std::max(delta, 3 * hdlNorm);
+            else if (rho < 0.25) delta *= 0.5;
+            if (!good) {
+                if (trial_gn) while (tries < h->max_tries && hgnNorm < delta) { ++tries; ++evals; delta *= 0.5; }
+                if (h->noise_eps > 0 && rawGain <= h->noise_eps * cur_chi + 1e-300) tries = h->max_tries;
+            }
+        } while (!good && tries < h->max_tries);
+        ++iterations;
+        if (tries >= h->max_tries || !good) ok = false;
+    }
+    *ok_out = !(cur_max > th);
+    *cur_buf = cur;
+    if (info) { info->max_chi2 = cur_max; info->cand_chi2 = cand_chi; info->sum_chi2 = cur_chi; info->iterations = iterations; info->evals = evals; info->window_len = L; info->n_loops = K; }
+    return IPC_OK;
+}
+
+}  // namespace
+
+int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, const double* info, int* accepted, ipc_check_info* out_info) {
+    if (!h || !meas || !info || !accepted) return fail(IPC_ERR_ARG, "null argument");
+    if (h->dim != 2) return fail(IPC_ERR_UNSUPPORTED, "SE(3) stream not built in this revision");
+    if (from < 0 || to < 0 || from >= h->n || to >= h->n || from == to) return fail(IPC_ERR_ARG, "invalid vertex ids");
+    CUDA_TRY(cudaSetDevice(h->device));
+    // computeIndependentSubgraph, src/consensus.cpp:123-171 (integer logic on the host mirror)
+    std::vector<int> members;
+    auto ext = h->hs.independent_subgraph(from, to, members);
+    const int lo = ext.first, hi = ext.second, K = (int)members.size() + 1;
+    const bool slow = !members.empty();
+    const double th = slow ? h->cfg.slow_reject_th : h->cfg.fast_reject_th;          // src/consensus.cpp:50-52
+    const int ib = slow ? h->cfg.slow_reject_iter_base : h->cfg.fast_reject_iter_base;
+    int rc = cl_ensure(h, hi - lo, K);
+    if (rc != IPC_OK) return rc;
+    std::vector<ClLoop> loops(K);
+    auto fill = [&](ClLoop& o, int f, int t, const double* m, const double* w) {
+        o.jf = f - lo; o.jt = t - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
+        HostState::se2_edge_record(m, w, 1.0, o.meas, o.D);
+        HostState::inv_sym3_host(o.D, o.V);
+    };
+    for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; fill(loops[i], e.from, e.to, e.meas.data(), e.info.data()); }
+    fill(loops[K - 1], from, to, meas, info);
+    CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice, h->stream));
+    bool ok = false; int cur = 0;
+    rc = cl_window_check(h, lo, hi, K, th, ib, &ok, out_info, &cur);
+    if (rc != IPC_OK) return rc;
+    *accepted = ok ? 1 : 0;
+    if (ok) {   // discard + push_back + propagateCurrentGuess (src/consensus.cpp:69-71); a rejection leaves d_pose untouched (restore)
+        cl_store_window<<<16, 256, 0, h->stream>>>(h->d_pose, lo, hi - lo, h->clB[cur].W);
+        cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, hi, h->n, h->d_pose);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + 3); e.info.assign(info, info + 9);
+        h->hs.cns.push_back(std::move(e));
+    }
+    return IPC_OK;
+}
+
+int ipc_get_poses(ipc_handle* h, double* out) {
+    if (!h || !out) return fail(IPC_ERR_ARG, "null argument");
+    if (h->dim != 2 || !h->d_pose) return fail(IPC_ERR_UNSUPPORTED, "SE(3) stream not built in this revision");
+    CUDA_TRY(cudaSetDevice(h->device));
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * 3 * (size_t)h->n));
+    cl_export_poses<<<64, 256, 0, h->stream>>>(h->d_pose, h->n, d_out);
+    cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * 3 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(IPC_ERR_CUDA, cudaGetErrorString(e));
+    return IPC_OK;
+}
+
 int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved) {
     if (!h || !rows_bits) return fail(IPC_ERR_ARG, "null argument");
     if (!h->d_loops || h->n_loops <= 0) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");

@@ -147,3 +147,40 @@ def test_consistency_matrix_and_greedy_consensus(gpu_lib, oracle_lib):
             S.append(k); ref[k] = True
     assert np.array_equal(in_set, ref)
     ipc.close()
+
+
+def _run_stream(ipc, g, order):
+    acc, mx, cc, K = [], [], [], []
+    for l in order:
+        ok, ci = ipc.agreementCheck((g.loop_from[l], g.loop_to[l], g.loop_meas[l], g.loop_info[l]))
+        acc.append(ok); mx.append(ci.max_chi2); cc.append(ci.cand_chi2); K.append(ci.n_loops)
+    return np.array(acc), np.array(mx), np.array(cc), np.array(K)
+
+
+def test_sequential_stream_matches_golden(gpu_lib):
+    """IPC::agreementCheck driven like simulating_incremental_data (src/simulation.cpp:34-47): clusters of K - 1 accepted
+    loops, commit / rollback, re-dead-reckoning after an accept. Inlier set bit-identical, chi2 within 1e-4, poses equal."""
+    z, g, cfg = load("stream_se2_intel.npz")
+    ipc = gpu_lib.IPC.from_graph(g, cfg, candidates=False)
+    acc, mx, cc, K = _run_stream(ipc, g, z["order"])
+    assert np.array_equal(acc, z["accept"])
+    assert np.array_equal(K, z["n_cluster"] + 1)
+    assert rel_err(mx, z["max_chi2"]).max() < CHI2_RTOL
+    assert np.array_equal(ipc.getMaxConsensusSet(), z["consensus"])
+    assert np.allclose(ipc.poses(), z["poses"], atol=1e-6)
+    ipc.close()
+
+
+def test_sequential_stream_matches_oracle_live(gpu_lib, oracle_lib):
+    g, cfg = synth.make_config("intel", scale=0.5)
+    oacc, orep = oracle_lib.OracleIPC(g, cfg, noise_exit=True).run_stream()
+    ipc = gpu_lib.IPC.from_graph(g, cfg, candidates=False)
+    acc, mx, cc, K = _run_stream(ipc, g, g.time_order())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(mx, orep["max_chi2"]).max() < CHI2_RTOL
+    assert K.max() > 10
+    # consensus-set edit API on the live object (src/consensus.cpp:77-121)
+    cs = ipc.getMaxConsensusSet()
+    assert ipc.removeEdgeFromCnS((cs[0][1], cs[0][0])) and not ipc.removeEdgeFromCnS((cs[0][0], cs[0][1]))
+    assert len(ipc.getMaxConsensusSet()) == len(cs) - 1
+    ipc.close()
