@@ -1,0 +1,251 @@
+// ipc_host.hpp — host side of the ipc_tester CLIs: flat YAML config, g2o-format graph files, trajectory / .PR output and the
+// incremental simulation loop, re-hosted over the C ABI (include/ipc_b200.h). Plain C++17, no third-party dependency
+// (the reference uses yaml-cpp and the g2o parser; neither is available offline).
+//
+// Reference sites mirrored (under /root/reference):
+//   struct Config / readConfig            include/ipc/utils.hpp:22-38, src/utils.cpp:316-337
+//   setProblem (load)                     src/utils.cpp:95-126        (optimizer.load: VERTEX_SE2 / EDGE_SE2 / *_SE3:QUAT / FIX)
+//   splitProblemConstraints               src/utils.cpp:172-189       (|id1 - id0| == 1 -> odometry, else loop; FILE order)
+//   simulating_incremental_data           src/simulation.cpp:8-108
+//   writeVertex / readSolutionFile        src/utils.cpp:239-282
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../include/ipc_b200.h"
+
+namespace ipc_host {
+
+// ---- Config (include/ipc/utils.hpp:22-38) -------------------------------------------------------------------------
+struct Config {
+    std::string name, dataset, ground_truth, output;
+    double s_factor = 1.0;
+    int visualize = 0;
+    int canonic_inliers = 0;
+    double fast_reject_th = 0, slow_reject_th = 0;
+    int fast_reject_iter_base = 0, slow_reject_iter_base = 0;
+    int use_best_k_buddies = 0, k_buddies = 0, use_recovery = 0;
+};
+
+inline std::string trim(const std::string& s) {
+    size_t a = s.find_first_not_of(" \t\r\n"), b = s.find_last_not_of(" \t\r\n");
+    return a == std::string::npos ? "" : s.substr(a, b - a + 1);
+}
+inline std::string unquote(std::string v) {
+    if (v.size() >= 2 && ((v.front() == '"' && v.back() == '"') || (v.front() == '\'' && v.back() == '\''))) v = v.substr(1, v.size() - 2);
+    return v;
+}
+inline bool parse_bool(const std::string& v) { std::string l = v; for (auto& c : l) c = (char)tolower(c); return l == "true" || l == "1" || l == "yes" || l == "on"; }
+
+// flat "key: value" YAML (all the reference's cfg/*.yaml files are flat scalars). Every key readConfig reads is required:
+// a missing one throws, like yaml-cpp's operator[] / as<T>() does in the reference.
+inline Config readConfig(const std::string& path) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot open config file " + path);
+    std::map<std::string, std::string> kv;
+    std::string line;
+    while (std::getline(f, line)) {
+        size_t h = line.find('#');
+        if (h != std::string::npos) line = line.substr(0, h);
+        size_t c = line.find(':');
+        if (c == std::string::npos) continue;
+        std::string k = trim(line.substr(0, c)), v = unquote(trim(line.substr(c + 1)));
+        if (!k.empty()) kv[k] = v;
+    }
+    auto need = [&](const char* k) -> const std::string& {
+        auto it = kv.find(k);
+        if (it == kv.end()) throw std::runtime_error(std::string("config key missing: ") + k);
+        return it->second;
+    };
+    Config c;
+    c.name = need("name"); c.dataset = need("dataset"); c.ground_truth = need("ground_truth"); c.output = need("output");
+    c.s_factor = std::stod(need("s_factor")); c.visualize = parse_bool(need("visualize"));
+    c.canonic_inliers = std::stoi(need("canonic_inliers"));
+    c.fast_reject_th = std::stod(need("fast_reject_th")); c.fast_reject_iter_base = std::stoi(need("fast_reject_iter_base"));
+    c.slow_reject_th = std::stod(need("slow_reject_th")); c.slow_reject_iter_base = std::stoi(need("slow_reject_iter_base"));
+    c.use_best_k_buddies = parse_bool(need("use_best_k_buddies")); c.k_buddies = std::stoi(need("k_buddies")); c.use_recovery = parse_bool(need("use_recovery"));
+    return c;
+}
+
+// ---- graph (g2o text format) --------------------------------------------------------------------------------------
+struct EdgeRec { int from, to; std::vector<double> meas, info; };   // meas 3 | 7, info d*d row-major full symmetric
+struct Graph {
+    int dim = 2;
+    std::vector<int> vertex_ids;
+    std::vector<std::vector<double>> vertex_est;
+    std::vector<EdgeRec> edges;        // FILE order
+    std::vector<int> fixed;
+};
+
+inline Graph loadG2O(const std::string& path, int dim) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot open dataset " + path);
+    Graph g; g.dim = dim;
+    const std::string vtag = dim == 2 ? "VERTEX_SE2" : "VERTEX_SE3:QUAT", etag = dim == 2 ? "EDGE_SE2" : "EDGE_SE3:QUAT";
+    const int mw = dim == 2 ? 3 : 7, d = dim == 2 ? 3 : 6;
+    std::string line;
+    while (std::getline(f, line)) {
+        std::istringstream is(line);
+        std::string tag;
+        if (!(is >> tag) || tag[0] == '#') continue;
+        if (tag == vtag) {
+            int id; is >> id; std::vector<double> e(mw); for (auto& x : e) is >> x;
+            if (!is) throw std::runtime_error("malformed vertex line: " + line);
+            g.vertex_ids.push_back(id); g.vertex_est.push_back(e);
+        } else if (tag == etag) {
+            EdgeRec e; is >> e.from >> e.to; e.meas.resize(mw); for (auto& x : e.meas) is >> x;
+            std::vector<double> up(d * (d + 1) / 2); for (auto& x : up) is >> x;      // upper triangle, row-major
+            if (!is) throw std::runtime_error("malformed edge line: " + line);
+            e.info.assign(d * d, 0.0);
+            int q = 0;
+            for (int r = 0; r < d; ++r) for (int c = r; c < d; ++c) { e.info[r * d + c] = up[q]; e.info[c * d + r] = up[q]; ++q; }
+            g.edges.push_back(std::move(e));
+        } else if (tag == "FIX") { int id; while (is >> id) g.fixed.push_back(id); }
+        // unknown tags are skipped, like g2o's loader (it prints a warning)
+    }
+    return g;
+}
+
+// splitProblemConstraints (src/utils.cpp:172-189) + getProblemOdom ordering (src/consensus.cpp:15): odometry j -> j+1
+struct Problem {
+    int dim = 2, n_poses = 0;
+    std::vector<double> odom_meas, odom_info;     // [n-1][mw], [n-1][d*d]
+    std::vector<EdgeRec> loops;                   // file order
+};
+inline Problem splitProblem(const Graph& g) {
+    Problem p; p.dim = g.dim;
+    const int mw = g.dim == 2 ? 3 : 7, d = g.dim == 2 ? 3 : 6;
+    int n = 0;
+    for (int id : g.vertex_ids) n = std::max(n, id + 1);
+    for (const auto& e : g.edges) n = std::max(n, std::max(e.from, e.to) + 1);
+    p.n_poses = n;
+    std::vector<const EdgeRec*> od(n > 0 ? n - 1 : 0, nullptr);
+    for (const auto& e : g.edges) {
+        if (std::abs(e.to - e.from) == 1) {
+            if (e.to != e.from + 1) throw std::runtime_error("odometry edge not oriented i -> i+1 (dataset not suitable, cf. cfg/3D/CUBE_params.yaml:12)");
+            if (od[e.from]) throw std::runtime_error("duplicate odometry edge");
+            od[e.from] = &e;
+        } else p.loops.push_back(e);
+    }
+    for (int j = 0; j + 1 < n; ++j) {
+        if (!od[j]) throw std::runtime_error("missing odometry edge " + std::to_string(j) + " -> " + std::to_string(j + 1) + " (vertex ids must be contiguous)");
+        p.odom_meas.insert(p.odom_meas.end(), od[j]->meas.begin(), od[j]->meas.end());
+        p.odom_info.insert(p.odom_info.end(), od[j]->info.begin(), od[j]->info.end());
+    }
+    (void)mw; (void)d;
+    return p;
+}
+
+// readSolutionFile (src/utils.cpp:262-282): the ground truth must exist and parse even though it is unused
+inline std::vector<std::vector<double>> readSolutionFile(const std::string& path, int dim) {
+    std::ifstream f(path);
+    if (!f) throw std::runtime_error("cannot open ground truth " + path);
+    std::vector<std::vector<double>> out;
+    std::string line;
+    const int w = dim == 2 ? 3 : 7;
+    while (std::getline(f, line)) {
+        std::istringstream is(line);
+        std::vector<double> v(w);
+        bool ok = true;
+        for (auto& x : v) if (!(is >> x)) { ok = false; break; }
+        if (ok) out.push_back(v);
+    }
+    return out;
+}
+inline void writeTrajectory(const std::string& path, const std::vector<double>& poses, int n, int w) {   // writeVertex, src/utils.cpp:239-258
+    std::ofstream f(path);
+    if (!f) throw std::runtime_error("cannot write " + path);
+    f.precision(10);
+    for (int i = 0; i < n; ++i) { for (int c = 0; c < w; ++c) f << poses[(size_t)i * w + c] << (c + 1 < w ? " " : "\n"); }
+}
+
+struct SimResult { int tp = 0, fp = 0, tn = 0, fn = 0; float precision = 0, recall = 0; double total_s = 0; int n_candidates = 0; std::vector<int> accepted; };
+
+inline void check(int rc) { if (rc != IPC_OK) throw std::runtime_error(std::string("ipc_b200: ") + ipc_last_error()); }
+
+// simulating_incremental_data (src/simulation.cpp:8-108) over the C ABI
+inline SimResult simulate(const Config& cfg, const Problem& p, int device, bool final_pgo, bool quiet) {
+    (void)readSolutionFile(cfg.ground_truth, p.dim);                         // :14-15
+    const int n_loops = (int)p.loops.size();
+    std::vector<int> order(n_loops);
+    for (int i = 0; i < n_loops; ++i) order[i] = i;
+    // labels: the first canonic_inliers loops (file order) are true (:24-25); candidates in time order (:26, stable)
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::max(p.loops[a].from, p.loops[a].to) < std::max(p.loops[b].from, p.loops[b].to); });
+    ipc_config c{cfg.s_factor, cfg.fast_reject_th, cfg.slow_reject_th, cfg.fast_reject_iter_base, cfg.slow_reject_iter_base};
+    ipc_handle* h = nullptr;
+    check(ipc_create(p.dim, p.n_poses, p.odom_meas.data(), p.odom_info.data(), &c, device, &h));   // IPC ipc(problem, cfg), :28
+    SimResult r; r.n_candidates = n_loops; r.accepted.assign(n_loops, 0);
+    for (int k = 0; k < n_loops; ++k) {                                      // :34-47
+        const EdgeRec& e = p.loops[order[k]];
+        int acc = 0;
+        auto t0 = std::chrono::steady_clock::now();
+        check(ipc_agreement_check(h, e.from, e.to, e.meas.data(), e.info.data(), &acc, nullptr));
+        r.total_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        r.accepted[order[k]] = acc;
+        const bool truth = order[k] < cfg.canonic_inliers;
+        if (acc && truth) ++r.tp; else if (acc && !truth) ++r.fp; else if (!acc && truth) ++r.fn; else ++r.tn;
+        if (!quiet && (k % 50 == 0 || k + 1 == n_loops)) { std::fprintf(stderr, "\r[%d / %d]", k + 1, n_loops); std::fflush(stderr); }
+    }
+    if (!quiet) std::fprintf(stderr, "\n");
+    r.precision = (r.tp + r.fp) > 0 ? (float)r.tp / (float)(r.tp + r.fp) : 0.f;   // float, :80-81
+    r.recall = (r.tp + r.fn) > 0 ? (float)r.tp / (float)(r.tp + r.fn) : 0.f;
+    const int w = p.dim == 2 ? 3 : 7;
+    std::vector<double> poses((size_t)p.n_poses * w);
+    if (final_pgo) {
+        double chi2 = 0; int iters = 0;
+        check(ipc_final_optimize(h, 1000, &chi2, &iters));                   // :50-65
+        if (!quiet) std::cout << "Final optimisation: chi2 = " << chi2 << " after " << iters << " iterations\n";
+    }
+    check(ipc_get_poses(h, poses.data()));
+    writeTrajectory(cfg.output, poses, p.n_poses, w);                        // :91-98
+    const std::string pr = cfg.output.substr(0, cfg.output.size() >= 3 ? cfg.output.size() - 3 : 0) + "PR";   // :101
+    std::ofstream f(pr);
+    f << r.precision << " " << r.recall << "\n" << r.total_s << " " << (n_loops ? r.total_s / n_loops : 0.0) << "\n";   // :103-104
+    ipc_destroy(h);
+    return r;
+}
+
+inline int tester_main(int argc, char** argv, int dim) {
+    std::string cfg_path; int device = 0; bool parse_only = false, quiet = false, final_pgo = true;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "-c" && i + 1 < argc) cfg_path = argv[++i];
+        else if (a == "--device" && i + 1 < argc) device = std::stoi(argv[++i]);
+        else if (a == "--parse-only") parse_only = true;
+        else if (a == "--no-final-pgo") final_pgo = false;
+        else if (a == "--quiet") quiet = true;
+        else { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [--device N] [--parse-only] [--no-final-pgo] [--quiet]\n"; return 2; }
+    }
+    if (cfg_path.empty()) { std::cerr << "usage: " << argv[0] << " -c <config.yaml>\n"; return 2; }
+    try {
+        Config cfg = readConfig(cfg_path);
+        Graph g = loadG2O(cfg.dataset, dim);
+        Problem p = splitProblem(g);
+        std::cout << "Dataset " << cfg.name << ": " << p.n_poses << " poses, " << p.n_poses - 1 << " odometry edges, " << p.loops.size() << " loop candidates ("
+                  << cfg.canonic_inliers << " canonic inliers)\n";
+        if (parse_only) {
+            std::cout << "s_factor " << cfg.s_factor << " fast " << cfg.fast_reject_th << "/" << cfg.fast_reject_iter_base << " slow " << cfg.slow_reject_th << "/"
+                      << cfg.slow_reject_iter_base << "\n";
+            return 0;
+        }
+        SimResult r = simulate(cfg, p, device, final_pgo, quiet);
+        std::cout << "TP " << r.tp << " FP " << r.fp << " TN " << r.tn << " FN " << r.fn << "\n";
+        std::cout << "Precision = " << r.precision << "  Recall = " << r.recall << "\n";
+        std::cout << "Total time = " << r.total_s << " s  Avg Time x test = " << (r.n_candidates ? r.total_s / r.n_candidates : 0.0) << " s\n";
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "error: " << e.what() << "\n";
+        return 1;
+    }
+}
+
+}  // namespace ipc_host

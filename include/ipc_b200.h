@@ -81,6 +81,10 @@ int ipc_consensus_size(ipc_handle* h, int* n);
 int ipc_get_consensus(ipc_handle* h, int* from_to, int capacity);
 /* Current vertex estimates (what simulation.cpp:93-97 writes out): [n_poses][3|7]. */
 int ipc_get_poses(ipc_handle* h, double* out);
+/* The final full-graph optimisation of simulating_incremental_data — src/simulation.cpp:50-65: propagateGuess(0, N-1),
+ * odometry information divided back by s_factor, Dogleg for at most max_iterations (1000 in the reference) on the odometry
+ * chain + the consensus set. chi2 / iterations may be NULL. */
+int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* iterations);
 
 /* ---- batched, independent checks: the throughput path --------------------------------------
  * A check is one isAgreeingWithCurrentState test (src/consensus_utils.cpp:6-22) on a window that

@@ -21,7 +21,7 @@ _LIB = None
 
 # every symbol include/ipc_b200.h declares
 SYMBOLS = ["ipc_last_error", "ipc_device_count", "ipc_create", "ipc_destroy", "ipc_agreement_check", "ipc_remove_edge",
-           "ipc_add_edge", "ipc_consensus_size", "ipc_get_consensus", "ipc_get_poses", "ipc_set_candidates", "ipc_check_batch",
+           "ipc_add_edge", "ipc_consensus_size", "ipc_get_consensus", "ipc_get_poses", "ipc_final_optimize", "ipc_set_candidates", "ipc_check_batch",
            "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_last_kernel_ms", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option"]
 
 
@@ -61,6 +61,7 @@ def lib():
         L.ipc_consensus_size.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ipc_get_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ipc_get_poses.argtypes = [C.c_void_p, C.c_void_p]
+        L.ipc_final_optimize.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ipc_set_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_check_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_check_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -162,6 +163,12 @@ class IPC:
         out = np.zeros((self.n_poses, self.mw), dtype=np.float64)
         _chk(lib().ipc_get_poses(self._h, _p(out)))
         return out
+
+    def final_optimize(self, max_iterations: int = 1000):
+        """Final full-graph optimisation of simulating_incremental_data (src/simulation.cpp:50-65). Returns (chi2, iterations)."""
+        chi2, it = C.c_double(0), C.c_int(0)
+        _chk(lib().ipc_final_optimize(self._h, int(max_iterations), C.byref(chi2), C.byref(it)))
+        return chi2.value, it.value
 
     # ---- batched path --------------------------------------------------------------------------
     def set_candidates(self, frm, to, meas, info):

@@ -20,6 +20,7 @@ struct HostState {
     int dim = 2, d = 3, mw = 3, n = 0;
     std::vector<double> odom_meas;   // [n-1][mw]
     std::vector<double> odom_info;   // [n-1][d*d], already multiplied by s_factor (robustifyVoters, consensus_utils.cpp:123-130)
+    std::vector<double> odom_info_raw;   // as given (the simulation divides s_factor back before the final optimisation, simulation.cpp:55-56)
     std::vector<HostEdge> cns;       // _max_consensus_set
     bool uniform_iso = false;        // every odometry edge carries the same information, isotropic in (x, y) and with no
     double Du[6] = {0}, Vu[6] = {0}; // x/y-theta coupling: E^T Omega E = Omega for every edge, kernels skip the per-edge loads
@@ -38,6 +39,7 @@ struct HostState {
         dim = dim_; d = dim == 2 ? 3 : 6; mw = dim == 2 ? 3 : 7; n = n_poses;
         odom_meas.assign(om, om + (size_t)(n - 1) * mw);
         odom_info.assign(oi, oi + (size_t)(n - 1) * d * d);
+        odom_info_raw = odom_info;
         for (auto& v : odom_info) v *= s_factor;
         for (size_t i = 0; i < odom_meas.size(); ++i) if (!std::isfinite(odom_meas[i])) { err = "non-finite odometry measurement"; return false; }
         for (size_t i = 0; i < odom_info.size(); ++i) if (!std::isfinite(odom_info[i])) { err = "non-finite odometry information"; return false; }
@@ -78,7 +80,8 @@ struct HostState {
 
     // AoS layout in HBM: (zx zy zt) per edge when uniform_iso (24 B), else (zx zy zt d00 d01 d02 d11 d12 d22) (72 B)
     int odom_rec_doubles(bool uni) const { return uni ? 3 : 9; }
-    void build_odom_aos(bool uni, int n_pad, std::vector<double>& rec) const {
+    void build_odom_aos(bool uni, int n_pad, std::vector<double>& rec, bool raw = false) const {
+        const std::vector<double>& odom_info = raw ? odom_info_raw : this->odom_info;
         const int w = odom_rec_doubles(uni);
         rec.assign((size_t)w * n_pad, 0.0);
         if (dim != 2) { rec.clear(); return; }

