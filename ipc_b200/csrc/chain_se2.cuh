@@ -284,7 +284,8 @@ enum { STEP_NONE = 0, STEP_GN = 1, STEP_BLEND = 2 };
 struct StepSpec {            // GN solution of one linearisation (uniform; lives in shared memory)
     double z[3][3];          // force per region
     double C[3][3];          // constant per region
-    double model;            // sum of linearised chi2 after the GN step
+    double model;            // sum of linearised chi2 after the GN step (diagnostic)
+    double gain_loops;       // loop-edge part of h_gn^T H h_gn = sum over edges |J h_gn|^2_Omega (the GN step's predicted gain)
     int rs, re;              // region boundaries (local vertex / edge indices)
 };
 
@@ -305,7 +306,7 @@ struct UniBlock {            // uniform per-check data (shared memory): read by 
 };
 constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
 
-constexpr int RED_DOUBLES_ = 16 * (NPRE + 3);
+constexpr int RED_DOUBLES_ = 16 * (NPRE + 4);
 struct ChainMem {            // three base pointers + a capacity: cheap to keep in registers and to pass by value
     double* st;              // per-vertex state, AoS of 5 doubles: x, y, theta, cos, sin. Shared memory (MODE 0) or global scratch (MODE 1)
     double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capv, then (b, h_gn) AoS[6] x capv
@@ -318,7 +319,7 @@ struct ChainMem {            // three base pointers + a capacity: cheap to keep 
     IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_; }
     IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + 2 * NSPEC * SPECW); }
 };
-constexpr int RED_DOUBLES = 16 * (NPRE + 3);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 2
+constexpr int RED_DOUBLES = 16 * (NPRE + 4);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 3
 constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
 constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
 constexpr int CHAIN_SCRATCH_ARRAYS = 9;          // per-vertex doubles in the global scratch (backup, b, h_gn)
@@ -407,7 +408,7 @@ template <bool UNI> IPC_HD void odom_terms(const OdomView& O, const OdomRec<UNI>
     }
 }
 
-struct SweepOut { double chi, mx, hh; };   // odometry chi2 sum / max at the new state, |h|^2 of the applied step
+struct SweepOut { double chi, mx, hh, gain; };   // odometry chi2 sum / max at the new state, |h|^2 of the applied step, odometry part of h^T H h (GN)
 
 // The sweep: apply a step (none / GN of M.U()->sol / blend c1 b + c2 h_gn from the scratch), re-linearise, chi2, interval
 // sums of the new linearisation at the special vertices. The GN step at vertex j needs the prefix of the OLD linearisation at
@@ -438,7 +439,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     double run[NPRE];        // local prefix of the NEW linearisation
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) run[m] = 0;
-    double chi = 0, mx = 0, hh = 0;
+    double chi = 0, mx = 0, hh = 0, gain = 0;
     bool has_spec = false;
 #pragma unroll
     for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
@@ -481,6 +482,25 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
             if (mode == STEP_GN) {
                 Lin2 eo; double to[NPRE];
                 odom_terms<UNI>(O, r, oca, osa, oa, ob, eo, to);
+                {   // predicted gain, accumulated edge by edge as |J h_gn|^2_Omega >= 0 (chi2 - model would cancel catastrophically
+                    // for a gross outlier): residual change of edge k under the force of its region is -(d + V Q^T z)
+                    const int rg = (k < sp->rs) ? 0 : (k < sp->re ? 1 : 2);
+                    const double* zr = sp->z[rg];
+                    const double y0 = eo.c * zr[0] + eo.s * zr[1], y1 = -eo.s * zr[0] + eo.c * zr[1], y2 = ob.y * zr[0] - ob.x * zr[1] + zr[2];
+                    double D6[6], V6[6];
+                    if (UNI) {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) { D6[q] = O.Du[q]; V6[q] = O.Vu[q]; }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 6; ++q) D6[q] = r.z[UNI ? 0 : 3 + q];
+                        inv_sym3(D6, V6);
+                    }
+                    const double w0 = eo.d0 + V6[0] * y0 + V6[1] * y1 + V6[2] * y2;
+                    const double w1 = eo.d1 + V6[1] * y0 + V6[3] * y1 + V6[4] * y2;
+                    const double w2 = eo.d2 + V6[2] * y0 + V6[4] * y1 + V6[5] * y2;
+                    gain += quad3(D6, w0, w1, w2);
+                }
 #pragma unroll
                 for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
                 gn_step_at(sp, j, pre, ob.x, ob.y, h);
@@ -515,11 +535,11 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
         oa = ob; oca = ocb; osa = osb;
         na = nb; nca = ncb; nsa = nsb;
     }
-    double s[2] = {chi, hh};
-    ScanSumMax<NT, 2>::run(run, s, mx, M.red() + (size_t)buf * RED_DOUBLES);
+    double s[3] = {chi, hh, gain};
+    ScanSumMax<NT, 3>::run(run, s, mx, M.red() + (size_t)buf * RED_DOUBLES);
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) ts.base[m] = run[m];
-    out.chi = s[0]; out.hh = s[1]; out.mx = mx;
+    out.chi = s[0]; out.hh = s[1]; out.gain = s[2]; out.mx = mx;
     if (has_spec) {
 #pragma unroll
         for (int q = 1; q < NSPEC; ++q) {
@@ -572,12 +592,13 @@ IPC_HD P2 sel_pose(bool c, const P2& a, const P2& b) { P2 r; r.x = c ? a.x : b.x
 // A loop edge in twist coordinates is one more edge of the cycle: with Q_l = [c_f -s_f y_t; s_f c_f -x_t; 0 0 1] (from-vertex
 // heading, to-vertex position) its terms W_l = Q_l V_l Q_l^T and Q_l d_l are what edge_prefix_terms() computes for an
 // odometry edge, and d(residual)/d(interval twist) = sigma Q_l^-1 with sigma = +1 when `to` is the later vertex.
-struct LoopNow { Lin2 e; double t[NPRE]; double sigma; };
+struct LoopNow { Lin2 e; double t[NPRE]; double sigma; double xt, yt; const double* D; const double* V; };
 IPC_HD void loop_now(const LoopRec2& L, const P2& pf, const P2& pt, LoopNow& o) {
     double s, c; ipc_sincos(pf.t, &s, &c);
     lin2cs(c, s, pf, pt, L.meas[0], L.meas[1], L.meas[2], L.D, o.e);
     edge_prefix_terms(o.e, L.V, pt.x, pt.y, o.t);
     o.sigma = L.to > L.from ? 1.0 : -1.0;
+    o.xt = pt.x; o.yt = pt.y; o.D = L.D; o.V = L.V;
 }
 IPC_HD void loops_eval(const SpecVals& sv, const CheckGeom& g, const LoopRec2& Lc, const LoopRec2& Lm, LoopNow& lc, LoopNow& lm) {
     const P2 org{0, 0, 0};
@@ -676,6 +697,25 @@ IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopNow& lc, 
         for (int q = 0; q < 3; ++q) { sp->z[r][q] = z[r][q]; sp->C[r][q] = C[r][q]; }
     double model = quad3(lc.t, zc[0], zc[1], zc[2]);
     if (g.K == 2) model += quad3(lm.t, zm[0], zm[1], zm[2]);
+    {   // loop part of the predicted gain: residual change of loop l is sigma V Q^T z_l - d_l
+        const Lin2& e = lc.e;
+        const double xb = lc.xt, yb = lc.yt;
+        const double y0 = e.c * zc[0] + e.s * zc[1], y1 = -e.s * zc[0] + e.c * zc[1], y2 = yb * zc[0] - xb * zc[1] + zc[2];
+        const double* V = lc.V; const double sg = lc.sigma;
+        const double w0 = sg * (V[0] * y0 + V[1] * y1 + V[2] * y2) - e.d0, w1 = sg * (V[1] * y0 + V[3] * y1 + V[4] * y2) - e.d1,
+                     w2 = sg * (V[2] * y0 + V[4] * y1 + V[5] * y2) - e.d2;
+        double gl = quad3(lc.D, w0, w1, w2);
+        if (g.K == 2) {
+            const Lin2& f = lm.e;
+            const double xm = lm.xt, ym = lm.yt;
+            const double u0 = f.c * zm[0] + f.s * zm[1], u1 = -f.s * zm[0] + f.c * zm[1], u2 = ym * zm[0] - xm * zm[1] + zm[2];
+            const double* Vm = lm.V; const double sm = lm.sigma;
+            const double v0 = sm * (Vm[0] * u0 + Vm[1] * u1 + Vm[2] * u2) - f.d0, v1 = sm * (Vm[1] * u0 + Vm[3] * u1 + Vm[4] * u2) - f.d1,
+                         v2 = sm * (Vm[2] * u0 + Vm[4] * u1 + Vm[5] * u2) - f.d2;
+            gl += quad3(lm.D, v0, v1, v2);
+        }
+        sp->gain_loops = gl;
+    }
 #pragma unroll
     for (int r = 0; r < 3; ++r) model += quad3(acc[r], z[r][0], z[r][1], z[r][2]);
     sp->model = model;
@@ -936,6 +976,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     double prev_hnorm = -1;      // norm of the last accepted step (speculation heuristic)
     bool have_norm = false, have_sd = false, need_rollback = false;
     double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0, linearGain = 0;
+    double gain_loops = 0;       // loop part of the GN predicted gain of the CURRENT linearisation (M.U()->sol)
     int purpose = P_INIT, mode = STEP_NONE;
     double c1 = 0, c2 = 0;
     for (;;) {
@@ -946,6 +987,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             double n_c, n_m;
             eval_and_solve<NT>(M, buf, so.chi, 0, 1, true, n_c, n_m);
             cur_chi = so.chi + n_c + n_m; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
+            gain_loops = M.U()->sol.gain_loops;
             start_iter = true;
         } else if (purpose == P_RELIN_SPECFAIL) {
             decide = true;                                   // same try, the GN norm is known now
@@ -960,6 +1002,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             }
             const bool trial_gn = purpose != P_TRIAL_BLEND;
             const double hdlNorm = sqrt(so.hh);
+            if (trial_gn) linearGain = so.gain + gain_loops;     // h_gn^T H h_gn (= b^T h_gn for the exact GN step)
             ++evals;
             // loop edges at the trial state; thread 0 also solves the new linearisation when the step is going to be kept
             double n_c, n_m;
@@ -973,6 +1016,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             else if (rho < 0.25) delta *= 0.5;
             if (rho > 0) {
                 cur_chi = newChi; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
+                gain_loops = M.U()->sol.gain_loops;
                 prev_hnorm = hdlNorm;
                 ++iterations; ++it;
                 start_iter = true;
@@ -1004,7 +1048,6 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         if (decide) {
             if (!have_norm) {
                 if (prm.speculate && prev_hnorm >= 0 && 4 * prev_hnorm < delta) {
-                    linearGain = cur_chi - M.U()->sol.model;
                     mode = STEP_GN; purpose = P_TRIAL_SPEC; c1 = 0; c2 = 1;
                     continue;
                 }
@@ -1012,7 +1055,6 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
                 hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); have_norm = true;
             }
             if (hgnNorm < delta) {
-                linearGain = cur_chi - M.U()->sol.model;     // predicted gain of the GN step of the current linearisation
                 mode = STEP_GN; purpose = P_TRIAL_GN; c1 = 0; c2 = 1;
                 continue;
             }

@@ -166,7 +166,9 @@ __global__ void cl_assemble(const ClLoop* __restrict__ loops, int K, int Lcap, C
 }
 
 // GN step from the forces z: f_k = sum_{l covers k} z_l, xi_k = m_k - M_k f_k, Xi = prefix(xi), h_j = T_j Xi_j.
-// H: AoS[3] x (L + 1). res[5] = |h|^2, res[6] = model = sum_k f_k^T M_k f_k + sum_l z_l^T W_l z_l.
+// H: AoS[3] x (L + 1). res[5] = |h|^2, res[6] = predicted gain h^T H h = sum over edges |J h|^2_Omega, accumulated edge by
+// edge from non-negative terms (chi2 - model cancels catastrophically for gross outliers): an odometry edge contributes
+// xi_k^T M_k^-1 xi_k, a loop eta^T W_l^-1 eta with eta = sigma W_l z_l - Q_l d_l.
 __global__ void __launch_bounds__(CL_NT) cl_gn_step(const ClLoop* __restrict__ loops, int K, int L, int Lcap, ClBuffers B, const double* __restrict__ z,
                                                     double* __restrict__ H, double* __restrict__ res) {
     __shared__ double red[32 * 3];
@@ -181,8 +183,10 @@ __global__ void __launch_bounds__(CL_NT) cl_gn_step(const ClLoop* __restrict__ l
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) t[m] = B.T[(size_t)m * Lcap + k];
         double Mf[3]; sym3_mul(t, f, Mf);
-        model += f[0] * Mf[0] + f[1] * Mf[1] + f[2] * Mf[2];
-        tot[0] += t[6] - Mf[0]; tot[1] += t[7] - Mf[1]; tot[2] += t[8] - Mf[2];
+        const double xi[3] = {t[6] - Mf[0], t[7] - Mf[1], t[8] - Mf[2]};
+        double Mi[6]; inv_sym3(t, Mi);
+        model += quad3(Mi, xi[0], xi[1], xi[2]);
+        tot[0] += xi[0]; tot[1] += xi[1]; tot[2] += xi[2];
         H[3 * (k + 1)] = tot[0]; H[3 * (k + 1) + 1] = tot[1]; H[3 * (k + 1) + 2] = tot[2];     // local inclusive prefix
     }
     cl_block_excl_scan<3>(tot, red);
@@ -196,7 +200,13 @@ __global__ void __launch_bounds__(CL_NT) cl_gn_step(const ClLoop* __restrict__ l
         hh += hx * hx + hy * hy + gt * gt;
     }
     if (threadIdx.x == 0) { H[0] = 0; H[1] = 0; H[2] = 0; }
-    for (int l = threadIdx.x; l < K; l += blockDim.x) model += quad3(B.lt + 12 * (size_t)l, z[3 * l], z[3 * l + 1], z[3 * l + 2]);
+    for (int l = threadIdx.x; l < K; l += blockDim.x) {
+        const double* t = B.lt + 12 * (size_t)l;
+        double Wz[3]; sym3_mul(t, z + 3 * l, Wz);
+        const double eta[3] = {t[9] * Wz[0] + t[6], t[9] * Wz[1] + t[7], t[9] * Wz[2] + t[8]};
+        double Wi[6]; inv_sym3(t, Wi);
+        model += quad3(Wi, eta[0], eta[1], eta[2]);
+    }
     double s[2] = {hh, model};
     cl_block_sum<2>(s, red);
     if (threadIdx.x == 0) { res[5] = s[0]; res[6] = s[1]; }

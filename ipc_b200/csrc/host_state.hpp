@@ -96,6 +96,51 @@ struct HostState {
         }
     }
 
+    // ---- SE(3) records: Z^-1 as (t, q = w x y z), Omega packed (21, row-major upper), V = Omega^-1 packed (21) -------------
+    static bool inv_spd6(const double* A, double* Ainv) {   // Gauss-Jordan on a symmetric positive definite 6x6
+        double M[6][12];
+        for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) { M[r][c] = A[r * 6 + c]; M[r][6 + c] = r == c ? 1.0 : 0.0; }
+        for (int c = 0; c < 6; ++c) {
+            int p = c; for (int r = c + 1; r < 6; ++r) if (std::fabs(M[r][c]) > std::fabs(M[p][c])) p = r;
+            if (M[p][c] == 0.0) return false;
+            if (p != c) for (int k = 0; k < 12; ++k) std::swap(M[p][k], M[c][k]);
+            double inv = 1.0 / M[c][c];
+            for (int k = 0; k < 12; ++k) M[c][k] *= inv;
+            for (int r = 0; r < 6; ++r) if (r != c) { double f = M[r][c]; if (f != 0.0) for (int k = 0; k < 12; ++k) M[r][k] -= f * M[c][k]; }
+        }
+        for (int r = 0; r < 6; ++r) for (int c = 0; c < 6; ++c) Ainv[r * 6 + c] = 0.5 * (M[r][6 + c] + M[c][6 + r]);
+        return true;
+    }
+    static bool se3_edge_record(const double* meas, const double* info, double scale, double* rec /* 49 */) {
+        // g2o reader: quaternion (qx qy qz qw in the file) normalised, w >= 0 (EDGE_SE3:QUAT)
+        double q[4] = {meas[6], meas[3], meas[4], meas[5]};
+        double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        if (!(n > 0)) return false;
+        for (double& v : q) v /= n;
+        if (q[0] < 0) for (double& v : q) v = -v;
+        // Z^-1 = (R^T, -R^T t)
+        const double w = q[0], x = q[1], y = q[2], z = q[3];
+        const double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                             2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+        for (int r = 0; r < 3; ++r) rec[r] = -(R[r] * meas[0] + R[3 + r] * meas[1] + R[6 + r] * meas[2]);
+        rec[3] = w; rec[4] = -x; rec[5] = -y; rec[6] = -z;
+        double W[36], Wi[36];
+        for (int i = 0; i < 36; ++i) W[i] = info[i] * scale;
+        if (!inv_spd6(W, Wi)) return false;
+        int k = 0;
+        for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { rec[7 + k] = 0.5 * (W[r * 6 + c] + W[c * 6 + r]); rec[28 + k] = Wi[r * 6 + c]; ++k; }
+        return true;
+    }
+    bool build_odom_aos3(int n_pad, std::vector<double>& rec) const {
+        rec.assign((size_t)49 * n_pad, 0.0);
+        for (int k = 0; k < n_pad; ++k) {
+            double* r = &rec[(size_t)k * 49];
+            if (k + 1 < n) { if (!se3_edge_record(&odom_meas[(size_t)k * 7], &odom_info[(size_t)k * 36], 1.0, r)) return false; }
+            else { r[3] = 1; for (int d = 0, q = 0; d < 6; ++d) { r[7 + q] = 1; r[28 + q] = 1; q += 6 - d; } }
+        }
+        return true;
+    }
+
     // removeEdgeFromCnS, src/consensus.cpp:77-98
     bool remove_edge(int from, int to) {
         int v0 = std::min(from, to), v1 = std::max(from, to);

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "chain_se2_kernel.cuh"
+#include "chain_se3_kernel.cuh"
 #include "host_state.hpp"
 #include "matrix.cuh"
 #include "cluster_se2.cuh"
@@ -81,14 +82,32 @@ struct Bucket { int cap; int nt; int mode; };
 // vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
 const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 64, 0}, {800, 128, 0}, {2600, 256, 0}, {5400, 512, 0}, {1 << 30, 512, 1}};
 
-size_t smem_bytes(int mode, int cap) {
-    size_t capv = cap + 2;
-    size_t n = CHAIN_SMALL_DOUBLES + (mode == 0 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0);
+// SE(3): 7 doubles of state per vertex, 256 resident threads per SM (the 27 running prefix values need the registers)
+const Bucket kBuckets3[NB] = {{96, 32, 0}, {320, 64, 0}, {800, 128, 0}, {3700, 256, 0}, {3701, 256, 0}, {1 << 30, 256, 1}};
+const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
+int threads_per_sm(int dim) { return dim == 2 ? 512 : 256; }
+
+size_t smem_bytes(int mode, int cap, int dim = 2, int nt = 0) {
+    size_t capv = std::max(cap + 2, nt);
+    size_t n = dim == 2 ? CHAIN_SMALL_DOUBLES + (mode == 0 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0)
+                        : se3::CHAIN3_SMALL_DOUBLES + (mode == 0 ? (size_t)se3::CHAIN3_STATE * capv : 0);
     return n * sizeof(double);
 }
-size_t scratch_doubles_per_cta(int mode, int cap) {
-    size_t capv = cap + 2;
-    return (size_t)(CHAIN_SCRATCH_ARRAYS + (mode == 1 ? CHAIN_STATE_ARRAYS : 0)) * capv;
+size_t scratch_doubles_per_cta(int mode, int cap, int dim = 2, int nt = 0) {
+    size_t capv = std::max(cap + 2, nt);
+    return dim == 2 ? (size_t)(CHAIN_SCRATCH_ARRAYS + (mode == 1 ? CHAIN_STATE_ARRAYS : 0)) * capv
+                    : (size_t)(se3::CHAIN3_SCRATCH + (mode == 1 ? se3::CHAIN3_STATE : 0)) * capv;
+}
+template <int NT, int MODE> int launch_se3(const BatchArgs& a, int grid, cudaStream_t st) {
+    size_t sm = smem_bytes(MODE, a.Lcap, 3, NT);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(chain_check_se3<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_done = true;
+    }
+    chain_check_se3<NT, MODE><<<grid, NT, sm, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return IPC_OK;
 }
 
 template <int NT, int MODE, bool UNI> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
@@ -122,6 +141,7 @@ struct ipc_handle {
     HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
     // device graph
     double* d_odom9 = nullptr;        // AoS odometry records, general (9 doubles / edge)
+    double* d_odom49 = nullptr;       // SE(3) AoS odometry records (Z^-1, Omega, Omega^-1: 49 doubles / edge)
     double* d_odom3 = nullptr;        // AoS odometry records, uniform isotropic information (3 doubles / edge); null if not applicable
     void* d_loops = nullptr;  int n_loops = 0;
     std::vector<int> h_lfrom, h_lto;  // host copy of candidate endpoints
@@ -172,37 +192,43 @@ int ensure_batch_buffers(ipc_handle* h, int n_checks) {
 // enqueue plan + bucket launches + pack on `st`; all pointers device; work buffer sized for cap >= n_checks
 int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev, int* work_dev, int work_stride,
                   unsigned char* verdict_dev, uint32_t* bits_dev, ipc_check_info* info_dev, cudaStream_t st) {
-    if (h->dim != 2) return fail(IPC_ERR_UNSUPPORTED, "SE(3) batch kernel not built in this revision");
+    const Bucket* kB = buckets_of(h->dim);
     CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * NB, st));
     CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * 2, st));
-    const int loop_stride_ints = (int)(sizeof(LoopRec2) / sizeof(int));
+    const int loop_stride_ints = (int)((h->dim == 2 ? sizeof(LoopRec2) : sizeof(se3::LoopRec3)) / sizeof(int));
     plan_checks<<<(n_checks + 255) / 256, 256, 0, st>>>(reinterpret_cast<const int*>(h->d_loops), loop_stride_ints, n_checks, member_dev, cand_dev,
                                                         h->d_bucket_cap, NB, h->d_counts, work_dev, work_stride, h->d_stats);
     CUDA_TRY(cudaGetLastError());
     int launches = 1;
     CUDA_TRY(cudaEventRecord(h->ev_k0, st));
     for (int b = 0; b < NB; ++b) {
-        const Bucket& bk = kBuckets2[b];
-        int lo_cap = b == 0 ? 0 : kBuckets2[b - 1].cap;
+        const Bucket& bk = kB[b];
+        int lo_cap = b == 0 ? 0 : kB[b - 1].cap;
         if (lo_cap >= h->n - 1) break;                 // no window can be this long
         BatchArgs a{};
         for (int c = 0; c < 6; ++c) { a.Du[c] = h->hs.Du[c]; a.Vu[c] = h->hs.Vu[c]; }
-        const bool uni = h->hs.uniform_iso && h->use_uniform && h->d_odom3;
-        a.odom = uni ? h->d_odom3 : h->d_odom9; a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
+        const bool uni = h->dim == 2 && h->hs.uniform_iso && h->use_uniform && h->d_odom3;
+        a.odom = h->dim == 3 ? h->d_odom49 : (uni ? h->d_odom3 : h->d_odom9); a.n_pad = h->n_pad; a.loops = h->d_loops; a.member = member_dev; a.cand = cand_dev;
         a.work = work_dev + (size_t)b * work_stride; a.n_work = h->d_counts + b; a.next = h->d_counts + NB + b;
         a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
         a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
         a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept;
         a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch;
-        a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap);
-        size_t sm = smem_bytes(bk.mode, a.Lcap);
+        a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap, h->dim, bk.nt);
+        size_t sm = smem_bytes(bk.mode, a.Lcap, h->dim, bk.nt);
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-        per_sm = std::min(per_sm, 512 / bk.nt);
+        per_sm = std::min(per_sm, threads_per_sm(h->dim) / bk.nt);
         int grid = std::min(n_checks, h->n_sm * per_sm);
         grid = (int)std::min<size_t>(grid, h->scratch_doubles / a.scratch_stride);
         int rc = IPC_OK;
-        if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st, uni);
+        if (h->dim == 3) {
+            if (bk.mode == 1) rc = launch_se3<256, 1>(a, grid, st);
+            else if (bk.nt == 32) rc = launch_se3<32, 0>(a, grid, st);
+            else if (bk.nt == 64) rc = launch_se3<64, 0>(a, grid, st);
+            else if (bk.nt == 128) rc = launch_se3<128, 0>(a, grid, st);
+            else rc = launch_se3<256, 0>(a, grid, st);
+        } else if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st, uni);
         else if (bk.nt == 32) rc = launch_se2<32, 0>(a, grid, st, uni);
         else if (bk.nt == 64) rc = launch_se2<64, 0>(a, grid, st, uni);
         else if (bk.nt == 128) rc = launch_se2<128, 0>(a, grid, st, uni);
@@ -253,10 +279,16 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     if (!h->hs.init(dim, n_poses, odom_meas, odom_info, cfg->s_factor, err)) { delete h; return fail(IPC_ERR_ARG, err); }
     // device odometry records
     std::vector<double> rec;
-    h->hs.build_odom_aos(false, h->n_pad, rec);
-    CUDA_TRY(cudaMalloc(&h->d_odom9, rec.size() * sizeof(double)));
-    CUDA_TRY(cudaMemcpy(h->d_odom9, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
-    if (h->hs.uniform_iso) {
+    if (dim == 3) {
+        if (!h->hs.build_odom_aos3(h->n_pad, rec)) { delete h; return fail(IPC_ERR_ARG, "odometry edge with a zero quaternion or a singular information matrix"); }
+        CUDA_TRY(cudaMalloc(&h->d_odom49, rec.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(h->d_odom49, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        h->hs.build_odom_aos(false, h->n_pad, rec);
+        CUDA_TRY(cudaMalloc(&h->d_odom9, rec.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(h->d_odom9, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (dim == 2 && h->hs.uniform_iso) {
         h->hs.build_odom_aos(true, h->n_pad, rec);
         CUDA_TRY(cudaMalloc(&h->d_odom3, rec.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(h->d_odom3, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -265,18 +297,19 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     CUDA_TRY(cudaMalloc(&h->d_bucket_cap, sizeof(int) * NB));
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * 2));
     int caps[NB];
-    for (int b = 0; b < NB; ++b) caps[b] = kBuckets2[b].cap;
+    for (int b = 0; b < NB; ++b) caps[b] = buckets_of(dim)[b].cap;
     CUDA_TRY(cudaMemcpy(h->d_bucket_cap, caps, sizeof(caps), cudaMemcpyHostToDevice));
     {   // per-CTA scratch: every bucket launch fits grid * stride into it
         size_t need = 0;
+        const Bucket* kB = buckets_of(dim);
         for (int b = 0; b < NB; ++b) {
-            int lo_cap = b == 0 ? 0 : kBuckets2[b - 1].cap;
+            int lo_cap = b == 0 ? 0 : kB[b - 1].cap;
             if (lo_cap >= n_poses - 1) break;
-            int Lcap = (std::min(kBuckets2[b].cap, n_poses - 1) + 1) & ~1;
-            size_t sm = smem_bytes(kBuckets2[b].mode, Lcap);
+            int Lcap = (std::min(kB[b].cap, n_poses - 1) + 1) & ~1;
+            size_t sm = smem_bytes(kB[b].mode, Lcap, dim, kB[b].nt);
             int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-            per_sm = std::min(per_sm, 512 / kBuckets2[b].nt);
-            need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kBuckets2[b].mode, Lcap));
+            per_sm = std::min(per_sm, threads_per_sm(dim) / kB[b].nt);
+            need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kB[b].mode, Lcap, dim, kB[b].nt));
         }
         h->scratch_doubles = need;
         CUDA_TRY(cudaMalloc(&h->d_scratch, need * sizeof(double)));
@@ -303,7 +336,7 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
 void ipc_destroy(ipc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
+    cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_odom49); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
     cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
     cudaFree(h->cl_info); cudaFree(h->cl_loops);
@@ -347,7 +380,18 @@ int ipc_set_candidates(ipc_handle* h, int n_loops, const int* from, const int* t
             CUDA_TRY(cudaMemcpy(h->d_loops, recs.data(), sizeof(LoopRec2) * n_loops, cudaMemcpyHostToDevice));
         }
     } else {
-        return fail(IPC_ERR_UNSUPPORTED, "SE(3) candidate table not built in this revision");
+        std::vector<se3::LoopRec3> recs(n_loops);
+        for (int i = 0; i < n_loops; ++i) {
+            double r[49];
+            if (!HostState::se3_edge_record(meas + 7 * i, info + 36 * i, 1.0, r)) return fail(IPC_ERR_ARG, "candidate " + std::to_string(i) + " has a zero quaternion or a singular information matrix");
+            recs[i].from = from[i]; recs[i].to = to[i];
+            for (int q = 0; q < 7; ++q) recs[i].zinv[q] = r[q];
+            for (int q = 0; q < 21; ++q) { recs[i].Om[q] = r[7 + q]; recs[i].V[q] = r[28 + q]; }
+        }
+        if (n_loops) {
+            CUDA_TRY(cudaMalloc(&h->d_loops, sizeof(se3::LoopRec3) * n_loops));
+            CUDA_TRY(cudaMemcpy(h->d_loops, recs.data(), sizeof(se3::LoopRec3) * n_loops, cudaMemcpyHostToDevice));
+        }
     }
     h->n_loops = n_loops;
     return IPC_OK;
@@ -503,7 +547,7 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
             CUDA_TRY(cudaGetLastError());
             rc = cl_read(h); if (rc != IPC_OK) return rc;
         }
-        const double hh = hr[5], hgnNorm = std::sqrt(hh), gn_gain = cur_chi - hr[6];
+        const double hh = hr[5], hgnNorm = std::sqrt(hh), gn_gain = hr[6];
         if (!std::isfinite(hgnNorm)) { ok = false; ++iterations; break; }     // factorisation broke down (g2o: Fail)
         bool have_sd = false, good = false;
         double bb = 0, bh = 0, bHb = 0, alpha = 0, hsdNorm = 0;

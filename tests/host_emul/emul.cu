@@ -55,3 +55,47 @@ extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const doub
     return emul_impl<double>(n_poses, odom_meas, odom_info, s_factor, n_loops, lfrom, lto, lmeas, linfo, n_checks, member, cand, fast_th, slow_th,
                              fast_iter, slow_iter, noise_eps, speculate, early_accept, want_info, use_uni, n_threads, verdict, info, sweeps);
 }
+
+// ---- SE(3) ------------------------------------------------------------------------------------------------------------
+#include "../../ipc_b200/csrc/chain_se3.cuh"
+extern "C" int emul_check_batch3(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
+                                 const int* lto, const double* lmeas, const double* linfo, int n_checks, const int* member, const int* cand,
+                                 double fast_th, double slow_th, int fast_iter, int slow_iter, double noise_eps, int speculate, int early_accept,
+                                 int want_info, int n_threads, unsigned char* verdict, ipc_check_info* info, int* sweeps) {
+    using namespace ipcb::se3;
+    HostState hs; std::string err;
+    if (!hs.init(3, n_poses, odom_meas, odom_info, s_factor, err)) return -1;
+    const int n_pad = (n_poses + 3) & ~1;
+    std::vector<double> rec;
+    if (!hs.build_odom_aos3(n_pad, rec)) return -2;
+    std::vector<LoopRec3> recs(n_loops);
+    for (int i = 0; i < n_loops; ++i) {
+        double r[49];
+        if (!HostState::se3_edge_record(lmeas + 7 * i, linfo + 36 * i, 1.0, r)) return -3;
+        recs[i].from = lfrom[i]; recs[i].to = lto[i];
+        for (int q = 0; q < 7; ++q) recs[i].zinv[q] = r[q];
+        for (int q = 0; q < 21; ++q) { recs[i].Om[q] = r[7 + q]; recs[i].V[q] = r[28 + q]; }
+    }
+    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept};
+    std::atomic<int> next{0};
+    auto work = [&]() {
+        const int capv = n_poses + 2;
+        std::vector<double> buf((size_t)(CHAIN3_STATE + CHAIN3_SCRATCH) * capv + CHAIN3_SMALL_DOUBLES, 0.0);
+        ChainMem3 M; double* p = buf.data();
+        M.small = p; M.st = p + CHAIN3_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN3_STATE * capv; M.capv = capv;
+        for (;;) {
+            int c = next.fetch_add(1);
+            if (c >= n_checks) break;
+            CheckResult r;
+            run_check3<1>(M, rec.data(), &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+            verdict[c] = (unsigned char)r.verdict;
+            if (info) { info[c].max_chi2 = r.max_chi2; info[c].cand_chi2 = r.cand_chi2; info[c].sum_chi2 = r.sum_chi2; info[c].iterations = r.iterations;
+                        info[c].evals = r.evals; info[c].window_len = r.window_len; info[c].n_loops = r.n_loops; }
+            if (sweeps) sweeps[c] = r.n_sweeps;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < (n_threads < 1 ? 1 : n_threads); ++t) th.emplace_back(work);
+    for (auto& t : th) t.join();
+    return 0;
+}

@@ -206,3 +206,32 @@ def test_cli_end_to_end_matches_oracle_stream(gpu_lib, oracle_lib, tmp_path):
     traj = np.loadtxt(out)
     assert traj.shape == (g.n_poses, 3) and np.isfinite(traj).all()
     assert f"TP {tp} FP {fp}" in r.stdout
+
+
+@pytest.mark.parametrize("noise_exit", [1, 0])
+def test_se3_pair_batch_matches_golden(gpu_lib, noise_exit):
+    """EdgeSE3 / VertexSE3 instantiation (src/consensus.cpp:175): sphere-shaped SE(3) graph, fast + pair checks."""
+    z, g, cfg = load("pairs_se3_sphere.npz")
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    ipc.set_option("noise_exit", noise_exit)
+    acc, info = ipc.check_batch(z["member"], z["cand"])
+    _compare(acc, info, z)
+    ipc.close()
+
+
+def test_se3_matches_oracle_live_and_matrix(gpu_lib, oracle_lib):
+    g, cfg = synth.make_config("sphere", scale=0.08)
+    mem, cnd = api.pair_checks(g)
+    sel = np.sort(np.random.default_rng(7).choice(len(cnd), min(len(cnd), 1500), replace=False))
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem[sel], cnd[sel])
+    ptr, idx = api.checks_to_csr(mem[sel], cnd[sel])
+    oacc, orep = oracle_lib.OracleIPC(g, cfg).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
+    assert acc.any() and (~acc).any()
+    rows, order, solved = ipc.consistency_matrix()
+    assert solved == len(cnd)
+    got = _unpack(rows, g.n_loops)
+    assert np.array_equal(got, got.T)
+    ipc.close()
