@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libipc_b200.so")
+LIB_PATH = os.environ.get("IPC_B200_LIB", os.path.join(_HERE, "libipc_b200.so"))
 _LIB = None
 
 # every symbol include/ipc_b200.h declares
@@ -61,7 +61,8 @@ def lib():
         L.ipc_consensus_size.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.ipc_get_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ipc_get_poses.argtypes = [C.c_void_p, C.c_void_p]
-        L.ipc_final_optimize.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        if hasattr(L, "ipc_final_optimize"):
+            L.ipc_final_optimize.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.ipc_set_candidates.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_check_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_check_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -302,6 +302,9 @@ struct UniBlock {            // uniform per-check data (shared memory): read by 
     LoopRec2 Lc, Lm;
     StepSpec sol;
     double n_c, n_m;         // chi2 of the loop edges at the state of the last sweep
+    double lt[2][20];        // per loop (candidate, member): terms t(9), sigma, chi, d(3), cos, sin, x_to, y_to — staged by warp 0
+    double sc[12];           // thread-uniform Dogleg scalars that are rarely touched (every thread writes the same values): keeps
+                             // them out of the registers that are live across the sweep
     CheckGeom g;
 };
 constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
@@ -482,24 +485,23 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
             if (mode == STEP_GN) {
                 Lin2 eo; double to[NPRE];
                 odom_terms<UNI>(O, r, oca, osa, oa, ob, eo, to);
-                {   // predicted gain, accumulated edge by edge as |J h_gn|^2_Omega >= 0 (chi2 - model would cancel catastrophically
-                    // for a gross outlier): residual change of edge k under the force of its region is -(d + V Q^T z)
+                {   // predicted gain h_gn^T H h_gn, accumulated edge by edge from non-negative terms |J h_gn|^2_Omega (chi2 - model
+                    // cancels catastrophically near convergence and for gross outliers): the residual change of edge k under the
+                    // force z of its region is -(d + V Q^T z)
                     const int rg = (k < sp->rs) ? 0 : (k < sp->re ? 1 : 2);
                     const double* zr = sp->z[rg];
-                    const double y0 = eo.c * zr[0] + eo.s * zr[1], y1 = -eo.s * zr[0] + eo.c * zr[1], y2 = ob.y * zr[0] - ob.x * zr[1] + zr[2];
-                    double D6[6], V6[6];
+                    const double z0 = zr[0], z1 = zr[1], z2 = zr[2];
+                    const double y0 = eo.c * z0 + eo.s * z1, y1 = -eo.s * z0 + eo.c * z1, y2 = ob.y * z0 - ob.x * z1 + z2;
                     if (UNI) {
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) { D6[q] = O.Du[q]; V6[q] = O.Vu[q]; }
+                        const double w0 = fma(O.Vu[0], y0, eo.d0), w1 = fma(O.Vu[0], y1, eo.d1), w2 = fma(O.Vu[5], y2, eo.d2);
+                        gain += O.Du[0] * (w0 * w0 + w1 * w1) + O.Du[5] * w2 * w2;
                     } else {
-#pragma unroll
-                        for (int q = 0; q < 6; ++q) D6[q] = r.z[UNI ? 0 : 3 + q];
-                        inv_sym3(D6, V6);
+                        double V6[6]; inv_sym3(r.z + (UNI ? 0 : 3), V6);
+                        const double w0 = eo.d0 + V6[0] * y0 + V6[1] * y1 + V6[2] * y2;
+                        const double w1 = eo.d1 + V6[1] * y0 + V6[3] * y1 + V6[4] * y2;
+                        const double w2 = eo.d2 + V6[2] * y0 + V6[4] * y1 + V6[5] * y2;
+                        gain += quad3(r.z + (UNI ? 0 : 3), w0, w1, w2);
                     }
-                    const double w0 = eo.d0 + V6[0] * y0 + V6[1] * y1 + V6[2] * y2;
-                    const double w1 = eo.d1 + V6[1] * y0 + V6[3] * y1 + V6[4] * y2;
-                    const double w2 = eo.d2 + V6[2] * y0 + V6[4] * y1 + V6[5] * y2;
-                    gain += quad3(D6, w0, w1, w2);
                 }
 #pragma unroll
                 for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
@@ -723,21 +725,138 @@ IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopNow& lc, 
 
 // After a sweep: thread 0 evaluates the loop edges at the published state and, if the trial is going to be kept
 // (rho > 0, or `force`), solves the new linearisation into M.U()->sol. One barrier; every thread gets the loop chi2.
-IPC_HD_COLD void eval_and_solve_t0(ChainMem M, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
+// After a sweep, warp 0: (phase 1) lane l linearises loop l at the published state and stages its terms in shared memory;
+// (phase 2) lane 0 decides whether the trial is kept (rho > 0, or `force`) and if so solves the new linearisation into
+// M.U()->sol, reading the interval sums straight from the special-vertex table. Everything is staged through shared memory
+// so this serial, latency-critical section keeps almost nothing in registers / local memory.
+IPC_HD_COLD void eval_and_solve_w0(ChainMem M, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
     UniBlock* U = M.U();
     const CheckGeom& g = U->g;
-    SpecVals sv; LoopNow lc, lm;
-    spec_load(M.spec() + (size_t)(buf ^ 1) * NSPEC * SPECW, g, sv);
-    loops_eval(sv, g, U->Lc, U->Lm, lc, lm);
-    const double c = lc.e.chi, m = g.K == 2 ? lm.e.chi : 0.0;
+    const double* spec = M.spec() + (size_t)(buf ^ 1) * NSPEC * SPECW;
+    const double* o1 = spec + 1 * SPECW; const double* o2 = spec + 2 * SPECW; const double* o3 = spec + 3 * SPECW;
+    const bool z1 = g.rs == 0;      // nobody owns vertex 0: prefix 0, pose = origin
+#ifdef __CUDA_ARCH__
+    const int l0 = threadIdx.x, l1 = threadIdx.x + 1;
+#else
+    const int l0 = 0, l1 = g.K;
+#endif
+    for (int l = l0; l < l1 && l < g.K; ++l) {
+        const LoopRec2& Lp = l == 0 ? U->Lc : U->Lm;
+        const bool a_is_rs = l == 0 ? g.c_a_is_rs : g.m_a_is_rs, b_is_L = l == 0 ? g.c_b_is_L : g.m_b_is_L;
+        // interval [a, b): a is vertex 0 or rs, b is re or L
+        const double* oa = o1; const double* ob = b_is_L ? o3 : o2;
+        const bool a_org = !a_is_rs || z1;
+        const P2 pa{a_org ? 0.0 : oa[NPRE], a_org ? 0.0 : oa[NPRE + 1], a_org ? 0.0 : oa[NPRE + 2]};
+        const P2 pb{ob[NPRE], ob[NPRE + 1], ob[NPRE + 2]};
+        const bool to_hi = Lp.to > Lp.from;
+        const P2 pf = to_hi ? pa : pb, pt = to_hi ? pb : pa;
+        double sn, cs; ipc_sincos(pf.t, &sn, &cs);
+        Lin2 e; lin2cs(cs, sn, pf, pt, Lp.meas[0], Lp.meas[1], Lp.meas[2], Lp.D, e);
+        double* o = U->lt[l];
+        edge_prefix_terms(e, Lp.V, pt.x, pt.y, o);
+        o[9] = to_hi ? 1.0 : -1.0; o[10] = e.chi; o[11] = e.d0; o[12] = e.d1; o[13] = e.d2; o[14] = e.c; o[15] = e.s; o[16] = pt.x; o[17] = pt.y;
+    }
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+    if (threadIdx.x != 0) return;
+#endif
+    const double* tc = U->lt[0]; const double* tm = U->lt[1];
+    const double c = tc[10], m = g.K == 2 ? tm[10] : 0.0;
     if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
     const double rho = (cur_chi - (odom_chi + c + m)) / linearGain;
-    if (force || rho > 0) gn_solve(sv, g, lc, lm, &U->sol);
     U->n_c = c; U->n_m = m;
+    if (!(force || rho > 0)) return;
+    StepSpec* sp = &U->sol;
+    // region sums: region 0 = [0, rs), region 1 = [rs, re), region 2 = [re, L), read on the fly:
+    //   acc0 = pre1, acc1 = pre2 - pre1, acc2 = pre3 - pre2  (pre1 = 0 when rs == 0)
+    auto P1 = [&](int q) { return z1 ? 0.0 : o1[q]; };
+    double zc[3], zm[3] = {0, 0, 0};
+    if (g.K == 1) {
+        double S[6], Si[6], r[3];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) S[q] = (o2[q] - P1(q)) + tc[q];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) r[q] = (o2[6 + q] - P1(6 + q)) - tc[9] * tc[6 + q];
+        inv_sym3(S, Si);
+        sym3_mul(Si, r, zc);
+    } else {
+        double A[6], B[6], Cm[6], rc[3], rm[3];
+#pragma unroll
+        for (int q = 0; q < NPRE; ++q) {
+            const double a0 = P1(q), a1 = o2[q] - a0, a2 = o3[q] - o2[q];
+            const double cc = a1 + (g.first_is_c ? a0 : 0.0) + (g.last_is_c ? a2 : 0.0);
+            const double mm = a1 + (g.first_is_c ? 0.0 : a0) + (g.last_is_c ? 0.0 : a2);
+            if (q < 6) { B[q] = a1; A[q] = cc + tc[q]; Cm[q] = mm + tm[q]; }
+            else { rc[q - 6] = cc - tc[9] * tc[q]; rm[q - 6] = mm - tm[9] * tm[q]; }
+        }
+        // [A B; B Cm] [zc; zm] = [rc; rm]:  Sch = Cm - B A^-1 B,  zm = Sch^-1 (rm - B A^-1 rc),  zc = A^-1 (rc - B zm)
+        double Ai[6], AiB[9], t[3], u[3];
+        inv_sym3(A, Ai);
+        sym3_sym3(Ai, B, AiB);
+        double Sch[6];
+        Sch[0] = Cm[0] - (B[0] * AiB[0] + B[1] * AiB[3] + B[2] * AiB[6]);
+        Sch[1] = Cm[1] - (B[0] * AiB[1] + B[1] * AiB[4] + B[2] * AiB[7]);
+        Sch[2] = Cm[2] - (B[0] * AiB[2] + B[1] * AiB[5] + B[2] * AiB[8]);
+        Sch[3] = Cm[3] - (B[1] * AiB[1] + B[3] * AiB[4] + B[4] * AiB[7]);
+        Sch[4] = Cm[4] - (B[1] * AiB[2] + B[3] * AiB[5] + B[4] * AiB[8]);
+        Sch[5] = Cm[5] - (B[2] * AiB[2] + B[4] * AiB[5] + B[5] * AiB[8]);
+        sym3_mul(Ai, rc, t);
+        sym3_mul(B, t, u);
+        const double rs2[3] = {rm[0] - u[0], rm[1] - u[1], rm[2] - u[2]};
+        double Schi[6];
+        inv_sym3(Sch, Schi);
+        sym3_mul(Schi, rs2, zm);
+        sym3_mul(B, zm, u);
+        const double rc2[3] = {rc[0] - u[0], rc[1] - u[1], rc[2] - u[2]};
+        sym3_mul(Ai, rc2, zc);
+    }
+    sp->rs = g.rs; sp->re = g.re;
+    double z0[3], zz1[3], z2[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (g.K == 1) { z0[q] = 0; zz1[q] = zc[q]; z2[q] = 0; }
+        else { z0[q] = g.first_is_c ? zc[q] : zm[q]; zz1[q] = zc[q] + zm[q]; z2[q] = g.last_is_c ? zc[q] : zm[q]; }
+        sp->z[0][q] = z0[q]; sp->z[1][q] = zz1[q]; sp->z[2][q] = z2[q];
+    }
+    {   // C_0 = 0, C_1 = PM(rs) (z_0 - z_1), C_2 = C_1 + PM(re) (z_1 - z_2)
+        const double dz0[3] = {z0[0] - zz1[0], z0[1] - zz1[1], z0[2] - zz1[2]}, dz1[3] = {zz1[0] - z2[0], zz1[1] - z2[1], zz1[2] - z2[2]};
+        const double p1[6] = {P1(0), P1(1), P1(2), P1(3), P1(4), P1(5)};
+        double c1v[3], c2v[3];
+        sym3_mul(p1, dz0, c1v);
+        sym3_mul(o2, dz1, c2v);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { sp->C[0][q] = 0; sp->C[1][q] = c1v[q]; sp->C[2][q] = c1v[q] + c2v[q]; }
+    }
+    {   // model value (cheap predicted gain = chi2 - model) and the loop part of the accurate gain
+        double model = quad3(tc, zc[0], zc[1], zc[2]);
+        if (g.K == 2) model += quad3(tm, zm[0], zm[1], zm[2]);
+        const double p1[6] = {P1(0), P1(1), P1(2), P1(3), P1(4), P1(5)};
+        double a1[6], a2[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { a1[q] = o2[q] - p1[q]; a2[q] = o3[q] - o2[q]; }
+        model += quad3(p1, z0[0], z0[1], z0[2]) + quad3(a1, zz1[0], zz1[1], zz1[2]) + quad3(a2, z2[0], z2[1], z2[2]);
+        sp->model = model;
+        double gl = 0;
+        for (int l = 0; l < g.K; ++l) {   // residual change of loop l is sigma V Q^T z_l - d_l
+            const double* o = U->lt[l];
+            const LoopRec2& Lp = l == 0 ? U->Lc : U->Lm;
+            const double* zl = l == 0 ? zc : zm;
+            const double y0 = o[14] * zl[0] + o[15] * zl[1], y1 = -o[15] * zl[0] + o[14] * zl[1], y2 = o[17] * zl[0] - o[16] * zl[1] + zl[2];
+            const double* V = Lp.V; const double sg = o[9];
+            const double w0 = sg * (V[0] * y0 + V[1] * y1 + V[2] * y2) - o[11], w1 = sg * (V[1] * y0 + V[3] * y1 + V[4] * y2) - o[12],
+                         w2 = sg * (V[2] * y0 + V[4] * y1 + V[5] * y2) - o[13];
+            gl += quad3(Lp.D, w0, w1, w2);
+        }
+        sp->gain_loops = gl;
+    }
 }
 template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, int buf, double odom_chi, double cur_chi, double linearGain, bool force, double& n_c,
                                              double& n_m) {
-    if (hd_tid() == 0) eval_and_solve_t0(M, buf, odom_chi, cur_chi, linearGain, force);
+#ifdef __CUDA_ARCH__
+    if (threadIdx.x < 32) eval_and_solve_w0(M, buf, odom_chi, cur_chi, linearGain, force);
+#else
+    eval_and_solve_w0(M, buf, odom_chi, cur_chi, linearGain, force);
+#endif
     bsync<NT>();
     n_c = M.U()->n_c; n_m = M.U()->n_m;
 }
@@ -873,6 +992,7 @@ struct CheckParams {
     double noise_eps;        // > 0: stop retrying once a rejected trial's own predicted gain is <= noise_eps * chi2 (below the
                              // round-off of the chi2 evaluation every later, smaller, retry is a coin flip on noise); 0 = replay all retries
     int max_tries, speculate, early_accept;
+    double acc_gain_ratio;   // the predicted GN gain is accumulated edge by edge (extra pass) once chi2 - model < ratio * chi2 (default 1e-6)
 };
 struct CheckResult {
     int verdict;
@@ -975,8 +1095,10 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     int iterations = 0, evals = 0, it = 0, tries = 0;
     double prev_hnorm = -1;      // norm of the last accepted step (speculation heuristic)
     bool have_norm = false, have_sd = false, need_rollback = false;
-    double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0, linearGain = 0;
-    double gain_loops = 0;       // loop part of the GN predicted gain of the CURRENT linearisation (M.U()->sol)
+    double hgnNorm = 0, linearGain = 0;
+    double* sc = M.U()->sc;
+    double &bb = sc[0], &bh = sc[1], &hh = sc[2], &bHb = sc[3], &alpha = sc[4], &hsdNorm = sc[5];
+    double& gain_loops = sc[6];      // loop part of the GN predicted gain of the CURRENT linearisation (M.U()->sol)
     int purpose = P_INIT, mode = STEP_NONE;
     double c1 = 0, c2 = 0;
     for (;;) {
@@ -1002,7 +1124,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             }
             const bool trial_gn = purpose != P_TRIAL_BLEND;
             const double hdlNorm = sqrt(so.hh);
-            if (trial_gn) linearGain = so.gain + gain_loops;     // h_gn^T H h_gn (= b^T h_gn for the exact GN step)
+            if (trial_gn) linearGain = so.gain + gain_loops;     // h_gn^T H h_gn (= b^T h_gn = chi2 - model for the exact GN step)
             ++evals;
             // loop edges at the trial state; thread 0 also solves the new linearisation when the step is going to be kept
             double n_c, n_m;

@@ -369,8 +369,8 @@ IPC_HD void gn_step_at3(const StepSpec3* sp, int j, const double* pre, const P3&
 
 struct SweepOut3 { double chi, mx, hh, gain; };
 
-template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int mode, double c1, double c2, ThreadState3& ts, SweepOut3& out, int& buf,
-                                     const int* spec_v) {
+template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int mode, double c1, double c2, bool acc_gain, ThreadState3& ts, SweepOut3& out,
+                                     int& buf, const int* spec_v) {
     const int k0 = ts.k0, k1 = ts.k1;
     const StepSpec3* sp = &M.U()->sol;
     double* spec = M.spec() + (size_t)buf * NSPEC * SPECW3;
@@ -404,7 +404,7 @@ template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int
             if (mode == STEP_GN) {
                 Lin3 eo; lin3(rec, oa, ob, rec + 7, eo);
                 const int rg = (k < sp->rs) ? 0 : (k < sp->re ? 1 : 2);
-                double to[NP3], ge = 0; edge_terms3(eo, rec + 7 + NS6, to, sp->z[rg], rec + 7, 0.0, &ge);
+                double to[NP3], ge = 0; edge_terms3(eo, rec + 7 + NS6, to, acc_gain ? sp->z[rg] : nullptr, rec + 7, 0.0, &ge);
                 gain += ge;
 #pragma unroll
                 for (int m = 0; m < NP3; ++m) pre[m] += to[m];
@@ -781,12 +781,13 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
     double prev_hnorm = -1;
     bool have_norm = false, have_sd = false, need_rollback = false;
     double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0, linearGain = 0;
-    double gain_loops = 0;
+    double gain_loops = 0, gn_gain_model = 0;
+    bool acc_gain = false;
     int purpose = P_INIT, mode = STEP_NONE;
     double c1 = 0, c2 = 0;
     for (;;) {
         if (need_rollback) { rollback3<NT>(M, ts); need_rollback = false; }
-        sweep3<NT>(M, odom, mode, c1, c2, ts, so, buf, spec_v); ++n_sweeps;
+        sweep3<NT>(M, odom, mode, c1, c2, acc_gain && mode == STEP_GN, ts, so, buf, spec_v); ++n_sweeps;
         bool start_iter = false, after_reject = false, decide = false;
         if (purpose == P_INIT) {
             double n_c, n_m;
@@ -804,7 +805,7 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
             if (specfail) { need_rollback = true; mode = STEP_NONE; purpose = P_RELIN_SPECFAIL; continue; }
             const bool trial_gn = purpose != P_TRIAL_BLEND;
             const double hdlNorm = sqrt(so.hh);
-            if (trial_gn) linearGain = so.gain + gain_loops;
+            if (trial_gn) linearGain = acc_gain ? so.gain + gain_loops : gn_gain_model;
             ++evals;
             double n_c, n_m;
             eval_and_solve3<NT>(M, buf, so.chi, cur_chi, linearGain, false, n_c, n_m);
@@ -843,6 +844,8 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
         }
         if (decide) {
             if (!have_norm) {
+                gn_gain_model = cur_chi - M.U()->sol.model;
+                acc_gain = true;   // always accumulate (the SE(3) edge loop is dominated by the 6x6 algebra)
                 if (prm.speculate && prev_hnorm >= 0 && 4 * prev_hnorm < delta) {
                     mode = STEP_GN; purpose = P_TRIAL_SPEC; c1 = 0; c2 = 1;
                     continue;

@@ -34,6 +34,7 @@ struct BatchArgs {
     double noise_eps;          // see CheckParams::noise_eps
     int max_tries;
     int speculate;             // apply the GN step before its norm is known when the trust region is far away
+    double acc_gain_ratio;     // see CheckParams::acc_gain_ratio
     int early_accept;          // verdict-only batches: stop once sum chi2 <= th (the verdict can no longer change)
     unsigned char* verdict;    // per check
     ipc_check_info* info;      // per check (may be null)

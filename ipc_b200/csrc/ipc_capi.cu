@@ -80,7 +80,7 @@ struct Bucket { int cap; int nt; int mode; };
 // 512 resident threads per SM (<= 128 registers): 16 x 32, 8 x 64, 4 x 128, 2 x 256 or 1 x 512 CTAs, so the serial part of
 // one check (capacitance solve by thread 0) overlaps with the sweeps of the CTAs sharing its SM. MODE 0 keeps 5 doubles per
 // vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
-const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 64, 0}, {800, 128, 0}, {2600, 256, 0}, {5400, 512, 0}, {1 << 30, 512, 1}};
+const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 64, 0}, {1300, 128, 0}, {2600, 256, 0}, {5400, 512, 0}, {1 << 30, 512, 1}};
 
 // SE(3): 7 doubles of state per vertex, 256 resident threads per SM (the 27 running prefix values need the registers)
 const Bucket kBuckets3[NB] = {{96, 32, 0}, {320, 64, 0}, {800, 128, 0}, {3700, 256, 0}, {3701, 256, 0}, {1 << 30, 256, 1}};
@@ -127,6 +127,9 @@ template <int NT, int MODE> int launch_se2(const BatchArgs& a, int grid, cudaStr
 
 }  // namespace
 
+struct ipc_handle;
+namespace { int size_scratch(ipc_handle* h); }
+
 struct ipc_handle {
     int dim = 2, d = 3, mw = 3;
     int n = 0, n_pad = 0;
@@ -138,6 +141,8 @@ struct ipc_handle {
     int speculate = 1;
     int early_accept = 0;
     int use_uniform = 1;              // allow the uniform-information kernels when the graph qualifies
+    double acc_gain_ratio = 1e-6;     // GN trials accumulate the predicted gain edge by edge once chi2 - model < ratio * chi2
+    Bucket buckets[NB];               // launch buckets (tunable: options bucket<i>_cap / bucket<i>_nt)
     HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
     // device graph
     double* d_odom9 = nullptr;        // AoS odometry records, general (9 doubles / edge)
@@ -173,6 +178,31 @@ struct ipc_handle {
 
 namespace {
 
+// per-CTA scratch: every bucket launch fits grid * stride into it; also uploads the bucket caps for plan_checks
+int size_scratch(ipc_handle* h) {
+    size_t need = 0;
+    const Bucket* kB = h->buckets;
+    for (int b = 0; b < NB; ++b) {
+        int lo_cap = b == 0 ? 0 : kB[b - 1].cap;
+        if (lo_cap >= h->n - 1) break;
+        int Lcap = (std::min(kB[b].cap, h->n - 1) + 1) & ~1;
+        size_t sm = smem_bytes(kB[b].mode, Lcap, h->dim, kB[b].nt);
+        if (kB[b].mode == 0 && sm > 226 * 1024) return fail(IPC_ERR_ARG, "bucket " + std::to_string(b) + " does not fit shared memory");
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
+        per_sm = std::min(per_sm, threads_per_sm(h->dim) / kB[b].nt);
+        need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kB[b].mode, Lcap, h->dim, kB[b].nt));
+    }
+    if (need > h->scratch_doubles) {
+        cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_doubles = 0;
+        CUDA_TRY(cudaMalloc(&h->d_scratch, need * sizeof(double)));
+        h->scratch_doubles = need;
+    }
+    int caps[NB];
+    for (int b = 0; b < NB; ++b) caps[b] = kB[b].cap;
+    CUDA_TRY(cudaMemcpy(h->d_bucket_cap, caps, sizeof(caps), cudaMemcpyHostToDevice));
+    return IPC_OK;
+}
+
 int ensure_batch_buffers(ipc_handle* h, int n_checks) {
     if (n_checks <= h->cap_checks) return IPC_OK;
     int cap = std::max(n_checks, 1024);
@@ -192,7 +222,7 @@ int ensure_batch_buffers(ipc_handle* h, int n_checks) {
 // enqueue plan + bucket launches + pack on `st`; all pointers device; work buffer sized for cap >= n_checks
 int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev, int* work_dev, int work_stride,
                   unsigned char* verdict_dev, uint32_t* bits_dev, ipc_check_info* info_dev, cudaStream_t st) {
-    const Bucket* kB = buckets_of(h->dim);
+    const Bucket* kB = h->buckets;
     CUDA_TRY(cudaMemsetAsync(h->d_counts, 0, sizeof(int) * 2 * NB, st));
     CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(unsigned long long) * 2, st));
     const int loop_stride_ints = (int)((h->dim == 2 ? sizeof(LoopRec2) : sizeof(se3::LoopRec3)) / sizeof(int));
@@ -213,7 +243,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
         a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
-        a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept;
+        a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept; a.acc_gain_ratio = h->acc_gain_ratio;
         a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch;
         a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap, h->dim, bk.nt);
         size_t sm = smem_bytes(bk.mode, a.Lcap, h->dim, bk.nt);
@@ -296,24 +326,8 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     CUDA_TRY(cudaMalloc(&h->d_counts, sizeof(int) * 2 * NB));
     CUDA_TRY(cudaMalloc(&h->d_bucket_cap, sizeof(int) * NB));
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * 2));
-    int caps[NB];
-    for (int b = 0; b < NB; ++b) caps[b] = buckets_of(dim)[b].cap;
-    CUDA_TRY(cudaMemcpy(h->d_bucket_cap, caps, sizeof(caps), cudaMemcpyHostToDevice));
-    {   // per-CTA scratch: every bucket launch fits grid * stride into it
-        size_t need = 0;
-        const Bucket* kB = buckets_of(dim);
-        for (int b = 0; b < NB; ++b) {
-            int lo_cap = b == 0 ? 0 : kB[b - 1].cap;
-            if (lo_cap >= n_poses - 1) break;
-            int Lcap = (std::min(kB[b].cap, n_poses - 1) + 1) & ~1;
-            size_t sm = smem_bytes(kB[b].mode, Lcap, dim, kB[b].nt);
-            int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-            per_sm = std::min(per_sm, threads_per_sm(dim) / kB[b].nt);
-            need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kB[b].mode, Lcap, dim, kB[b].nt));
-        }
-        h->scratch_doubles = need;
-        CUDA_TRY(cudaMalloc(&h->d_scratch, need * sizeof(double)));
-    }
+    for (int b = 0; b < NB; ++b) h->buckets[b] = buckets_of(dim)[b];
+    { int rc2 = size_scratch(h); if (rc2 != IPC_OK) return rc2; }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     if (dim == 2) {   // IPC::IPC: vertex 0 at the origin, everything else dead-reckoned (propagateGuess, src/consensus_utils.cpp:98-116)
         CUDA_TRY(cudaMalloc(&h->d_pose, sizeof(double) * 5 * (size_t)n_poses));
@@ -352,6 +366,19 @@ void ipc_destroy(ipc_handle* h) {
 int ipc_set_option(ipc_handle* h, const char* name, double value) {
     if (!h || !name) return fail(IPC_ERR_ARG, "null argument");
     if (!strcmp(name, "noise_exit")) { h->noise_eps = value == 1.0 ? 1e-13 : value; return IPC_OK; }   // 0 = off, 1 = default eps, else eps
+    if (!strcmp(name, "acc_gain_ratio")) { h->acc_gain_ratio = value; return IPC_OK; }
+    if (!strncmp(name, "bucket", 6) && name[6] >= '0' && name[6] < '0' + NB - 1 && name[7] == '_') {
+        const int b = name[6] - '0';
+        if (!strcmp(name + 8, "cap")) h->buckets[b].cap = (int)value;
+        else if (!strcmp(name + 8, "nt")) {
+            const int nt = (int)value;
+            if (nt != 32 && nt != 64 && nt != 128 && nt != 256 && !(nt == 512 && h->dim == 2)) return fail(IPC_ERR_ARG, "unsupported thread count");
+            h->buckets[b].nt = nt;
+        } else return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
+        for (int q = 1; q < NB - 1; ++q) if (h->buckets[q].cap < h->buckets[q - 1].cap) return fail(IPC_ERR_ARG, "bucket caps must be non-decreasing");
+        CUDA_TRY(cudaSetDevice(h->device));
+        return size_scratch(h);
+    }
     if (!strcmp(name, "use_uniform")) { h->use_uniform = value != 0; return IPC_OK; }
     if (!strcmp(name, "speculate")) { h->speculate = value != 0; return IPC_OK; }
     if (!strcmp(name, "early_accept")) { h->early_accept = value != 0; return IPC_OK; }
