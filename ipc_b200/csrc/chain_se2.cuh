@@ -446,38 +446,16 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     bool has_spec = false;
 #pragma unroll
     for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
-    // records and state of the next edge are fetched one iteration ahead (L2 latency of the odometry records)
-    OdomRec<UNI> rn; double sn[5] = {0, 0, 0, 0, 0}, gn[6] = {0, 0, 0, 0, 0, 0};
-    if (k0 < k1) {
-        odom_load<UNI>(O, k0, rn);
-        const double* pp = M.P(k0 + 1);
-#pragma unroll
-        for (int q = 0; q < 5; ++q) sn[q] = pp[q];
-        if (mode == STEP_BLEND) {
-            const double* gq = M.G(k0 + 1);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) gn[q] = gq[q];
-        }
-    }
+    // the odometry record of the next edge is fetched one iteration ahead (L2 latency); state comes from shared memory
+    OdomRec<UNI> rn;
+    if (k0 < k1) odom_load<UNI>(O, k0, rn);
     for (int k = k0; k < k1; ++k) {
         const int j = k + 1;
         const OdomRec<UNI> r = rn;
-        const P2 ob{sn[0], sn[1], sn[2]};
-        const double ocb = sn[3], osb = sn[4];
-        double g6[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) g6[q] = gn[q];
-        if (j < k1) {
-            odom_load<UNI>(O, k + 1, rn);
-            const double* pp = M.P(j + 1);
-#pragma unroll
-            for (int q = 0; q < 5; ++q) sn[q] = pp[q];
-            if (mode == STEP_BLEND) {
-                const double* gq = M.G(j + 1);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) gn[q] = gq[q];
-            }
-        }
+        if (j < k1) odom_load<UNI>(O, k + 1, rn);
+        const double* pq0 = M.P(j);
+        const P2 ob{pq0[0], pq0[1], pq0[2]};
+        const double ocb = pq0[3], osb = pq0[4];
         P2 nb = ob;
         double ncb = ocb, nsb = osb;
         if (mode != STEP_NONE) {
@@ -507,6 +485,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
                 for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
                 gn_step_at(sp, j, pre, ob.x, ob.y, h);
             } else {
+                const double* g6 = M.G(j);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) h[q] = c1 * g6[q] + c2 * g6[3 + q];
             }

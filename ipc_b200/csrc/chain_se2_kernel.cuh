@@ -6,8 +6,10 @@
 
 namespace ipcb {
 
-template <int NT, int MODE, bool UNI>
-__global__ void __launch_bounds__(NT, 512 / NT) chain_check_se2(BatchArgs A) {
+// MINB = CTAs per SM the kernel is compiled for: registers per thread <= 65536 / (NT * MINB). The edge loop wants ~170
+// registers; variants with fewer threads and no spills beat fuller SMs that spill (profiles/).
+template <int NT, int MODE, bool UNI, int MINB>
+__global__ void __launch_bounds__(NT, MINB) chain_check_se2(BatchArgs A) {
     extern __shared__ __align__(16) double sm[];
     const int capv = A.Lcap + 2;
     double* scr = A.scratch + (size_t)blockIdx.x * A.scratch_stride;

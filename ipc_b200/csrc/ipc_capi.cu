@@ -75,15 +75,15 @@ __global__ void pack_bits(const unsigned char* __restrict__ verdict, int n, uint
 namespace {
 
 constexpr int NB = 6;   // launch buckets
-struct Bucket { int cap; int nt; int mode; };
+struct Bucket { int cap; int nt; int mode; int minb; };   // minb: CTAs per SM the variant is compiled for (register budget)
 // window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh). Every kernel is compiled for
 // 512 resident threads per SM (<= 128 registers): 16 x 32, 8 x 64, 4 x 128, 2 x 256 or 1 x 512 CTAs, so the serial part of
 // one check (capacitance solve by thread 0) overlaps with the sweeps of the CTAs sharing its SM. MODE 0 keeps 5 doubles per
 // vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
-const Bucket kBuckets2[NB] = {{96, 32, 0}, {320, 64, 0}, {1300, 128, 0}, {2600, 256, 0}, {5400, 512, 0}, {1 << 30, 512, 1}};
+const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3}, {2600, 128, 0, 2}, {5400, 256, 0, 1}, {1 << 30, 512, 1, 1}};
 
 // SE(3): 7 doubles of state per vertex, 256 resident threads per SM (the 27 running prefix values need the registers)
-const Bucket kBuckets3[NB] = {{96, 32, 0}, {320, 64, 0}, {800, 128, 0}, {3700, 256, 0}, {3701, 256, 0}, {1 << 30, 256, 1}};
+const Bucket kBuckets3[NB] = {{96, 32, 0, 8}, {320, 64, 0, 4}, {800, 128, 0, 2}, {3700, 256, 0, 1}, {3701, 256, 0, 1}, {1 << 30, 256, 1, 1}};
 const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
 int threads_per_sm(int dim) { return dim == 2 ? 512 : 256; }
 
@@ -110,19 +110,27 @@ template <int NT, int MODE> int launch_se3(const BatchArgs& a, int grid, cudaStr
     return IPC_OK;
 }
 
-template <int NT, int MODE, bool UNI> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
+template <int NT, int MODE, bool UNI, int MINB> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
     size_t sm = smem_bytes(MODE, a.Lcap);
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         attr_done = true;
     }
-    chain_check_se2<NT, MODE, UNI><<<grid, NT, sm, st>>>(a);
+    chain_check_se2<NT, MODE, UNI, MINB><<<grid, NT, sm, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return IPC_OK;
 }
-template <int NT, int MODE> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
-    return uni ? launch_se2u<NT, MODE, true>(a, grid, st) : launch_se2u<NT, MODE, false>(a, grid, st);
+template <int NT, int MODE, int MINB> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
+    return uni ? launch_se2u<NT, MODE, true, MINB>(a, grid, st) : launch_se2u<NT, MODE, false, MINB>(a, grid, st);
+}
+// the instantiated (threads, CTAs per SM) variants
+int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
+    if (mode == 1) return launch_se2<512, 1, 1>(a, grid, st, uni);
+#define V(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2<NT_, 0, MB_>(a, grid, st, uni);
+    V(32, 16) V(32, 8) V(64, 8) V(64, 4) V(64, 2) V(128, 4) V(128, 3) V(128, 2) V(128, 1) V(192, 2) V(256, 2) V(256, 1) V(384, 1) V(512, 1)
+#undef V
+    return fail(IPC_ERR_ARG, "no kernel variant for " + std::to_string(nt) + " threads x " + std::to_string(minb) + " CTAs per SM");
 }
 
 }  // namespace
@@ -189,7 +197,7 @@ int size_scratch(ipc_handle* h) {
         size_t sm = smem_bytes(kB[b].mode, Lcap, h->dim, kB[b].nt);
         if (kB[b].mode == 0 && sm > 226 * 1024) return fail(IPC_ERR_ARG, "bucket " + std::to_string(b) + " does not fit shared memory");
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-        per_sm = std::min(per_sm, threads_per_sm(h->dim) / kB[b].nt);
+        per_sm = std::min(per_sm, kB[b].minb);
         need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kB[b].mode, Lcap, h->dim, kB[b].nt));
     }
     if (need > h->scratch_doubles) {
@@ -248,7 +256,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap, h->dim, bk.nt);
         size_t sm = smem_bytes(bk.mode, a.Lcap, h->dim, bk.nt);
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
-        per_sm = std::min(per_sm, threads_per_sm(h->dim) / bk.nt);
+        per_sm = std::min(per_sm, bk.minb);
         int grid = std::min(n_checks, h->n_sm * per_sm);
         grid = (int)std::min<size_t>(grid, h->scratch_doubles / a.scratch_stride);
         int rc = IPC_OK;
@@ -258,12 +266,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
             else if (bk.nt == 64) rc = launch_se3<64, 0>(a, grid, st);
             else if (bk.nt == 128) rc = launch_se3<128, 0>(a, grid, st);
             else rc = launch_se3<256, 0>(a, grid, st);
-        } else if (bk.mode == 1) rc = launch_se2<512, 1>(a, grid, st, uni);
-        else if (bk.nt == 32) rc = launch_se2<32, 0>(a, grid, st, uni);
-        else if (bk.nt == 64) rc = launch_se2<64, 0>(a, grid, st, uni);
-        else if (bk.nt == 128) rc = launch_se2<128, 0>(a, grid, st, uni);
-        else if (bk.nt == 256) rc = launch_se2<256, 0>(a, grid, st, uni);
-        else rc = launch_se2<512, 0>(a, grid, st, uni);
+        } else rc = launch_se2_variant(bk.nt, bk.minb, bk.mode, a, grid, st, uni);
         if (rc != IPC_OK) return rc;
         ++launches;
     }
@@ -370,11 +373,9 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
     if (!strncmp(name, "bucket", 6) && name[6] >= '0' && name[6] < '0' + NB - 1 && name[7] == '_') {
         const int b = name[6] - '0';
         if (!strcmp(name + 8, "cap")) h->buckets[b].cap = (int)value;
-        else if (!strcmp(name + 8, "nt")) {
-            const int nt = (int)value;
-            if (nt != 32 && nt != 64 && nt != 128 && nt != 256 && !(nt == 512 && h->dim == 2)) return fail(IPC_ERR_ARG, "unsupported thread count");
-            h->buckets[b].nt = nt;
-        } else return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
+        else if (!strcmp(name + 8, "nt")) h->buckets[b].nt = (int)value;        // (nt, minb) must name an instantiated variant: checked at launch
+        else if (!strcmp(name + 8, "minb")) h->buckets[b].minb = (int)value;
+        else return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
         for (int q = 1; q < NB - 1; ++q) if (h->buckets[q].cap < h->buckets[q - 1].cap) return fail(IPC_ERR_ARG, "bucket caps must be non-decreasing");
         CUDA_TRY(cudaSetDevice(h->device));
         return size_scratch(h);

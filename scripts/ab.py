@@ -12,14 +12,13 @@ dev = torch.device("cuda", 0)
 md, cd = torch.from_numpy(mem).to(dev), torch.from_numpy(cnd).to(dev)
 bits = torch.zeros((n_s + 31) // 32, dtype=torch.int32, device=dev)
 variants = {
-    "default": {},
-    "gain_model_only": {"acc_gain_ratio": 0.0},
-    "gain_always": {"acc_gain_ratio": 1e30},
-    "old_buckets_800": {"bucket2_cap": 800},
-    "b3_2000": {"bucket3_cap": 2000},
-    "b3_2000_b2_1000": {"bucket3_cap": 2000, "bucket2_cap": 1000},
-    "no_speculate": {"speculate": 0},
-    "early_accept": {"early_accept": 1},
+    "default(128x3,128x2,256x1)": {},
+    "b3_64x2": {"bucket3_nt": 64, "bucket3_minb": 2},
+    "b2_64x4": {"bucket2_nt": 64, "bucket2_minb": 4},
+    "b4_128x1": {"bucket4_nt": 128, "bucket4_minb": 1},
+    "b1_64x4": {"bucket1_minb": 4},
+    "b0_32x8": {"bucket0_minb": 8},
+    "b2_cap1700": {"bucket2_cap": 1700},
 }
 ref = None
 for name, opts in variants.items():
