@@ -235,3 +235,26 @@ def test_se3_matches_oracle_live_and_matrix(gpu_lib, oracle_lib):
     got = _unpack(rows, g.n_loops)
     assert np.array_equal(got, got.T)
     ipc.close()
+
+
+def test_launch_variants_and_global_state_mode(gpu_lib):
+    """Every launch shape must give the same verdicts: (a) all checks forced through the global-state kernel (MODE 1, used for
+    windows longer than shared memory holds), (b) a few alternative (threads, CTAs per SM) variants, (c) the general
+    (non-uniform information) kernel on a graph that qualifies for the uniform one."""
+    z, g, cfg = load("pairs_se2_m3500.npz")
+    ref = None
+    for opts in ({}, {"bucket0_cap": 4, "bucket1_cap": 4, "bucket2_cap": 4, "bucket3_cap": 4, "bucket4_cap": 4},
+                 {"bucket0_minb": 8, "bucket1_minb": 4, "bucket2_nt": 64, "bucket2_minb": 4}, {"use_uniform": 0}, {"speculate": 0}):
+        ipc = gpu_lib.IPC.from_graph(g, cfg)
+        for k, v in opts.items():
+            ipc.set_option(k, v)
+        acc, info = ipc.check_batch(z["member"], z["cand"])
+        _compare(acc, info, z)
+        if ref is None:
+            ref = info["max_chi2"].copy()
+        assert rel_err(info["max_chi2"], ref).max() < 1e-6
+        ipc.close()
+    with pytest.raises(api.IpcError):
+        ipc = gpu_lib.IPC.from_graph(g, cfg)
+        ipc.set_option("bucket0_nt", 96)          # not an instantiated variant: fails loudly at launch
+        ipc.check_batch(z["member"], z["cand"])
