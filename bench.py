@@ -152,7 +152,11 @@ def run_reference(args):
 
 
 def run_ours(args):
-    os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    # keep stdout to the ONE JSON line: libraries (NCCL prints its version) write to fd 1 from C, so park fd 1 on stderr
+    sys.stdout.flush()
+    _saved_fd1 = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from ipc_b200 import api
@@ -276,7 +280,10 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                    "sample": f"seeded random sample of {ns} checks of the same list, {dt:.1f} s, one check per thread",
                                    "verdict_mismatches_vs_gpu": int((gacc != oacc).sum())}
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(_saved_fd1, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     ipc.close()
     if world > 1:
         dist.destroy_process_group()

@@ -137,6 +137,7 @@ int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid,
 
 struct ipc_handle;
 namespace { int size_scratch(ipc_handle* h); }
+extern "C" { namespace { int cl_ensure(ipc_handle* h, int L, int K); } }
 
 struct ipc_handle {
     int dim = 2, d = 3, mw = 3;
@@ -342,6 +343,15 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
         CUDA_TRY(cudaMalloc(&h->cl_info, sizeof(int)));
         if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(IPC_ERR_CUDA, "cusolverDnCreate failed");
         cusolverDnSetStream(h->solver, h->stream);
+        {   // warm cuSOLVER up here (its first potrf loads modules for seconds) so that the first agreementCheck is not charged for it
+            int rcw = cl_ensure(h, 16, 1);
+            if (rcw != IPC_OK) return rcw;
+            const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            CUDA_TRY(cudaMemcpyAsync(h->cl_S, eye, sizeof(eye), cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaMemcpyAsync(h->cl_z, eye, 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, 3, h->cl_S, 3, h->cl_work, h->cl_work_n, h->cl_info);
+            cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, 3, 1, h->cl_S, 3, h->cl_z, 3, h->cl_info);
+        }
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
     CUDA_TRY(cudaEventCreate(&h->ev_k0));
@@ -764,7 +774,11 @@ int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, i
     MTRY(cudaMalloc(&d_rows, sizeof(uint32_t) * (size_t)n * words));
     overlap_fill<<<n, 256, 0, st>>>(d_lo, d_hi, d_order, n, d_rowptr, d_member, d_cand, d_pi, d_pj);
     MTRY(cudaGetLastError());
+    // only verdict bits leave this call: the rigorous early accept (sum chi2 <= th can no longer be rejected) applies
+    const int saved_ea = h->early_accept;
+    h->early_accept = 1;
     int rc = enqueue_batch(h, n_checks, d_member, d_cand, d_work, n_checks, d_verdict, nullptr, nullptr, st);
+    h->early_accept = saved_ea;
     if (rc != IPC_OK) { cleanup(); return rc; }
     {
         const long long warps = (long long)n * words;

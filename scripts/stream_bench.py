@@ -10,7 +10,9 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 with_oracle = "--oracle" in sys.argv
 g, cfg = synth.make_config(name, scale=scale)
 order = g.time_order()
+t = time.perf_counter()
 ipc = api.IPC.from_graph(g, cfg, candidates=False)
+create_s = time.perf_counter() - t
 acc = np.zeros(len(order), dtype=bool); mx = np.zeros(len(order)); K = np.zeros(len(order), dtype=int); L = np.zeros(len(order), dtype=int)
 ev = np.zeros(len(order), dtype=int)
 t = time.perf_counter()
@@ -20,7 +22,7 @@ for k, l in enumerate(order):
 dt = time.perf_counter() - t
 truth = order < g.n_true
 tp = int((acc & truth).sum()); fp = int((acc & ~truth).sum()); fn = int((~acc & truth).sum())
-out = {"config": name, "scale": scale, "n_poses": g.n_poses, "candidates": len(order), "gpu_stream_s": dt, "gpu_checks_per_s": len(order) / dt,
+out = {"config": name, "scale": scale, "create_s": create_s, "n_poses": g.n_poses, "candidates": len(order), "gpu_stream_s": dt, "gpu_checks_per_s": len(order) / dt,
        "accepted": int(acc.sum()), "precision": tp / max(1, tp + fp), "recall": tp / max(1, tp + fn), "K_median": float(np.median(K)), "K_max": int(K.max()),
        "L_median": float(np.median(L)), "evals_mean": float(ev.mean())}
 if with_oracle:
