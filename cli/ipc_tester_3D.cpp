@@ -1,4 +1,4 @@
-// ipc_tester_3D -c <config.yaml> — drop-in for /root/reference/examples/ipc_tester_3D.cpp:10-35. Parses SE(3) configs and
-// graphs; the SE(3) CUDA path is not built in this revision, so the run stops with IPC_ERR_UNSUPPORTED after --parse-only work.
+// ipc_tester_3D -c <config.yaml> — drop-in for /root/reference/examples/ipc_tester_3D.cpp:10-35 over libipc_b200.so
+// (EDGE_SE3:QUAT / VERTEX_SE3:QUAT graphs, IPC<EdgeSE3, VertexSE3>).
 #include "ipc_host.hpp"
 int main(int argc, char** argv) { return ipc_host::tester_main(argc, argv, 3); }

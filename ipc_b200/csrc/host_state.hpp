@@ -131,7 +131,8 @@ struct HostState {
         for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { rec[7 + k] = 0.5 * (W[r * 6 + c] + W[c * 6 + r]); rec[28 + k] = Wi[r * 6 + c]; ++k; }
         return true;
     }
-    bool build_odom_aos3(int n_pad, std::vector<double>& rec) const {
+    bool build_odom_aos3(int n_pad, std::vector<double>& rec, bool raw = false) const {
+        const std::vector<double>& odom_info = raw ? odom_info_raw : this->odom_info;
         rec.assign((size_t)49 * n_pad, 0.0);
         for (int k = 0; k < n_pad; ++k) {
             double* r = &rec[(size_t)k * 49];

@@ -13,6 +13,7 @@
 #include "host_state.hpp"
 #include "matrix.cuh"
 #include "cluster_se2.cuh"
+#include "cluster_se3.cuh"
 #include <cusolverDn.h>
 
 using namespace ipcb;
@@ -179,7 +180,9 @@ struct ipc_handle {
     ClBuffers clB[2] = {};
     double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_work = nullptr;
     int* cl_info = nullptr;
-    ClLoop* cl_loops = nullptr;
+    void* cl_loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the current cluster
+    double* cl_stage = nullptr;       // SE(3) dead-reckoning staging (CL_NT poses)
+    double* d_odom49_raw = nullptr;   // SE(3) records with the information as given (final optimisation)
     double* cl_hres = nullptr;        // pinned
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
     bool ev_valid = false;
@@ -333,10 +336,16 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     for (int b = 0; b < NB; ++b) h->buckets[b] = buckets_of(dim)[b];
     { int rc2 = size_scratch(h); if (rc2 != IPC_OK) return rc2; }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    if (dim == 2) {   // IPC::IPC: vertex 0 at the origin, everything else dead-reckoned (propagateGuess, src/consensus_utils.cpp:98-116)
-        CUDA_TRY(cudaMalloc(&h->d_pose, sizeof(double) * 5 * (size_t)n_poses));
-        cl_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
-        cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, 0, n_poses, h->d_pose);
+    {   // IPC::IPC: vertex 0 at the origin, everything else dead-reckoned (propagateGuess, src/consensus_utils.cpp:98-116)
+        CUDA_TRY(cudaMalloc(&h->d_pose, sizeof(double) * (dim == 2 ? 5 : 7) * (size_t)n_poses));
+        if (dim == 2) {
+            cl_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
+            cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, 0, n_poses, h->d_pose);
+        } else {
+            CUDA_TRY(cudaMalloc(&h->cl_stage, sizeof(double) * 7 * CL_NT));
+            cl3_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
+            cl3_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom49, 0, n_poses, h->d_pose, h->cl_stage);
+        }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMallocHost(&h->cl_hres, sizeof(double) * CL_NRES));
         CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES));
@@ -366,7 +375,7 @@ void ipc_destroy(ipc_handle* h) {
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_odom49); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
     cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
-    cudaFree(h->cl_info); cudaFree(h->cl_loops);
+    cudaFree(h->cl_info); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
     for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
     if (h->cl_hres) cudaFreeHost(h->cl_hres);
     if (h->solver) cusolverDnDestroy(h->solver);
@@ -515,30 +524,31 @@ int ipc_get_consensus(ipc_handle* h, int* from_to, int capacity) {
 namespace {
 
 int cl_ensure(ipc_handle* h, int L, int K) {
+    const int PW = h->dim == 2 ? 5 : 7, NPQ = h->dim == 2 ? NPRE : se3::NP3, DQ = h->dim == 2 ? 3 : 6, LTW = h->dim == 2 ? 12 : CL3_LT;
     if (L > h->cl_Lcap) {
         int cap = std::max(L, 256);
         for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); h->clB[q].W = h->clB[q].T = h->clB[q].P = h->clB[q].chi_e = nullptr; }
         cudaFree(h->cl_G); cudaFree(h->cl_H); h->cl_G = h->cl_H = nullptr; h->cl_Lcap = 0;
         for (int q = 0; q < 2; ++q) {
-            CUDA_TRY(cudaMalloc(&h->clB[q].W, sizeof(double) * 5 * (size_t)(cap + 1)));
-            CUDA_TRY(cudaMalloc(&h->clB[q].T, sizeof(double) * NPRE * (size_t)cap));
-            CUDA_TRY(cudaMalloc(&h->clB[q].P, sizeof(double) * NPRE * (size_t)(cap + 1)));
+            CUDA_TRY(cudaMalloc(&h->clB[q].W, sizeof(double) * PW * (size_t)(cap + 1)));
+            CUDA_TRY(cudaMalloc(&h->clB[q].T, sizeof(double) * NPQ * (size_t)cap));
+            CUDA_TRY(cudaMalloc(&h->clB[q].P, sizeof(double) * NPQ * (size_t)(cap + 1)));
             CUDA_TRY(cudaMalloc(&h->clB[q].chi_e, sizeof(double) * (size_t)cap));
         }
-        CUDA_TRY(cudaMalloc(&h->cl_G, sizeof(double) * 3 * (size_t)(cap + 1)));
-        CUDA_TRY(cudaMalloc(&h->cl_H, sizeof(double) * 3 * (size_t)(cap + 1)));
+        CUDA_TRY(cudaMalloc(&h->cl_G, sizeof(double) * DQ * (size_t)(cap + 1)));
+        CUDA_TRY(cudaMalloc(&h->cl_H, sizeof(double) * DQ * (size_t)(cap + 1)));
         h->cl_Lcap = cap;
     }
     if (K > h->cl_Kcap) {
         int cap = std::max(K + K / 2, 64);
         for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].lt); h->clB[q].lt = nullptr; }
         cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_loops); cudaFree(h->cl_work); h->cl_S = h->cl_z = h->cl_work = nullptr; h->cl_loops = nullptr; h->cl_Kcap = 0;
-        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&h->clB[q].lt, sizeof(double) * 12 * (size_t)cap));
-        CUDA_TRY(cudaMalloc(&h->cl_S, sizeof(double) * 9 * (size_t)cap * cap));
-        CUDA_TRY(cudaMalloc(&h->cl_z, sizeof(double) * 3 * (size_t)cap));
-        CUDA_TRY(cudaMalloc(&h->cl_loops, sizeof(ClLoop) * (size_t)cap));
+        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&h->clB[q].lt, sizeof(double) * LTW * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&h->cl_S, sizeof(double) * DQ * DQ * (size_t)cap * cap));
+        CUDA_TRY(cudaMalloc(&h->cl_z, sizeof(double) * DQ * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&h->cl_loops, std::max(sizeof(ClLoop), sizeof(ClLoop3)) * (size_t)cap));
         int lwork = 0;
-        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, 3 * cap, h->cl_S, 3 * cap, &lwork) != CUSOLVER_STATUS_SUCCESS)
+        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, DQ * cap, h->cl_S, DQ * cap, &lwork) != CUSOLVER_STATUS_SUCCESS)
             return fail(IPC_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
         CUDA_TRY(cudaMalloc(&h->cl_work, sizeof(double) * (size_t)std::max(lwork, 1)));
         h->cl_work_n = lwork; h->cl_Kcap = cap;
@@ -554,15 +564,24 @@ int cl_read(ipc_handle* h) {   // device scalars -> pinned host buffer
 
 // isAgreeingWithCurrentState on the window [lo, hi] with the K loops already uploaded (the candidate is the last one)
 int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_base, bool* ok_out, ipc_check_info* info, int* cur_buf, bool exact_iters = false) {
-    const double* odom9 = h->cl_odom ? h->cl_odom : h->d_odom9;
+    const bool d2 = h->dim == 2;
+    const double* odom9 = h->cl_odom ? h->cl_odom : (d2 ? h->d_odom9 : h->d_odom49);
+    const ClLoop* loops2 = static_cast<const ClLoop*>(h->cl_loops);
+    const ClLoop3* loops3 = static_cast<const ClLoop3*>(h->cl_loops);
     const int L = hi - lo, Lcap = h->cl_Lcap;
     cudaStream_t st = h->stream;
     int cur = 0;
     double* res = h->cl_res;
     const double* hr = h->cl_hres;
-    cl_load_window<<<16, 256, 0, st>>>(h->d_pose, lo, L, h->clB[0].W);
-    cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[cur], res);
-    cl_loops<<<1, 256, 0, st>>>(h->cl_loops, K, h->clB[cur], res);
+    if (d2) {
+        cl_load_window<<<16, 256, 0, st>>>(h->d_pose, lo, L, h->clB[0].W);
+        cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[cur], res);
+        cl_loops<<<1, 256, 0, st>>>(loops2, K, h->clB[cur], res);
+    } else {
+        cl_copy<<<16, 256, 0, st>>>(h->d_pose + 7 * (size_t)lo, h->clB[0].W, 7LL * (L + 1));
+        cl3_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[cur], res);
+        cl3_loops<<<1, 256, 0, st>>>(loops3, K, h->clB[cur], res);
+    }
     CUDA_TRY(cudaGetLastError());
     int rc = cl_read(h); if (rc != IPC_OK) return rc;
     double cur_chi = hr[0] + hr[2], cur_max = std::max(hr[1], hr[3]), cand_chi = hr[4];
@@ -571,17 +590,19 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
     double delta = 1e4;
     int iterations = 0, evals = 0;
     bool ok = true;
-    const int n3 = 3 * K;
+    const int n3 = (d2 ? 3 : 6) * K;
     for (int it = 0; it < max_iter && ok; ++it) {
         // ---- Gauss-Newton step of the current linearisation
         {
             const long long nb = ((long long)K * K + 255) / 256;
-            cl_assemble<<<(unsigned)nb, 256, 0, st>>>(h->cl_loops, K, Lcap, h->clB[cur], h->cl_S, h->cl_z);
+            if (d2) cl_assemble<<<(unsigned)nb, 256, 0, st>>>(loops2, K, Lcap, h->clB[cur], h->cl_S, h->cl_z);
+            else cl3_assemble<<<(unsigned)nb, 256, 0, st>>>(loops3, K, Lcap, h->clB[cur], h->cl_S, h->cl_z);
             if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, n3, h->cl_S, n3, h->cl_work, h->cl_work_n, h->cl_info) != CUSOLVER_STATUS_SUCCESS)
                 return fail(IPC_ERR_CUDA, "cusolverDnDpotrf failed");
             if (cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, n3, 1, h->cl_S, n3, h->cl_z, n3, h->cl_info) != CUSOLVER_STATUS_SUCCESS)
                 return fail(IPC_ERR_CUDA, "cusolverDnDpotrs failed");
-            cl_gn_step<<<1, CL_NT, 0, st>>>(h->cl_loops, K, L, Lcap, h->clB[cur], h->cl_z, h->cl_H, res);
+            if (d2) cl_gn_step<<<1, CL_NT, 0, st>>>(loops2, K, L, Lcap, h->clB[cur], h->cl_z, h->cl_H, res);
+            else cl3_gn_step<<<1, CL_NT, 0, st>>>(loops3, K, L, Lcap, h->clB[cur], h->cl_z, h->cl_H, res);
             CUDA_TRY(cudaGetLastError());
             rc = cl_read(h); if (rc != IPC_OK) return rc;
         }
@@ -596,9 +617,15 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
             const bool trial_gn = hgnNorm < delta;
             if (!trial_gn) {
                 if (!have_sd) {
-                    cl_grad_odom<<<1, CL_NT, 0, st>>>(odom9, lo, L, h->clB[cur], h->cl_G);
-                    cl_grad_loops<<<1, 32, 0, st>>>(h->cl_loops, K, h->clB[cur], h->cl_G);
-                    cl_sd_scalars<<<1, CL_NT, 0, st>>>(odom9, h->cl_loops, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
+                    if (d2) {
+                        cl_grad_odom<<<1, CL_NT, 0, st>>>(odom9, lo, L, h->clB[cur], h->cl_G);
+                        cl_grad_loops<<<1, 32, 0, st>>>(loops2, K, h->clB[cur], h->cl_G);
+                        cl_sd_scalars<<<1, CL_NT, 0, st>>>(odom9, loops2, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
+                    } else {
+                        cl3_grad_odom<<<1, CL_NT, 0, st>>>(odom9, lo, L, h->clB[cur], h->cl_G);
+                        cl3_grad_loops<<<1, 32, 0, st>>>(loops3, K, h->clB[cur], h->cl_G);
+                        cl3_sd_scalars<<<1, CL_NT, 0, st>>>(odom9, loops3, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
+                    }
                     CUDA_TRY(cudaGetLastError());
                     rc = cl_read(h); if (rc != IPC_OK) return rc;
                     bb = hr[7]; bh = hr[8]; bHb = hr[9];
@@ -616,9 +643,15 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
                 linearGain = -(c1 * c1 * bHb + 2 * c1 * c2 * bb + c2 * c2 * bh) + 2 * (c1 * bb + c2 * bh);
             }
             const int nxt = cur ^ 1;
-            cl_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
-            cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[nxt], res);
-            cl_loops<<<1, 256, 0, st>>>(h->cl_loops, K, h->clB[nxt], res);
+            if (d2) {
+                cl_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
+                cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[nxt], res);
+                cl_loops<<<1, 256, 0, st>>>(loops2, K, h->clB[nxt], res);
+            } else {
+                cl3_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
+                cl3_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[nxt], res);
+                cl3_loops<<<1, 256, 0, st>>>(loops3, K, h->clB[nxt], res);
+            }
             CUDA_TRY(cudaGetLastError());
             rc = cl_read(h); if (rc != IPC_OK) return rc;
             ++evals;
@@ -647,7 +680,6 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_ba
 
 int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, const double* info, int* accepted, ipc_check_info* out_info) {
     if (!h || !meas || !info || !accepted) return fail(IPC_ERR_ARG, "null argument");
-    if (h->dim != 2) return fail(IPC_ERR_UNSUPPORTED, "SE(3) stream not built in this revision");
     if (from < 0 || to < 0 || from >= h->n || to >= h->n || from == to) return fail(IPC_ERR_ARG, "invalid vertex ids");
     CUDA_TRY(cudaSetDevice(h->device));
     // computeIndependentSubgraph, src/consensus.cpp:123-171 (integer logic on the host mirror)
@@ -659,25 +691,49 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
     const int ib = slow ? h->cfg.slow_reject_iter_base : h->cfg.fast_reject_iter_base;
     int rc = cl_ensure(h, hi - lo, K);
     if (rc != IPC_OK) return rc;
-    std::vector<ClLoop> loops(K);
-    auto fill = [&](ClLoop& o, int f, int t, const double* m, const double* w) {
-        o.jf = f - lo; o.jt = t - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
-        HostState::se2_edge_record(m, w, 1.0, o.meas, o.D);
-        HostState::inv_sym3_host(o.D, o.V);
-    };
-    for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; fill(loops[i], e.from, e.to, e.meas.data(), e.info.data()); }
-    fill(loops[K - 1], from, to, meas, info);
-    CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice, h->stream));
+    std::vector<ClLoop> loops;
+    std::vector<ClLoop3> loops3v;
+    if (h->dim == 2) {
+        loops.resize(K);
+        auto fill = [&](ClLoop& o, int f, int t, const double* m, const double* w) {
+            o.jf = f - lo; o.jt = t - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
+            HostState::se2_edge_record(m, w, 1.0, o.meas, o.D);
+            HostState::inv_sym3_host(o.D, o.V);
+        };
+        for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; fill(loops[i], e.from, e.to, e.meas.data(), e.info.data()); }
+        fill(loops[K - 1], from, to, meas, info);
+        CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        loops3v.resize(K);
+        auto fill = [&](ClLoop3& o, int f, int t, const double* m, const double* w) {
+            o.jf = f - lo; o.jt = t - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
+            double r[49];
+            if (!HostState::se3_edge_record(m, w, 1.0, r)) return false;
+            for (int q = 0; q < 7; ++q) o.zinv[q] = r[q];
+            for (int q = 0; q < 21; ++q) { o.Om[q] = r[7 + q]; o.V[q] = r[28 + q]; }
+            return true;
+        };
+        bool okf = true;
+        for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; okf = okf && fill(loops3v[i], e.from, e.to, e.meas.data(), e.info.data()); }
+        okf = okf && fill(loops3v[K - 1], from, to, meas, info);
+        if (!okf) return fail(IPC_ERR_ARG, "loop edge with a zero quaternion or a singular information matrix");
+        CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops3v.data(), sizeof(ClLoop3) * K, cudaMemcpyHostToDevice, h->stream));
+    }
     bool ok = false; int cur = 0;
     rc = cl_window_check(h, lo, hi, K, th, ib, &ok, out_info, &cur);
     if (rc != IPC_OK) return rc;
     *accepted = ok ? 1 : 0;
     if (ok) {   // discard + push_back + propagateCurrentGuess (src/consensus.cpp:69-71); a rejection leaves d_pose untouched (restore)
-        cl_store_window<<<16, 256, 0, h->stream>>>(h->d_pose, lo, hi - lo, h->clB[cur].W);
-        cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, hi, h->n, h->d_pose);
+        if (h->dim == 2) {
+            cl_store_window<<<16, 256, 0, h->stream>>>(h->d_pose, lo, hi - lo, h->clB[cur].W);
+            cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, hi, h->n, h->d_pose);
+        } else {
+            cl_copy<<<16, 256, 0, h->stream>>>(h->clB[cur].W, h->d_pose + 7 * (size_t)lo, 7LL * (hi - lo + 1));
+            cl3_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom49, hi, h->n, h->d_pose, h->cl_stage);
+        }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + 3); e.info.assign(info, info + 9);
+        HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + h->mw); e.info.assign(info, info + h->d * h->d);
         h->hs.cns.push_back(std::move(e));
     }
     return IPC_OK;
@@ -685,17 +741,28 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
 
 int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* iterations) {
     if (!h) return fail(IPC_ERR_ARG, "null handle");
-    if (h->dim != 2 || !h->d_pose) return fail(IPC_ERR_UNSUPPORTED, "SE(3) stream not built in this revision");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (!h->d_odom9_raw) {
+    const bool d2 = h->dim == 2;
+    if (d2 && !h->d_odom9_raw) {
         std::vector<double> rec;
         h->hs.build_odom_aos(false, h->n_pad, rec, /*raw=*/true);
         CUDA_TRY(cudaMalloc(&h->d_odom9_raw, rec.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(h->d_odom9_raw, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (!d2 && !h->d_odom49_raw) {
+        std::vector<double> rec;
+        if (!h->hs.build_odom_aos3(h->n_pad, rec, /*raw=*/true)) return fail(IPC_ERR_ARG, "singular odometry information");
+        CUDA_TRY(cudaMalloc(&h->d_odom49_raw, rec.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(h->d_odom49_raw, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
     // propagateGuess(0, N-1): vertex 0 at the origin and fixed, the rest dead-reckoned (src/simulation.cpp:50-53)
-    cl_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
-    cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, 0, h->n, h->d_pose);
+    if (d2) {
+        cl_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
+        cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, 0, h->n, h->d_pose);
+    } else {
+        cl3_set_origin<<<1, 32, 0, h->stream>>>(h->d_pose);
+        cl3_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom49, 0, h->n, h->d_pose, h->cl_stage);
+    }
     CUDA_TRY(cudaGetLastError());
     const int K = (int)h->hs.cns.size();
     if (chi2) *chi2 = 0;
@@ -704,21 +771,35 @@ int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* ite
     const int lo = 0, hi = h->n - 1;
     int rc = cl_ensure(h, hi - lo, K);
     if (rc != IPC_OK) return rc;
-    std::vector<ClLoop> loops(K);
-    for (int i = 0; i < K; ++i) {
-        const HostEdge& e = h->hs.cns[i];
-        ClLoop& o = loops[i];
-        o.jf = e.from - lo; o.jt = e.to - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
-        HostState::se2_edge_record(e.meas.data(), e.info.data(), 1.0, o.meas, o.D);
-        HostState::inv_sym3_host(o.D, o.V);
+    if (d2) {
+        std::vector<ClLoop> loops(K);
+        for (int i = 0; i < K; ++i) {
+            const HostEdge& e = h->hs.cns[i];
+            ClLoop& o = loops[i];
+            o.jf = e.from - lo; o.jt = e.to - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
+            HostState::se2_edge_record(e.meas.data(), e.info.data(), 1.0, o.meas, o.D);
+            HostState::inv_sym3_host(o.D, o.V);
+        }
+        CUDA_TRY(cudaMemcpy(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<ClLoop3> loops(K);
+        for (int i = 0; i < K; ++i) {
+            const HostEdge& e = h->hs.cns[i];
+            ClLoop3& o = loops[i];
+            o.jf = e.from - lo; o.jt = e.to - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
+            double r[49];
+            if (!HostState::se3_edge_record(e.meas.data(), e.info.data(), 1.0, r)) return fail(IPC_ERR_ARG, "bad loop edge");
+            for (int q = 0; q < 7; ++q) o.zinv[q] = r[q];
+            for (int q = 0; q < 21; ++q) { o.Om[q] = r[7 + q]; o.V[q] = r[28 + q]; }
+        }
+        CUDA_TRY(cudaMemcpy(h->cl_loops, loops.data(), sizeof(ClLoop3) * K, cudaMemcpyHostToDevice));
     }
-    CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice, h->stream));
     bool ok = false; int cur = 0; ipc_check_info ci{};
-    h->cl_odom = h->d_odom9_raw;                            // odometry information / s_factor (src/simulation.cpp:55-56)
+    h->cl_odom = d2 ? h->d_odom9_raw : h->d_odom49_raw;        // odometry information / s_factor (src/simulation.cpp:55-56)
     rc = cl_window_check(h, lo, hi, K, 0.0, max_iterations, &ok, &ci, &cur, /*exact_iters=*/true);
     h->cl_odom = nullptr;
     if (rc != IPC_OK) return rc;
-    cl_store_window<<<16, 256, 0, h->stream>>>(h->d_pose, lo, hi - lo, h->clB[cur].W);
+    cl_copy<<<16, 256, 0, h->stream>>>(h->clB[cur].W, h->d_pose, (long long)(d2 ? 5 : 7) * (hi - lo + 1));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (chi2) *chi2 = ci.sum_chi2;
@@ -728,12 +809,12 @@ int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* ite
 
 int ipc_get_poses(ipc_handle* h, double* out) {
     if (!h || !out) return fail(IPC_ERR_ARG, "null argument");
-    if (h->dim != 2 || !h->d_pose) return fail(IPC_ERR_UNSUPPORTED, "SE(3) stream not built in this revision");
     CUDA_TRY(cudaSetDevice(h->device));
     double* d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * 3 * (size_t)h->n));
-    cl_export_poses<<<64, 256, 0, h->stream>>>(h->d_pose, h->n, d_out);
-    cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * 3 * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * h->mw * (size_t)h->n));
+    if (h->dim == 2) cl_export_poses<<<64, 256, 0, h->stream>>>(h->d_pose, h->n, d_out);
+    else cl3_export_poses<<<64, 256, 0, h->stream>>>(h->d_pose, h->n, d_out);
+    cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * h->mw * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     cudaFree(d_out);
     if (e != cudaSuccess) return fail(IPC_ERR_CUDA, cudaGetErrorString(e));

@@ -186,17 +186,18 @@ def test_sequential_stream_matches_oracle_live(gpu_lib, oracle_lib):
     ipc.close()
 
 
-def test_cli_end_to_end_matches_oracle_stream(gpu_lib, oracle_lib, tmp_path):
-    """ipc_tester_2D -c cfg.yaml on a synthetic g2o file: precision / recall of the .PR file equal the oracle stream's, the
-    trajectory file has one pose per vertex, and the final optimisation lowers chi2 (src/simulation.cpp:50-105)."""
+@pytest.mark.parametrize("name,scale,tester,width", [("intel", 0.3, "ipc_tester_2D", 3), ("sphere", 0.05, "ipc_tester_3D", 7)])
+def test_cli_end_to_end_matches_oracle_stream(gpu_lib, oracle_lib, tmp_path, name, scale, tester, width):
+    """ipc_tester_2D / _3D -c cfg.yaml on a synthetic g2o file: precision / recall of the .PR file equal the oracle stream's, the
+    trajectory file has one pose per vertex, and the final optimisation runs (src/simulation.cpp:50-105)."""
     import subprocess
     from ipc_b200 import g2o
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call(["make", "-s", "-C", os.path.join(root, "cli")])
-    g, cfg = synth.make_config("intel", scale=0.3)
+    g, cfg = synth.make_config(name, scale=scale)
     ds, gt, out, yml = (str(tmp_path / f) for f in ("graph.g2o", "gt.txt", "res.txt", "cfg.yaml"))
-    g2o.write_g2o(g, ds); g2o.write_trajectory(g.gt, gt); g2o.write_config(yml, "intel", ds, gt, out, g.n_true, cfg)
-    r = subprocess.run([os.path.join(root, "cli", "ipc_tester_2D"), "-c", yml, "--quiet"], capture_output=True, text=True)
+    g2o.write_g2o(g, ds); g2o.write_trajectory(g.gt, gt); g2o.write_config(yml, name, ds, gt, out, g.n_true, cfg)
+    r = subprocess.run([os.path.join(root, "cli", tester), "-c", yml, "--quiet"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr + r.stdout
     oacc, _ = oracle_lib.OracleIPC(g, cfg, noise_exit=True).run_stream()
     truth = g.time_order() < g.n_true
@@ -204,7 +205,7 @@ def test_cli_end_to_end_matches_oracle_stream(gpu_lib, oracle_lib, tmp_path):
     pr = open(out[:-3] + "PR").read().split()
     assert float(pr[0]) == pytest.approx(tp / max(1, tp + fp), rel=1e-5) and float(pr[1]) == pytest.approx(tp / max(1, tp + fn), rel=1e-5)
     traj = np.loadtxt(out)
-    assert traj.shape == (g.n_poses, 3) and np.isfinite(traj).all()
+    assert traj.shape == (g.n_poses, width) and np.isfinite(traj).all()
     assert f"TP {tp} FP {fp}" in r.stdout
 
 
@@ -258,3 +259,19 @@ def test_launch_variants_and_global_state_mode(gpu_lib):
         ipc = gpu_lib.IPC.from_graph(g, cfg)
         ipc.set_option("bucket0_nt", 96)          # not an instantiated variant: fails loudly at launch
         ipc.check_batch(z["member"], z["cand"])
+
+
+def test_sequential_stream_se3_matches_golden(gpu_lib):
+    """IPC<EdgeSE3, VertexSE3>::agreementCheck stream on the sphere-shaped graph: inlier set, chi2, consensus set and final
+    poses against the oracle fixture; then the final full-graph optimisation lowers chi2."""
+    z, g, cfg = load("stream_se3_sphere.npz")
+    ipc = gpu_lib.IPC.from_graph(g, cfg, candidates=False)
+    acc, mx, cc, K = _run_stream(ipc, g, z["order"])
+    assert np.array_equal(acc, z["accept"])
+    assert np.array_equal(K, z["n_cluster"] + 1)
+    assert rel_err(mx, z["max_chi2"]).max() < CHI2_RTOL
+    assert np.array_equal(ipc.getMaxConsensusSet(), z["consensus"])
+    assert np.allclose(ipc.poses(), z["poses"], atol=1e-6)
+    chi2, iters = ipc.final_optimize(1000)
+    assert np.isfinite(chi2) and iters >= 1
+    ipc.close()
