@@ -448,11 +448,25 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
     // the odometry record of the next edge is fetched one iteration ahead (L2 latency); state comes from shared memory
     OdomRec<UNI> rn;
-    if (k0 < k1) odom_load<UNI>(O, k0, rn);
+    double gn6[6] = {0, 0, 0, 0, 0, 0};      // blend steps: (b, h_gn) of the next vertex, from the global scratch
+    if (k0 < k1) {
+        odom_load<UNI>(O, k0, rn);
+        if (mode == STEP_BLEND) { const double* gq = M.G(k0 + 1);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
+    }
     for (int k = k0; k < k1; ++k) {
         const int j = k + 1;
         const OdomRec<UNI> r = rn;
-        if (j < k1) odom_load<UNI>(O, k + 1, rn);
+        double g6[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) g6[q] = gn6[q];
+        if (j < k1) {
+            odom_load<UNI>(O, k + 1, rn);
+            if (mode == STEP_BLEND) { const double* gq = M.G(j + 1);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
+        }
         const double* pq0 = M.P(j);
         const P2 ob{pq0[0], pq0[1], pq0[2]};
         const double ocb = pq0[3], osb = pq0[4];
@@ -485,7 +499,6 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
                 for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
                 gn_step_at(sp, j, pre, ob.x, ob.y, h);
             } else {
-                const double* g6 = M.G(j);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) h[q] = c1 * g6[q] + c2 * g6[3 + q];
             }
@@ -848,11 +861,14 @@ template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const Od
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
     P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
+    OdomRec<UNI> rn;
+    if (ts.k0 < ts.k1) odom_load<UNI>(O, ts.k0, rn);
     for (int k = ts.k0; k < ts.k1; ++k) {
         const int j = k + 1;
         const double* pq = M.P(j);
         const P2 pb{pq[0], pq[1], pq[2]};
-        OdomRec<UNI> r; odom_load<UNI>(O, k, r);
+        const OdomRec<UNI> r = rn;
+        if (j < ts.k1) odom_load<UNI>(O, k + 1, rn);
         Lin2 e; double t[NPRE], h[3];
         odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
 #pragma unroll
@@ -910,10 +926,12 @@ template <int NT, bool UNI> IPC_HD void sd_sweeps(const ChainMem& M, const OdomV
     if (k0 < k1) {
         P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
         double gprev[3] = {0, 0, 0};   // gj of the edge that ends at the current vertex
+        OdomRec<UNI> rn; odom_load<UNI>(O, k0, rn);
         for (int k = k0; k <= k1 && k < L; ++k) {      // one extra edge (k1) for the gradient at the last owned vertex
             P2 pb{M.P(k + 1)[0], M.P(k + 1)[1], M.P(k + 1)[2]};
             Lin2 e; double t[NPRE];
-            OdomRec<UNI> r; odom_load<UNI>(O, k, r);
+            const OdomRec<UNI> r = rn;
+            if (k + 1 <= k1 && k + 1 < L) odom_load<UNI>(O, k + 1, rn);
             odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
             double gi[3], gj[3]; grad2(e, gi, gj);
             if (k > k0) {   // vertex j = k is complete: gj(edge j-1) + gi(edge j)
@@ -939,14 +957,17 @@ template <int NT, bool UNI> IPC_HD void sd_sweeps(const ChainMem& M, const OdomV
     if (k0 < k1) {
         P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
         double ba[3] = {M.G(k0)[0], M.G(k0)[1], M.G(k0)[2]};
+        OdomRec<UNI> rn; odom_load<UNI>(O, k0, rn);
+        double bn[3] = {M.G(k0 + 1)[0], M.G(k0 + 1)[1], M.G(k0 + 1)[2]};
         for (int k = k0; k < k1; ++k) {
             P2 pb{M.P(k + 1)[0], M.P(k + 1)[1], M.P(k + 1)[2]};
-            OdomRec<UNI> r; odom_load<UNI>(O, k, r);
+            const OdomRec<UNI> r = rn;
+            const double bv[3] = {bn[0], bn[1], bn[2]};
+            if (k + 1 < k1) { odom_load<UNI>(O, k + 1, rn); const double* gq = M.G(k + 2); bn[0] = gq[0]; bn[1] = gq[1]; bn[2] = gq[2]; }
             double D[6];
 #pragma unroll
             for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : r.z[UNI ? 0 : 3 + c];
             Lin2 e; lin2cs(ca, sa, pa, pb, r.z[0], r.z[1], r.z[2], D, e);
-            double bv[3] = {M.G(k + 1)[0], M.G(k + 1)[1], M.G(k + 1)[2]};
             double q0, q1, q2; dlin2(e, ba, bv, q0, q1, q2);
             w[0] += quad3(D, q0, q1, q2);
             ba[0] = bv[0]; ba[1] = bv[1]; ba[2] = bv[2];
