@@ -83,3 +83,20 @@ def matrix_from_verdicts(graph, member, cand, verdict, order=None):
     M[pos[cand[p]], pos[member[p]]] = verdict[p]
     M[np.arange(n), np.arange(n)] = diag
     return M
+
+
+def consistency_matrix_sharded(ipc, graph, world: int = 1, rank: int = 0, dist=None, device=None):
+    """Pairwise consistency matrix with the solved checks dealt across `world` ranks (one process per GPU, each holding the
+    whole graph and its own `ipc` handle): local ipc.check_batch on this rank's shard, ONE all_gather of the packed verdict
+    words, then every rank assembles the same dense boolean matrix (time order). Returns (matrix, order)."""
+    from . import api
+    order = graph.time_order()
+    member, cand = api.pair_checks(graph, order)
+    cost = window_lengths(graph, member, cand)
+
+    def local(idx):
+        acc, _ = ipc.check_batch(member[idx], cand[idx], want_info=False)
+        return acc
+
+    verdict = sharded_verdicts(cost, local, world, rank, dist=dist, device=device)
+    return matrix_from_verdicts(graph, member, cand, verdict, order), order

@@ -275,3 +275,16 @@ def test_sequential_stream_se3_matches_golden(gpu_lib):
     chi2, iters = ipc.final_optimize(1000)
     assert np.isfinite(chi2) and iters >= 1
     ipc.close()
+
+
+def test_sharded_matrix_equals_device_matrix(gpu_lib):
+    """The multi-GPU assembly path (ipc_b200/sharding.py; world = 1 here, world = 2 over gloo in the CPU suite) gives the same
+    matrix as ipc_consistency_matrix."""
+    from ipc_b200 import sharding
+    g, cfg = synth.make_config("intel", scale=0.25)
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    rows, order, _ = ipc.consistency_matrix()
+    M, order2 = sharding.consistency_matrix_sharded(ipc, g)
+    assert np.array_equal(order, order2)
+    assert np.array_equal(_unpack(rows, g.n_loops), M)
+    ipc.close()
