@@ -29,7 +29,7 @@ namespace ipcb {
 
 #ifdef __CUDACC__
 #define IPC_HD __host__ __device__ __forceinline__
-#define IPC_HD_COLD __host__ __device__ __noinline__      // cold / once-per-sweep code: keep its registers out of the hot loop
+#define IPC_HD_COLD inline __host__ __device__ __noinline__      // cold / once-per-sweep code: keep its registers out of the hot loop
 #else
 #define IPC_HD inline
 #define IPC_HD_COLD inline
@@ -39,7 +39,7 @@ namespace ipcb {
 // fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp each). The CUDA library sincos carries a Payne-Hanek slow path
 // (local-memory table) that this kernel never needs. Coefficients sit in constant memory so the FMAs read them as operands.
 #ifdef __CUDACC__
-__constant__ double kSinCos[12] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+static __constant__ double kSinCos[12] = {1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
                                    -1.98412698298579493134e-04, 8.33333333332248946124e-03,  -1.66666666666666324348e-01,
                                    -1.13596475577881948265e-11, 2.08757232129817482790e-09,  -2.75573143513906633035e-07,
                                    2.48015872894767294178e-05,  -1.38888888888741095749e-03, 4.16666666666666019037e-02};

@@ -8,8 +8,7 @@
 #include <string>
 #include <vector>
 
-#include "chain_se2_kernel.cuh"
-#include "chain_se3_kernel.cuh"
+#include "launch_common.hpp"
 #include "host_state.hpp"
 #include "matrix.cuh"
 #include "cluster_se2.cuh"
@@ -23,11 +22,6 @@ thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 }  // namespace ipcb
 
-#define CUDA_TRY(x)                                                                                                   \
-    do {                                                                                                              \
-        cudaError_t _e = (x);                                                                                         \
-        if (_e != cudaSuccess) return fail(IPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e));            \
-    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // planning kernels: bucket checks by window length (K3: interval overlap) and pack verdict bits
@@ -75,8 +69,6 @@ __global__ void pack_bits(const unsigned char* __restrict__ verdict, int n, uint
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int NB = 6;   // launch buckets
-struct Bucket { int cap; int nt; int mode; int minb; };   // minb: CTAs per SM the variant is compiled for (register budget)
 // window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh). Every kernel is compiled for
 // 512 resident threads per SM (<= 128 registers): 16 x 32, 8 x 64, 4 x 128, 2 x 256 or 1 x 512 CTAs, so the serial part of
 // one check (capacitance solve by thread 0) overlaps with the sweeps of the CTAs sharing its SM. MODE 0 keeps 5 doubles per
@@ -88,51 +80,6 @@ const Bucket kBuckets3[NB] = {{96, 32, 0, 8}, {320, 64, 0, 4}, {800, 128, 0, 2},
 const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
 int threads_per_sm(int dim) { return dim == 2 ? 512 : 256; }
 
-size_t smem_bytes(int mode, int cap, int dim = 2, int nt = 0) {
-    size_t capv = std::max(cap + 2, nt);
-    size_t n = dim == 2 ? CHAIN_SMALL_DOUBLES + (mode == 0 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0)
-                        : se3::CHAIN3_SMALL_DOUBLES + (mode == 0 ? (size_t)se3::CHAIN3_STATE * capv : 0);
-    return n * sizeof(double);
-}
-size_t scratch_doubles_per_cta(int mode, int cap, int dim = 2, int nt = 0) {
-    size_t capv = std::max(cap + 2, nt);
-    return dim == 2 ? (size_t)(CHAIN_SCRATCH_ARRAYS + (mode == 1 ? CHAIN_STATE_ARRAYS : 0)) * capv
-                    : (size_t)(se3::CHAIN3_SCRATCH + (mode == 1 ? se3::CHAIN3_STATE : 0)) * capv;
-}
-template <int NT, int MODE> int launch_se3(const BatchArgs& a, int grid, cudaStream_t st) {
-    size_t sm = smem_bytes(MODE, a.Lcap, 3, NT);
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(chain_check_se3<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_done = true;
-    }
-    chain_check_se3<NT, MODE><<<grid, NT, sm, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return IPC_OK;
-}
-
-template <int NT, int MODE, bool UNI, int MINB> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
-    size_t sm = smem_bytes(MODE, a.Lcap);
-    static bool attr_done = false;
-    if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_done = true;
-    }
-    chain_check_se2<NT, MODE, UNI, MINB><<<grid, NT, sm, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
-    return IPC_OK;
-}
-template <int NT, int MODE, int MINB> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
-    return uni ? launch_se2u<NT, MODE, true, MINB>(a, grid, st) : launch_se2u<NT, MODE, false, MINB>(a, grid, st);
-}
-// the instantiated (threads, CTAs per SM) variants
-int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
-    if (mode == 1) return launch_se2<512, 1, 1>(a, grid, st, uni);
-#define V(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2<NT_, 0, MB_>(a, grid, st, uni);
-    V(32, 16) V(32, 8) V(64, 8) V(64, 4) V(64, 2) V(128, 4) V(128, 3) V(128, 2) V(128, 1) V(192, 2) V(256, 2) V(256, 1) V(384, 1) V(512, 1)
-#undef V
-    return fail(IPC_ERR_ARG, "no kernel variant for " + std::to_string(nt) + " threads x " + std::to_string(minb) + " CTAs per SM");
-}
 
 }  // namespace
 
@@ -265,11 +212,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         grid = (int)std::min<size_t>(grid, h->scratch_doubles / a.scratch_stride);
         int rc = IPC_OK;
         if (h->dim == 3) {
-            if (bk.mode == 1) rc = launch_se3<256, 1>(a, grid, st);
-            else if (bk.nt == 32) rc = launch_se3<32, 0>(a, grid, st);
-            else if (bk.nt == 64) rc = launch_se3<64, 0>(a, grid, st);
-            else if (bk.nt == 128) rc = launch_se3<128, 0>(a, grid, st);
-            else rc = launch_se3<256, 0>(a, grid, st);
+            rc = launch_se3_variant(bk.nt, bk.mode, a, grid, st);
         } else rc = launch_se2_variant(bk.nt, bk.minb, bk.mode, a, grid, st, uni);
         if (rc != IPC_OK) return rc;
         ++launches;

@@ -1,0 +1,30 @@
+// launch_se2.cu — instantiations of the SE(2) chain-check kernel (own translation unit: built in parallel with the rest)
+#include "launch_common.hpp"
+#include "chain_se2_kernel.cuh"
+
+namespace ipcb {
+
+template <int NT, int MODE, bool UNI, int MINB> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
+    size_t sm = smem_bytes(MODE, a.Lcap);
+    static bool attr_done = false;
+    if (!attr_done) {
+        CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        attr_done = true;
+    }
+    chain_check_se2<NT, MODE, UNI, MINB><<<grid, NT, sm, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return IPC_OK;
+}
+template <int NT, int MODE, int MINB> int launch_se2(const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
+    return uni ? launch_se2u<NT, MODE, true, MINB>(a, grid, st) : launch_se2u<NT, MODE, false, MINB>(a, grid, st);
+}
+// the instantiated (threads, CTAs per SM) variants
+int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
+    if (mode == 1) return launch_se2<512, 1, 1>(a, grid, st, uni);
+#define V(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2<NT_, 0, MB_>(a, grid, st, uni);
+    V(32, 16) V(32, 8) V(64, 8) V(64, 4) V(64, 2) V(128, 4) V(128, 3) V(128, 2) V(128, 1) V(192, 2) V(256, 2) V(256, 1) V(384, 1) V(512, 1)
+#undef V
+    return fail(IPC_ERR_ARG, "no kernel variant for " + std::to_string(nt) + " threads x " + std::to_string(minb) + " CTAs per SM");
+}
+
+}  // namespace ipcb
