@@ -10,8 +10,8 @@
  *
  * Flat formats
  *   SE(2): measurement / pose = (x, y, theta), information = 3x3 row-major full symmetric.
- *   SE(3): measurement / pose = (x, y, z, qx, qy, qz, qw) (g2o EDGE_SE3:QUAT order), information =
- *          6x6 row-major full symmetric (translation block first, then the quaternion-vector block).
+ *   SE(3): measurement / pose = (x, y, z, qx, qy, qz, qw) (g2o EDGE_SE3:QUAT order, quaternion normalised on input),
+ *          information = 6x6 row-major full symmetric (translation block first, then the quaternion-vector block).
  *   Vertex ids must be 0..n_poses-1 and odometry edge j must connect j -> j+1
  *   (the reference assumes both: src/consensus_utils.cpp:32-40, src/consensus.cpp:55).
  */
@@ -124,8 +124,10 @@ int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, i
  * matrix's order) joins iff it is consistent with every current member. in_set: n_loops bytes. */
 int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsigned char* in_set);
 
-/* Knobs (non-reference): noise_exit = 1 stops the Dogleg retry loop once a rejected step's predicted
- * gain is below round-off of chi2 (DESIGN.md "Termination"); 0 replays all 100 retries like g2o. */
+/* Knobs (non-reference). noise_exit: 1 (default) stops the Dogleg retry loop once a rejected trial's own predicted gain is
+ * below 1e-13 * chi2 (DESIGN.md "Termination"), 0 replays all 100 retries like g2o, any other value is used as the threshold.
+ * early_accept: 1 lets verdict-only batches stop as soon as sum chi2 <= threshold (same bits). speculate, use_uniform,
+ * max_tries, bucket<i>_cap / bucket<i>_nt / bucket<i>_minb (launch shapes, i = 0..4): tuning, see DESIGN.md. */
 int ipc_set_option(ipc_handle* h, const char* name, double value);
 
 #ifdef __cplusplus

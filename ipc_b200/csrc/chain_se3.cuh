@@ -369,37 +369,32 @@ IPC_HD void gn_step_at3(const StepSpec3* sp, int j, const double* pre, const P3&
 
 struct SweepOut3 { double chi, mx, hh, gain; };
 
+// Two loops per sweep: loop A applies the step (old linearisation -> running prefix -> u -> new pose, backup), loop B
+// re-linearises at the new poses read back from shared memory. With 27 prefix values and a 46-double linearisation per
+// edge, keeping both running prefixes alive in one loop spills hundreds of bytes per thread even at 255 registers.
 template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int mode, double c1, double c2, bool acc_gain, ThreadState3& ts, SweepOut3& out,
                                      int& buf, const int* spec_v) {
     const int k0 = ts.k0, k1 = ts.k1;
     const StepSpec3* sp = &M.U()->sol;
     double* spec = M.spec() + (size_t)buf * NSPEC * SPECW3;
-    double pre[NP3];
+    double hh = 0, gain = 0;
+    if (mode != STEP_NONE) {
+        double pre[NP3];
 #pragma unroll
-    for (int m = 0; m < NP3; ++m) pre[m] = ts.base[m];
-    P3 oa = ts.pa, na = ts.pa;
-    if (mode != STEP_NONE && k0 > 0 && k0 < k1) {
-        double u[6];
-        if (mode == STEP_GN) gn_step_at3(sp, k0, pre, oa, u);
-        else { const double* gq = M.G(k0);
+        for (int m = 0; m < NP3; ++m) pre[m] = ts.base[m];
+        P3 oa = ts.pa;
+        if (k0 > 0 && k0 < k1) {     // boundary vertex k0: same arithmetic as its owner => identical bits
+            double u[6];
+            if (mode == STEP_GN) gn_step_at3(sp, k0, pre, oa, u);
+            else { const double* gq = M.G(k0);
 #pragma unroll
-            for (int q = 0; q < 6; ++q) u[q] = c1 * gq[q] + c2 * gq[6 + q]; }
-        oplus3(oa, u, na);
-    }
-    ts.pa = na;
-    double run[NP3];
-#pragma unroll
-    for (int m = 0; m < NP3; ++m) run[m] = 0;
-    double chi = 0, mx = 0, hh = 0, gain = 0;
-    bool has_spec = false;
-#pragma unroll
-    for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
-    for (int k = k0; k < k1; ++k) {
-        const int j = k + 1;
-        const double* rec = odom + (size_t)ODOM_REC3 * k;
-        P3 ob; load_pose(M.P(j), ob);
-        P3 nb = ob;
-        if (mode != STEP_NONE) {
+                for (int q = 0; q < 6; ++q) u[q] = c1 * gq[q] + c2 * gq[6 + q]; }
+            oplus3(oa, u, ts.pa);
+        }
+        for (int k = k0; k < k1; ++k) {
+            const int j = k + 1;
+            const double* rec = odom + (size_t)ODOM_REC3 * k;
+            P3 ob; load_pose(M.P(j), ob);
             double u[6];
             if (mode == STEP_GN) {
                 Lin3 eo; lin3(rec, oa, ob, rec + 7, eo);
@@ -413,25 +408,41 @@ template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int
 #pragma unroll
                 for (int q = 0; q < 6; ++q) u[q] = c1 * gq[q] + c2 * gq[6 + q]; }
             store_pose(M.B(j), ob);
-            oplus3(ob, u, nb);
+            P3 nb; oplus3(ob, u, nb);
 #pragma unroll
             for (int q = 0; q < 6; ++q) hh += u[q] * u[q];
             store_pose(M.P(j), nb);
+            oa = ob;
         }
-        Lin3 e; lin3(rec, na, nb, rec + 7, e);
-        double t[NP3]; edge_terms3(e, rec + 7 + NS6, t);
-        chi += e.chi; mx = fmax(mx, e.chi);
+    }
+    double run[NP3];
 #pragma unroll
-        for (int m = 0; m < NP3; ++m) run[m] += t[m];
-        if (has_spec) {
+    for (int m = 0; m < NP3; ++m) run[m] = 0;
+    double chi = 0, mx = 0;
+    bool has_spec = false;
 #pragma unroll
-            for (int q = 1; q < NSPEC; ++q)
-                if (j == spec_v[q]) { double* o = spec + q * SPECW3;
+    for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
+    {
+        P3 na = ts.pa;
+        for (int k = k0; k < k1; ++k) {
+            const int j = k + 1;
+            const double* rec = odom + (size_t)ODOM_REC3 * k;
+            P3 nb; load_pose(M.P(j), nb);
+            Lin3 e; lin3(rec, na, nb, rec + 7, e);
+            double t[NP3]; edge_terms3(e, rec + 7 + NS6, t);
+            chi += e.chi; mx = fmax(mx, e.chi);
 #pragma unroll
-                    for (int m = 0; m < NP3; ++m) o[m] = run[m];
-                    store_pose(o + NP3, nb); }
+            for (int m = 0; m < NP3; ++m) run[m] += t[m];
+            if (has_spec) {
+#pragma unroll
+                for (int q = 1; q < NSPEC; ++q)
+                    if (j == spec_v[q]) { double* o = spec + q * SPECW3;
+#pragma unroll
+                        for (int m = 0; m < NP3; ++m) o[m] = run[m];
+                        store_pose(o + NP3, nb); }
+            }
+            na = nb;
         }
-        oa = ob; na = nb;
     }
     double s[3] = {chi, hh, gain};
     ScanSumMax3<NT, 3>::run(run, s, mx, M.red() + (size_t)buf * RED3_DOUBLES);
