@@ -73,7 +73,7 @@ namespace {
 // 512 resident threads per SM (<= 128 registers): 16 x 32, 8 x 64, 4 x 128, 2 x 256 or 1 x 512 CTAs, so the serial part of
 // one check (capacitance solve by thread 0) overlaps with the sweeps of the CTAs sharing its SM. MODE 0 keeps 5 doubles per
 // vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
-const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3}, {2600, 128, 0, 2}, {5400, 256, 0, 1}, {1 << 30, 512, 1, 1}};
+const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3}, {2600, 128, 0, 2}, {5400, 256, 0, 1}, {1 << 30, 256, 1, 1}};
 
 // SE(3): 7 doubles of state per vertex, 256 resident threads per SM (the 27 running prefix values need the registers)
 const Bucket kBuckets3[NB] = {{96, 32, 0, 8}, {320, 64, 0, 4}, {800, 128, 0, 2}, {3700, 256, 0, 1}, {3701, 256, 0, 1}, {1 << 30, 256, 1, 1}};
@@ -332,7 +332,7 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
     if (!h || !name) return fail(IPC_ERR_ARG, "null argument");
     if (!strcmp(name, "noise_exit")) { h->noise_eps = value == 1.0 ? 1e-13 : value; return IPC_OK; }   // 0 = off, 1 = default eps, else eps
     if (!strcmp(name, "acc_gain_ratio")) { h->acc_gain_ratio = value; return IPC_OK; }
-    if (!strncmp(name, "bucket", 6) && name[6] >= '0' && name[6] < '0' + NB - 1 && name[7] == '_') {
+    if (!strncmp(name, "bucket", 6) && name[6] >= '0' && name[6] < '0' + NB && name[7] == '_') {
         const int b = name[6] - '0';
         if (!strcmp(name + 8, "cap")) h->buckets[b].cap = (int)value;
         else if (!strcmp(name + 8, "nt")) h->buckets[b].nt = (int)value;        // (nt, minb) must name an instantiated variant: checked at launch

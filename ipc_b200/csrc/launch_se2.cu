@@ -20,7 +20,7 @@ template <int NT, int MODE, int MINB> int launch_se2(const BatchArgs& a, int gri
 }
 // the instantiated (threads, CTAs per SM) variants
 int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
-    if (mode == 1) return launch_se2<512, 1, 1>(a, grid, st, uni);
+    if (mode == 1) return nt == 256 ? launch_se2<256, 1, 1>(a, grid, st, uni) : launch_se2<512, 1, 1>(a, grid, st, uni);
 #define V(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2<NT_, 0, MB_>(a, grid, st, uni);
     V(32, 16) V(32, 8) V(64, 8) V(64, 4) V(64, 2) V(128, 4) V(128, 3) V(128, 2) V(128, 1) V(192, 2) V(256, 2) V(256, 1) V(384, 1) V(512, 1)
 #undef V
