@@ -77,6 +77,25 @@ IPC_HD double wrap_pi_hd(double t) {
     return fma(-k, 6.28318530717958647692, t);
 }
 
+// Optional phase clocks (-DIPC_PHASE_CLOCKS, profiling builds only): thread 0 of every CTA adds the cycles since its previous
+// mark to a global counter per phase. The default build compiles every mark to nothing.
+#ifdef IPC_PHASE_CLOCKS
+static __device__ unsigned long long g_phase[16];
+#define IPC_PH_ARG , long long& ph_last
+#define IPC_PH_PASS , ph_last
+#ifdef __CUDA_ARCH__
+#define IPC_PH(i) do { long long now_ = clock64(); if (threadIdx.x == 0) atomicAdd(&g_phase[i], (unsigned long long)(now_ - ph_last)); ph_last = now_; } while (0)
+#define IPC_PH_COUNT(i, n) do { if (threadIdx.x == 0) atomicAdd(&g_phase[i], (unsigned long long)(n)); } while (0)
+#else
+#define IPC_PH(i) do { (void)ph_last; } while (0)
+#define IPC_PH_COUNT(i, n) do {} while (0)
+#endif
+#else
+#define IPC_PH_ARG
+#define IPC_PH_PASS
+#define IPC_PH(i) do {} while (0)
+#define IPC_PH_COUNT(i, n) do {} while (0)
+#endif
 struct P2 { double x, y, t; };
 struct Lin2 {            // linearisation of one relative-pose edge a -> b in its own frame
     double c, s;         // cos / sin of theta_a
@@ -312,16 +331,22 @@ constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
 constexpr int RED_DOUBLES_ = 16 * (NPRE + 4);
 struct ChainMem {            // three base pointers + a capacity: cheap to keep in registers and to pass by value
     double* st;              // per-vertex state, AoS of 5 doubles: x, y, theta, cos, sin. Shared memory (MODE 0) or global scratch (MODE 1)
-    double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capv, then (b, h_gn) AoS[6] x capv
+    double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capg, then (b, h_gn) AoS[6] x capg, indexed
+                             // by SLOT (vslot below), not by vertex: the threads of a warp walk their segments in lock step, so
+                             // slot = step * NT + thread makes every scratch access of a warp one contiguous run of records
     double* small;           // shared memory: collective staging (2 buffers), special-vertex table (2 buffers), UniBlock
-    int capv;
+    int capv, capg;          // capacity of the state arrays (vertices) and of the scratch arrays (slots)
     IPC_HD double* P(int j) const { return st + 5 * j; }                          // x y theta cos sin of vertex j
-    IPC_HD double* B(int j) const { return scr + 3 * j; }                         // pose backup: state before the last trial sweep
-    IPC_HD double* G(int j) const { return scr + 3 * (size_t)capv + 6 * j; }      // gradient b_j (3) and h_gn,j (3), g2o vertex coordinates
+    IPC_HD double* B(int sl) const { return scr + 3 * sl; }                       // pose backup: state before the last trial sweep
+    IPC_HD double* G(int sl) const { return scr + 3 * (size_t)capg + 6 * sl; }    // gradient b_j (3) and h_gn,j (3), g2o vertex coordinates
     IPC_HD double* red() const { return small; }
     IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_; }
     IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + 2 * NSPEC * SPECW); }
 };
+// scratch slot of vertex j for segments of S vertices per thread: vertex 0 -> 0; vertex k0 + 1 + i of thread t -> i * NT + t + 1.
+// Slots reach S * NT <= L + 2 NT, hence capg = capv + 2 NT + 2.
+template <int NT> IPC_HD int vslot(int j, int S) { return j == 0 ? 0 : ((j - 1) % S) * NT + (j - 1) / S + 1; }
+template <int NT> IPC_HD constexpr int scratch_slots(int capv) { return capv + 2 * NT + 2; }
 constexpr int RED_DOUBLES = 16 * (NPRE + 4);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 3
 constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
 constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
@@ -344,6 +369,7 @@ IPC_HD double ldg_d(const double* p) {
 
 struct ThreadState {         // registers carried from sweep to sweep
     int k0, k1;              // owned edges [k0, k1); owned vertices k0+1 .. k1
+    int S, tid;              // segment length (vertices per thread) and the thread's index: scratch slots (vslot)
     P2 pa; double ca, sa;    // pose (+ cos / sin) of vertex k0 at the current state
     double base[NPRE];       // prefix (PM, Pm) at vertex k0 for the linearisation of the current state
 };
@@ -418,7 +444,7 @@ struct SweepOut { double chi, mx, hh, gain; };   // odometry chi2 sum / max at t
 // j: it is rebuilt on the fly from the old poses (no sincos: cos / sin are stored). Writes the pose backup when a step is
 // applied. Two block barriers.
 template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
-                                              SweepOut& out, int& buf, const int* spec_v) {
+                                              SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
     const int k0 = ts.k0, k1 = ts.k1;
     const StepSpec* sp = &M.U()->sol;
     double* spec = M.spec() + (size_t)buf * NSPEC * SPECW;
@@ -431,7 +457,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
         double h[3];
         if (mode == STEP_GN) gn_step_at(sp, k0, pre, oa.x, oa.y, h);
         else {
-            const double* gq = M.G(k0);
+            const double* gq = M.G((ts.S - 1) * NT + ts.tid);      // vertex k0 = the last vertex of thread tid - 1
 #pragma unroll
             for (int q = 0; q < 3; ++q) h[q] = c1 * gq[q] + c2 * gq[3 + q];
         }
@@ -449,13 +475,14 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     // the odometry record of the next edge is fetched one iteration ahead (L2 latency); state comes from shared memory
     OdomRec<UNI> rn;
     double gn6[6] = {0, 0, 0, 0, 0, 0};      // blend steps: (b, h_gn) of the next vertex, from the global scratch
+    int sl = ts.tid + 1;                     // scratch slot of vertex k0 + 1; + NT per vertex
     if (k0 < k1) {
         odom_load<UNI>(O, k0, rn);
-        if (mode == STEP_BLEND) { const double* gq = M.G(k0 + 1);
+        if (mode == STEP_BLEND) { const double* gq = M.G(sl);
 #pragma unroll
             for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
     }
-    for (int k = k0; k < k1; ++k) {
+    for (int k = k0; k < k1; ++k, sl += NT) {
         const int j = k + 1;
         const OdomRec<UNI> r = rn;
         double g6[6];
@@ -463,7 +490,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
         for (int q = 0; q < 6; ++q) g6[q] = gn6[q];
         if (j < k1) {
             odom_load<UNI>(O, k + 1, rn);
-            if (mode == STEP_BLEND) { const double* gq = M.G(j + 1);
+            if (mode == STEP_BLEND) { const double* gq = M.G(sl + NT);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
         }
@@ -502,7 +529,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
 #pragma unroll
                 for (int q = 0; q < 3; ++q) h[q] = c1 * g6[q] + c2 * g6[3 + q];
             }
-            double* bq = M.B(j);
+            double* bq = M.B(sl);
             bq[0] = ob.x; bq[1] = ob.y; bq[2] = ob.t;
             nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
             hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
@@ -530,6 +557,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
         na = nb; nca = ncb; nsa = nsb;
     }
     double s[3] = {chi, hh, gain};
+    IPC_PH(1);
     ScanSumMax<NT, 3>::run(run, s, mx, M.red() + (size_t)buf * RED_DOUBLES);
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) ts.base[m] = run[m];
@@ -547,17 +575,20 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     }
     bsync<NT>();
     buf ^= 1;
+    IPC_PH(2);
 }
 
 // undo the last applied sweep: poses from the backup, cos / sin recomputed, boundary registers re-read. Thread bases are NOT
 // restored: every caller re-linearises (GN rejection) or only runs blend sweeps (which do not read them) until a step is kept.
 template <int NT> IPC_HD void rollback(const ChainMem& M, ThreadState& ts) {
-    for (int k = ts.k0; k < ts.k1; ++k) {
+    int sl = ts.tid + 1;
+    for (int k = ts.k0; k < ts.k1; ++k, sl += NT) {
         const int j = k + 1;
-        const double t = M.B(j)[2];
+        const double* bq = M.B(sl);
+        const double t = bq[2];
         double s, c; ipc_sincos(t, &s, &c);
         double* pq = M.P(j);
-        pq[0] = M.B(j)[0]; pq[1] = M.B(j)[1]; pq[2] = t; pq[3] = c; pq[4] = s;
+        pq[0] = bq[0]; pq[1] = bq[1]; pq[2] = t; pq[3] = c; pq[4] = s;
     }
     bsync<NT>();
     if (ts.k0 < ts.k1 && ts.k0 > 0) {
@@ -881,36 +912,42 @@ template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const Od
     return v[0];
 }
 
-// steepest-descent sweeps at the current state (poses + prefixes valid): gradient b and h_gn per vertex into the scratch,
-// bb = |b|^2, bh = b . h_gn, hh = |h_gn|^2, bHb = b^T H b.
-template <int NT, bool UNI> IPC_HD void sd_sweeps(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
-                                                  double& bh, double& hh, double& bHb) {
+// Steepest-descent pass at the current state (poses + prefixes valid): gradient b and h_gn per vertex (g2o vertex coordinates)
+// into the scratch, bb = |b|^2, bh = b . h_gn, hh = |h_gn|^2, bHb = b^T H b = sum over edges |J (b_k, b_k+1)|^2_D — in ONE pass:
+// the edge term of b^T H b lags one edge behind the gradient, so both are finished from a single evaluation of every edge. A thread owns the vertices
+// k0+1..k1 and the Hessian terms of the edges k0+1..k1 (thread 0 also edge 0); the one term that needs the next thread's first
+// gradient is completed after the block barrier from the scratch. Stands in for gn_norm_sq + a separate gradient pass when the
+// iteration is expected to be trust-region bound (gn_norm_sq alone is the cheaper pass when the GN step is expected to fit).
+template <int NT, bool UNI> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
+                                                 double& bh, double& hh, double& bHb) {
     const CheckGeom& g = M.U()->g;
     const int k0 = ts.k0, k1 = ts.k1, L = g.L;
     const StepSpec* sp = &M.U()->sol;
     const LoopRec2& Lc = M.U()->Lc; const LoopRec2& Lm = M.U()->Lm;
-    // loop edges at the current state (poses are stable in M.X: nobody writes them during these sweeps)
     Lin2 ec, em; const int cjf = Lc.from - g.lo, cjt = Lc.to - g.lo; int mjf = -1, mjt = -1;
     {
-        P2 pf{M.P(cjf)[0], M.P(cjf)[1], M.P(cjf)[2]}, pt{M.P(cjt)[0], M.P(cjt)[1], M.P(cjt)[2]};
-        double s, c; ipc_sincos(pf.t, &s, &c);
-        lin2cs(c, s, pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
+        const double* qf = M.P(cjf); const double* qt = M.P(cjt);
+        P2 pf{qf[0], qf[1], qf[2]}, pt{qt[0], qt[1], qt[2]};
+        lin2cs(qf[3], qf[4], pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
     }
     double gci[3], gcj[3], gmi[3] = {0, 0, 0}, gmj[3] = {0, 0, 0};
     grad2(ec, gci, gcj);
     if (g.K == 2) {
         mjf = Lm.from - g.lo; mjt = Lm.to - g.lo;
-        P2 pf{M.P(mjf)[0], M.P(mjf)[1], M.P(mjf)[2]}, pt{M.P(mjt)[0], M.P(mjt)[1], M.P(mjt)[2]};
-        double s, c; ipc_sincos(pf.t, &s, &c);
-        lin2cs(c, s, pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
+        const double* qf = M.P(mjf); const double* qt = M.P(mjt);
+        P2 pf{qf[0], qf[1], qf[2]}, pt{qt[0], qt[1], qt[2]};
+        lin2cs(qf[3], qf[4], pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
         grad2(em, gmi, gmj);
     }
-    double v[3] = {0, 0, 0};
-    double pre[NPRE];        // running prefix of the current linearisation at the vertex being finished
+    double v[4] = {0, 0, 0, 0};
+    double pre[NPRE];
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
-    auto finish_vertex = [&](int j, const double* gsum, double x, double y) {   // b_j = -(odometry terms) - loop terms
-        double b[3] = {-gsum[0], -gsum[1], -gsum[2]};
+    double bprev[3] = {0, 0, 0};        // gradient at the tail vertex of the lagging edge (vertex 0: fixed, zero)
+    double pc = 1, ps = 0, prx = 0, pry = 0, pD[6] = {0, 0, 0, 0, 0, 0};   // Jacobian pieces (and information) of the lagging edge
+    bool tail_pending = false;          // edge k1 (< L) waits for the next thread's first gradient
+    auto finish_vertex = [&](int j, int sl, const double* gsum, double x, double y, double* b) {
+        b[0] = -gsum[0]; b[1] = -gsum[1]; b[2] = -gsum[2];
         if (j == cjf) { b[0] -= gci[0]; b[1] -= gci[1]; b[2] -= gci[2]; }
         if (j == cjt) { b[0] -= gcj[0]; b[1] -= gcj[1]; b[2] -= gcj[2]; }
         if (j == mjf) { b[0] -= gmi[0]; b[1] -= gmi[1]; b[2] -= gmi[2]; }
@@ -918,72 +955,75 @@ template <int NT, bool UNI> IPC_HD void sd_sweeps(const ChainMem& M, const OdomV
         double h[3];
         gn_step_at(sp, j, pre, x, y, h);
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { M.G(j)[q] = b[q]; M.G(j)[3 + q] = h[q]; }
+        for (int q = 0; q < 3; ++q) { M.G(sl)[q] = b[q]; M.G(sl)[3 + q] = h[q]; }
         v[0] += b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
         v[1] += b[0] * h[0] + b[1] * h[1] + b[2] * h[2];
         v[2] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
     };
+    auto lag_term = [&](const double* ba, const double* bv) {   // |J (ba, bv)|^2_D of the lagging edge
+        const double ux = bv[0] - ba[0], uy = bv[1] - ba[1];
+        const double q0 = pc * ux + ps * uy + pry * ba[2], q1 = -ps * ux + pc * uy - prx * ba[2], q2 = bv[2] - ba[2];
+        v[3] += quad3(UNI ? O.Du : pD, q0, q1, q2);
+    };
     if (k0 < k1) {
         P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
-        double gprev[3] = {0, 0, 0};   // gj of the edge that ends at the current vertex
+        double gprev[3] = {0, 0, 0};
+        int sl = ts.tid + 1;
         OdomRec<UNI> rn; odom_load<UNI>(O, k0, rn);
-        for (int k = k0; k <= k1 && k < L; ++k) {      // one extra edge (k1) for the gradient at the last owned vertex
-            P2 pb{M.P(k + 1)[0], M.P(k + 1)[1], M.P(k + 1)[2]};
+        for (int k = k0; k <= k1 && k < L; ++k) {
+            const double* pq = M.P(k + 1);
+            P2 pb{pq[0], pq[1], pq[2]};
             Lin2 e; double t[NPRE];
             const OdomRec<UNI> r = rn;
             if (k + 1 <= k1 && k + 1 < L) odom_load<UNI>(O, k + 1, rn);
             odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
             double gi[3], gj[3]; grad2(e, gi, gj);
-            if (k > k0) {   // vertex j = k is complete: gj(edge j-1) + gi(edge j)
+            if (k > k0) {
                 const double gs[3] = {gprev[0] + gi[0], gprev[1] + gi[1], gprev[2] + gi[2]};
-                finish_vertex(k, gs, pa.x, pa.y);
+                double b[3];
+                finish_vertex(k, sl, gs, pa.x, pa.y, b);     // vertex k = k0 + 1 + (k - k0 - 1)
+                sl += NT;
+                if (k - 1 > k0 || k0 == 0) lag_term(bprev, b);      // edge k-1: both gradients are this thread's
+                bprev[0] = b[0]; bprev[1] = b[1]; bprev[2] = b[2];
             }
 #pragma unroll
             for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
             gprev[0] = gj[0]; gprev[1] = gj[1]; gprev[2] = gj[2];
-            pa = pb; ipc_sincos(pb.t, &sa, &ca);
+            pc = e.c; ps = e.s; prx = e.rx; pry = e.ry;
+            if (!UNI) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pD[c] = r.z[UNI ? 0 : 3 + c];
+            }
+            pa = pb; ca = pq[3]; sa = pq[4];
         }
-        if (k1 == L) finish_vertex(L, gprev, pa.x, pa.y);   // last vertex of the window: no outgoing odometry edge
+        if (k1 == L) {
+            double b[3];
+            finish_vertex(L, sl, gprev, pa.x, pa.y, b);
+            if (L - 1 > k0 || k0 == 0) lag_term(bprev, b);
+        } else tail_pending = true;
     }
     if (hd_tid() == 0) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q) { M.G(0)[q] = 0; M.G(0)[3 + q] = 0; }   // vertex 0 is fixed
+        for (int q = 0; q < 3; ++q) { M.G(0)[q] = 0; M.G(0)[3 + q] = 0; }
     }
-    hd_block_sum<NT, 3>(v, M.red());
-    bsync<NT>();                        // GB / GH visible to the neighbours
-    bb = v[0]; bh = v[1]; hh = v[2];
-    // b^T H b = sum over edges |J b|^2_D
-    double w[1] = {0};
-    if (k0 < k1) {
-        P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
-        double ba[3] = {M.G(k0)[0], M.G(k0)[1], M.G(k0)[2]};
-        OdomRec<UNI> rn; odom_load<UNI>(O, k0, rn);
-        double bn[3] = {M.G(k0 + 1)[0], M.G(k0 + 1)[1], M.G(k0 + 1)[2]};
-        for (int k = k0; k < k1; ++k) {
-            P2 pb{M.P(k + 1)[0], M.P(k + 1)[1], M.P(k + 1)[2]};
-            const OdomRec<UNI> r = rn;
-            const double bv[3] = {bn[0], bn[1], bn[2]};
-            if (k + 1 < k1) { odom_load<UNI>(O, k + 1, rn); const double* gq = M.G(k + 2); bn[0] = gq[0]; bn[1] = gq[1]; bn[2] = gq[2]; }
-            double D[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) D[c] = UNI ? O.Du[c] : r.z[UNI ? 0 : 3 + c];
-            Lin2 e; lin2cs(ca, sa, pa, pb, r.z[0], r.z[1], r.z[2], D, e);
-            double q0, q1, q2; dlin2(e, ba, bv, q0, q1, q2);
-            w[0] += quad3(D, q0, q1, q2);
-            ba[0] = bv[0]; ba[1] = bv[1]; ba[2] = bv[2];
-            pa = pb; ipc_sincos(pb.t, &sa, &ca);
-        }
+    bsync<NT>();                        // every gradient is in the scratch
+    if (tail_pending) {
+        const double* gq = M.G(ts.tid + 2);         // vertex k1 + 1 = the first vertex of thread tid + 1
+        const double bn[3] = {gq[0], gq[1], gq[2]};
+        lag_term(bprev, bn);
     }
     if (hd_tid() == 0) {
-        double bf[3] = {M.G(cjf)[0], M.G(cjf)[1], M.G(cjf)[2]}, bt[3] = {M.G(cjt)[0], M.G(cjt)[1], M.G(cjt)[2]}, q0, q1, q2;
-        dlin2(ec, bf, bt, q0, q1, q2); w[0] += quad3(Lc.D, q0, q1, q2);
+        const double* gf = M.G(vslot<NT>(cjf, ts.S)); const double* gt = M.G(vslot<NT>(cjt, ts.S));
+        double bf[3] = {gf[0], gf[1], gf[2]}, bt[3] = {gt[0], gt[1], gt[2]}, q0, q1, q2;
+        dlin2(ec, bf, bt, q0, q1, q2); v[3] += quad3(Lc.D, q0, q1, q2);
         if (g.K == 2) {
-            double mf[3] = {M.G(mjf)[0], M.G(mjf)[1], M.G(mjf)[2]}, mt[3] = {M.G(mjt)[0], M.G(mjt)[1], M.G(mjt)[2]};
-            dlin2(em, mf, mt, q0, q1, q2); w[0] += quad3(Lm.D, q0, q1, q2);
+            gf = M.G(vslot<NT>(mjf, ts.S)); gt = M.G(vslot<NT>(mjt, ts.S));
+            double mf[3] = {gf[0], gf[1], gf[2]}, mt[3] = {gt[0], gt[1], gt[2]};
+            dlin2(em, mf, mt, q0, q1, q2); v[3] += quad3(Lm.D, q0, q1, q2);
         }
     }
-    hd_block_sum<NT, 1>(w, M.red());
-    bHb = w[0];
+    hd_block_sum<NT, 4>(v, M.red());
+    bb = v[0]; bh = v[1]; hh = v[2]; bHb = v[3];
 }
 
 struct CheckParams {
@@ -992,13 +1032,17 @@ struct CheckParams {
     double noise_eps;        // > 0: stop retrying once a rejected trial's own predicted gain is <= noise_eps * chi2 (below the
                              // round-off of the chi2 evaluation every later, smaller, retry is a coin flip on noise); 0 = replay all retries
     int max_tries, speculate, early_accept;
+    int sd_fuse;             // when the GN norm is needed before a trial: 0 = norm pass, then the steepest-descent pass if the step
+                             // does not fit; 1 = always the steepest-descent pass (it also delivers the norm); 2 (default) = the
+                             // steepest-descent pass when the previous decision was trust-region bound, else the norm pass
     double acc_gain_ratio;   // the predicted GN gain is accumulated edge by edge (extra pass) once chi2 - model < ratio * chi2 (default 1e-6)
 };
 struct CheckResult {
     int verdict;
     double max_chi2, cand_chi2, sum_chi2;
     int iterations, evals, window_len, n_loops;
-    int n_sweeps;            // diagnostics: sweeps of every kind executed
+    int n_sweeps;            // diagnostics: passes over the chain of every kind (trial / re-linearisation sweeps, norm and gradient passes)
+    int n_norm, n_sd, n_relin, n_blend;   // diagnostics: norm pre-passes, steepest-descent pass pairs, re-linearisation sweeps, blend trials
 };
 
 // One check, executed cooperatively by NT threads (device) or by the calling thread (host, NT = 1).
@@ -1009,6 +1053,9 @@ enum { P_INIT = 0, P_TRIAL_SPEC, P_TRIAL_GN, P_TRIAL_BLEND, P_RELIN_SPECFAIL, P_
 template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
                                                   const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res) {
     const int tid = hd_tid();
+#if defined(IPC_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+    const long long ph_start = clock64();
+#endif
     bsync<NT>();                                            // previous check is done with every array and with the UniBlock
     if (tid == 0) {
         UniBlock* U = M.U();
@@ -1049,6 +1096,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     ThreadState ts;
     int S = (L + NT - 1) / NT; if (S < 1) S = 1; S |= 1;   // odd segment length: conflict-free strided shared-memory access
     ts.k0 = tid * S < L ? tid * S : L; ts.k1 = ts.k0 + S < L ? ts.k0 + S : L;
+    ts.S = S; ts.tid = tid;
     const int k0 = ts.k0, k1 = ts.k1;
 
     // ---- dead-reckoning (propagateGuess, src/consensus_utils.cpp:98-116) as two block scans --------------
@@ -1088,13 +1136,21 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         for (int m = 0; m < NPRE; ++m) ts.base[m] = 0;
     }
 
-    int buf = 0, n_sweeps = 0;
+    int buf = 0, n_sweeps = 0, n_norm = 0, n_sd = 0, n_relin = 0, n_blend = 0;
+#ifdef IPC_PHASE_CLOCKS
+    long long ph_last = 0;
+#ifdef __CUDA_ARCH__
+    ph_last = ph_start;
+#endif
+    IPC_PH(0);
+#endif
     SweepOut so;
     double cur_chi = 0, cur_max = 0, cand_chi = 0;
     double delta = 1e4;
     int iterations = 0, evals = 0, it = 0, tries = 0;
     double prev_hnorm = -1;      // norm of the last accepted step (speculation heuristic)
     bool have_norm = false, have_sd = false, need_rollback = false;
+    bool last_bound = false;     // the previous decision was trust-region bound (steepest-descent / blend step)
     double hgnNorm = 0, linearGain = 0;
     double* sc = M.U()->sc;
     double &bb = sc[0], &bh = sc[1], &hh = sc[2], &bHb = sc[3], &alpha = sc[4], &hsdNorm = sc[5];
@@ -1102,12 +1158,17 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     int purpose = P_INIT, mode = STEP_NONE;
     double c1 = 0, c2 = 0;
     for (;;) {
-        if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; }
-        sweep<NT, UNI>(M, O, mode, c1, c2, ts, so, buf, spec_v); ++n_sweeps;
+        if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
+        IPC_PH(7);
+        sweep<NT, UNI>(M, O, mode, c1, c2, ts, so, buf, spec_v IPC_PH_PASS); ++n_sweeps;
+        IPC_PH_COUNT(mode == STEP_GN ? 8 : (mode == STEP_BLEND ? 9 : 10), 1);
+        if (mode == STEP_NONE && purpose != P_INIT) ++n_relin;
+        if (mode == STEP_BLEND) ++n_blend;
         bool start_iter = false, after_reject = false, decide = false;
         if (purpose == P_INIT) {
             double n_c, n_m;
             eval_and_solve<NT>(M, buf, so.chi, 0, 1, true, n_c, n_m);
+            IPC_PH(3);
             cur_chi = so.chi + n_c + n_m; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
             gain_loops = M.U()->sol.gain_loops;
             start_iter = true;
@@ -1129,6 +1190,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             // loop edges at the trial state; thread 0 also solves the new linearisation when the step is going to be kept
             double n_c, n_m;
             eval_and_solve<NT>(M, buf, so.chi, cur_chi, linearGain, false, n_c, n_m);
+            IPC_PH(3);
             const double newChi = so.chi + n_c + n_m;
             const double rawGain = linearGain;
             double lg = linearGain;
@@ -1173,16 +1235,30 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
                     mode = STEP_GN; purpose = P_TRIAL_SPEC; c1 = 0; c2 = 1;
                     continue;
                 }
-                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; }
-                hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); have_norm = true;
+                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
+                IPC_PH(7);
+                if (prm.sd_fuse == 1 || (prm.sd_fuse == 2 && last_bound)) {
+                    sd_fused<NT, UNI>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps; ++n_sd;
+                    IPC_PH(5); IPC_PH_COUNT(12, 1);
+                    hgnNorm = sqrt(hh);
+                    alpha = bb / bHb; hsdNorm = alpha * sqrt(bb); have_sd = true;
+                } else {
+                    hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); ++n_norm; ++n_sweeps;
+                    IPC_PH(4); IPC_PH_COUNT(11, 1);
+                }
+                have_norm = true;
             }
             if (hgnNorm < delta) {
-                mode = STEP_GN; purpose = P_TRIAL_GN; c1 = 0; c2 = 1;
+                mode = STEP_GN; purpose = P_TRIAL_GN; c1 = 0; c2 = 1; last_bound = false;
                 continue;
             }
+            last_bound = true;
             if (!have_sd) {
-                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; }
-                sd_sweeps<NT, UNI>(M, O, ts, bb, bh, hh, bHb); n_sweeps += 2;
+                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
+                IPC_PH(7);
+                sd_fused<NT, UNI>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps;
+                IPC_PH(5); IPC_PH_COUNT(12, 1);
+                ++n_sd;
                 alpha = bb / bHb;
                 hsdNorm = alpha * sqrt(bb);
                 have_sd = true;
@@ -1207,6 +1283,8 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     res.verdict = (cur_max > th) ? 0 : 1;                      // every edge chi2 <= th (src/consensus_utils.cpp:17-19)
     res.max_chi2 = cur_max; res.cand_chi2 = cand_chi; res.sum_chi2 = cur_chi;
     res.iterations = iterations; res.evals = evals; res.window_len = L; res.n_loops = K; res.n_sweeps = n_sweeps;
+    res.n_norm = n_norm; res.n_sd = n_sd; res.n_relin = n_relin; res.n_blend = n_blend;
+    IPC_PH(7); IPC_PH_COUNT(13, 1); IPC_PH_COUNT(14, L); IPC_PH_COUNT(15, evals);
 }
 
 }  // namespace ipcb

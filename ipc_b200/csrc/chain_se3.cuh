@@ -791,6 +791,7 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
     int iterations = 0, evals = 0, it = 0, tries = 0;
     double prev_hnorm = -1;
     bool have_norm = false, have_sd = false, need_rollback = false;
+    bool last_bound = false;     // the previous decision was trust-region bound
     double hgnNorm = 0, bb = 0, bh = 0, hh = 0, bHb = 0, alpha = 0, hsdNorm = 0, linearGain = 0;
     double gain_loops = 0, gn_gain_model = 0;
     bool acc_gain = false;
@@ -862,12 +863,20 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
                     continue;
                 }
                 if (need_rollback) { rollback3<NT>(M, ts); need_rollback = false; }
-                hgnNorm = sqrt(gn_norm_sq3<NT>(M, odom, ts)); have_norm = true;
+                if (prm.sd_fuse && last_bound) {    // expected trust-region bound: the gradient passes also deliver |h_gn|^2
+                    sd_sweeps3<NT>(M, odom, ts, bb, bh, hh, bHb); n_sweeps += 2;
+                    hgnNorm = sqrt(hh);
+                    alpha = bb / bHb; hsdNorm = alpha * sqrt(bb); have_sd = true;
+                } else {
+                    hgnNorm = sqrt(gn_norm_sq3<NT>(M, odom, ts)); ++n_sweeps;
+                }
+                have_norm = true;
             }
             if (hgnNorm < delta) {
-                mode = STEP_GN; purpose = P_TRIAL_GN; c1 = 0; c2 = 1;
+                mode = STEP_GN; purpose = P_TRIAL_GN; c1 = 0; c2 = 1; last_bound = false;
                 continue;
             }
+            last_bound = true;
             if (!have_sd) {
                 if (need_rollback) { rollback3<NT>(M, ts); need_rollback = false; }
                 sd_sweeps3<NT>(M, odom, ts, bb, bh, hh, bHb); n_sweeps += 2;

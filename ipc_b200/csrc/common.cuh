@@ -35,6 +35,7 @@ struct BatchArgs {
     int max_tries;
     int speculate;             // apply the GN step before its norm is known when the trust region is far away
     double acc_gain_ratio;     // see CheckParams::acc_gain_ratio
+    int sd_fuse;               // see CheckParams::sd_fuse
     int early_accept;          // verdict-only batches: stop once sum chi2 <= th (the verdict can no longer change)
     unsigned char* verdict;    // per check
     ipc_check_info* info;      // per check (may be null)

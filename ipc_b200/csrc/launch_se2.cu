@@ -28,3 +28,12 @@ int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid,
 }
 
 }  // namespace ipcb
+
+#ifdef IPC_PHASE_CLOCKS
+// profiling builds only: cycles per phase summed over the CTAs' thread 0 (see IPC_PH in chain_se2.cuh)
+extern "C" int ipc_debug_phase_clocks(unsigned long long* out16, int reset) {
+    if (cudaMemcpyFromSymbol(out16, ipcb::g_phase, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; if (cudaMemcpyToSymbol(ipcb::g_phase, z, sizeof z) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif

@@ -12,13 +12,9 @@ dev = torch.device("cuda", 0)
 md, cd = torch.from_numpy(mem).to(dev), torch.from_numpy(cnd).to(dev)
 bits = torch.zeros((n_s + 31) // 32, dtype=torch.int32, device=dev)
 variants = {
-    "default(128x3,128x2,256x1)": {},
-    "b3_64x2": {"bucket3_nt": 64, "bucket3_minb": 2},
-    "b2_64x4": {"bucket2_nt": 64, "bucket2_minb": 4},
-    "b4_128x1": {"bucket4_nt": 128, "bucket4_minb": 1},
-    "b1_64x4": {"bucket1_minb": 4},
-    "b0_32x8": {"bucket0_minb": 8},
-    "b2_cap1700": {"bucket2_cap": 1700},
+    "sd_fuse=0 (norm pass, then gradient pass)": {"sd_fuse": 0},
+    "sd_fuse=1 (always fused)": {"sd_fuse": 1},
+    "sd_fuse=2 (default: fused when bound)": {},
 }
 ref = None
 for name, opts in variants.items():
@@ -32,5 +28,5 @@ for name, opts in variants.items():
         torch.cuda.synchronize(); ts.append(time.perf_counter() - t)
     b = bits.clone()
     if ref is None: ref = b
-    print(json.dumps({"variant": name, "checks_per_s": n_s / min(ts[1:]), "times": [round(x, 3) for x in ts], "bits_equal_default": bool((b == ref).all().item())}), flush=True)
+    print(json.dumps({"variant": name, "checks_per_s": n_s / min(ts[1:]), "times": [round(x, 3) for x in ts], "bits_equal_first": bool((b == ref).all().item())}), flush=True)
     ipc.close()

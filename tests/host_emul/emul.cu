@@ -10,6 +10,10 @@
 
 using namespace ipcb;
 
+static int* g_diag = nullptr;
+static int g_sd_fuse = 2;
+extern "C" void emul_set_sd_fuse(int v) { g_sd_fuse = v; }
+extern "C" void emul_set_diag(int* p) { g_diag = p; }
 template <class PT> static int emul_impl(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
                                 const int* lto, const double* lmeas, const double* linfo, int n_checks, const int* member, const int* cand,
                                 double fast_th, double slow_th, int fast_iter, int slow_iter, double noise_eps, int speculate, int early_accept,
@@ -21,13 +25,14 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
     std::vector<double> soa; hs.build_odom_aos(uni, n_pad, soa);
     std::vector<LoopRec2> recs(n_loops);
     for (int i = 0; i < n_loops; ++i) { recs[i].from = lfrom[i]; recs[i].to = lto[i]; HostState::se2_edge_record(lmeas + 3 * i, linfo + 9 * i, 1.0, recs[i].meas, recs[i].D); HostState::inv_sym3_host(recs[i].D, recs[i].V); }
-    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, 1e-6};
+    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse, 1e-6};
     std::atomic<int> next{0};
     auto work = [&]() {
         const int capv = n_poses + 2;
-        std::vector<double> buf((size_t)(CHAIN_STATE_ARRAYS + CHAIN_SCRATCH_ARRAYS) * capv + CHAIN_SMALL_DOUBLES, 0.0);
+        const int capg = scratch_slots<1>(capv);
+        std::vector<double> buf((size_t)CHAIN_STATE_ARRAYS * capv + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
         ChainMem M; double* p = buf.data();
-        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN_STATE_ARRAYS * capv; M.capv = capv;
+        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN_STATE_ARRAYS * capv; M.capv = capv; M.capg = capg;
         for (;;) {
             int c = next.fetch_add(1);
             if (c >= n_checks) break;
@@ -38,6 +43,7 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
             if (info) { info[c].max_chi2 = r.max_chi2; info[c].cand_chi2 = r.cand_chi2; info[c].sum_chi2 = r.sum_chi2; info[c].iterations = r.iterations;
                         info[c].evals = r.evals; info[c].window_len = r.window_len; info[c].n_loops = r.n_loops; }
             if (sweeps) sweeps[c] = r.n_sweeps;
+            if (g_diag) { g_diag[4 * c] = r.n_norm; g_diag[4 * c + 1] = r.n_sd; g_diag[4 * c + 2] = r.n_relin; g_diag[4 * c + 3] = r.n_blend; }
         }
     };
     std::vector<std::thread> th;
@@ -76,7 +82,7 @@ extern "C" int emul_check_batch3(int n_poses, const double* odom_meas, const dou
         for (int q = 0; q < 7; ++q) recs[i].zinv[q] = r[q];
         for (int q = 0; q < 21; ++q) { recs[i].Om[q] = r[7 + q]; recs[i].V[q] = r[28 + q]; }
     }
-    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, 1e-6};
+    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse, 1e-6};
     std::atomic<int> next{0};
     auto work = [&]() {
         const int capv = n_poses + 2;

@@ -40,3 +40,21 @@ def test_early_accept_keeps_verdicts():
     assert np.array_equal(a1, z["accept"])
     a0, i0, s0 = emul.check_batch(g, cfg, z["member"], z["cand"], early_accept=0, want_info=0)
     assert s1.sum() < s0.sum()
+
+
+def test_fused_steepest_descent_pass_equals_separate_passes():
+    """sd_fuse only changes how many passes compute (|h_gn|, b.b, b.h, bHb): the Dogleg trajectory must not move."""
+    from tests.host_emul import emul
+    z, g, cfg = load("pairs_se2_m3500.npz")
+    out = {}
+    try:
+        for mode in (0, 1, 2):
+            emul.lib().emul_set_sd_fuse(mode)
+            out[mode] = emul.check_batch(g, cfg, z["member"], z["cand"])
+    finally:
+        emul.lib().emul_set_sd_fuse(2)
+    for mode in (1, 2):
+        assert np.array_equal(out[mode][0], out[0][0])
+        assert np.array_equal(out[mode][1]["iterations"], out[0][1]["iterations"])
+        assert rel_err(out[mode][1]["max_chi2"], out[0][1]["max_chi2"]).max() < 1e-9
+        assert out[mode][2].sum() < out[0][2].sum()      # fewer passes over the chain
