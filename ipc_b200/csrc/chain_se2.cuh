@@ -331,7 +331,7 @@ constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
 constexpr int RED_DOUBLES_ = 16 * (NPRE + 4);
 struct ChainMem {            // three base pointers + a capacity: cheap to keep in registers and to pass by value
     double* st;              // per-vertex state, AoS of 5 doubles: x, y, theta, cos, sin. Shared memory (MODE 0) or global scratch (MODE 1)
-    double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capg, then (b, h_gn) AoS[6] x capg, indexed
+    double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capg, (b, h_gn) AoS[6] x capg, odometry records, indexed
                              // by SLOT (vslot below), not by vertex: the threads of a warp walk their segments in lock step, so
                              // slot = step * NT + thread makes every scratch access of a warp one contiguous run of records
     double* small;           // shared memory: collective staging (2 buffers), special-vertex table (2 buffers), UniBlock
@@ -339,6 +339,7 @@ struct ChainMem {            // three base pointers + a capacity: cheap to keep 
     IPC_HD double* P(int j) const { return st + 5 * j; }                          // x y theta cos sin of vertex j
     IPC_HD double* B(int sl) const { return scr + 3 * sl; }                       // pose backup: state before the last trial sweep
     IPC_HD double* G(int sl) const { return scr + 3 * (size_t)capg + 6 * sl; }    // gradient b_j (3) and h_gn,j (3), g2o vertex coordinates
+    IPC_HD double* Z() const { return scr + 9 * (size_t)capg; }                  // odometry records of the window, slot order (3 or 9 / edge)
     IPC_HD double* red() const { return small; }
     IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_; }
     IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + 2 * NSPEC * SPECW); }
@@ -350,13 +351,15 @@ template <int NT> IPC_HD constexpr int scratch_slots(int capv) { return capv + 2
 constexpr int RED_DOUBLES = 16 * (NPRE + 4);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 3
 constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
 constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
-constexpr int CHAIN_SCRATCH_ARRAYS = 9;          // per-vertex doubles in the global scratch (backup, b, h_gn)
+constexpr int CHAIN_SCRATCH_ARRAYS = 18;         // per-slot doubles in the global scratch (backup 3, b + h_gn 6, odometry record <= 9)
 
 
 struct OdomView {            // odometry records of the window in HBM/L2, AoS: (zx zy zt) when every edge shares one isotropic
     const double* rec;       // information (UNI, 24 B / edge), else (zx zy zt d00 d01 d02 d11 d12 d22) (72 B / edge)
     const double* Du;        // UNI: the shared information matrix (frame independent) ...
     const double* Vu;        //      ... and its inverse
+    double* zs;              // the window's records again, in the per-CTA scratch in SLOT order (edge k0 + i of thread t at i * NT + t):
+                             // written once per check by the dead-reckoning pass, read by every later pass as contiguous warp accesses
 };
 template <bool UNI> IPC_HD const double* odom_rec(const OdomView& O, int k) { return O.rec + (UNI ? 3 : 9) * (size_t)k; }
 IPC_HD double ldg_d(const double* p) {
@@ -420,10 +423,10 @@ IPC_HD void edge_prefix_terms_iso(const Lin2& e, double va, double vc, double xb
 }
 // z[0..2] (and D for the general case) of one odometry edge, loaded ahead of use
 template <bool UNI> struct OdomRec { double z[UNI ? 3 : 9]; };
-template <bool UNI> IPC_HD void odom_load(const OdomView& O, int k, OdomRec<UNI>& r) {
-    const double* p = odom_rec<UNI>(O, k);
+template <bool UNI> IPC_HD void odom_load(const OdomView& O, int es /* edge slot */, OdomRec<UNI>& r) {
+    const double* p = O.zs + (UNI ? 3 : 9) * (size_t)es;
 #pragma unroll
-    for (int q = 0; q < (UNI ? 3 : 9); ++q) r.z[q] = ldg_d(p + q);
+    for (int q = 0; q < (UNI ? 3 : 9); ++q) r.z[q] = p[q];     // plain loads: this kernel wrote them
 }
 template <bool UNI> IPC_HD void odom_terms(const OdomView& O, const OdomRec<UNI>& r, double c, double s, const P2& a, const P2& b, Lin2& e, double* t) {
     if (UNI) {
@@ -477,7 +480,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     double gn6[6] = {0, 0, 0, 0, 0, 0};      // blend steps: (b, h_gn) of the next vertex, from the global scratch
     int sl = ts.tid + 1;                     // scratch slot of vertex k0 + 1; + NT per vertex
     if (k0 < k1) {
-        odom_load<UNI>(O, k0, rn);
+        odom_load<UNI>(O, sl - 1, rn);       // edge slot = slot of the edge's head vertex - 1
         if (mode == STEP_BLEND) { const double* gq = M.G(sl);
 #pragma unroll
             for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
@@ -489,7 +492,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
 #pragma unroll
         for (int q = 0; q < 6; ++q) g6[q] = gn6[q];
         if (j < k1) {
-            odom_load<UNI>(O, k + 1, rn);
+            odom_load<UNI>(O, sl + NT - 1, rn);
             if (mode == STEP_BLEND) { const double* gq = M.G(sl + NT);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
@@ -893,13 +896,14 @@ template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const Od
     for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
     P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
     OdomRec<UNI> rn;
-    if (ts.k0 < ts.k1) odom_load<UNI>(O, ts.k0, rn);
-    for (int k = ts.k0; k < ts.k1; ++k) {
+    int es = ts.tid;
+    if (ts.k0 < ts.k1) odom_load<UNI>(O, es, rn);
+    for (int k = ts.k0; k < ts.k1; ++k, es += NT) {
         const int j = k + 1;
         const double* pq = M.P(j);
         const P2 pb{pq[0], pq[1], pq[2]};
         const OdomRec<UNI> r = rn;
-        if (j < ts.k1) odom_load<UNI>(O, k + 1, rn);
+        if (j < ts.k1) odom_load<UNI>(O, es + NT, rn);
         Lin2 e; double t[NPRE], h[3];
         odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
 #pragma unroll
@@ -969,13 +973,14 @@ template <int NT, bool UNI> IPC_HD void sd_fused(const ChainMem& M, const OdomVi
         P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
         double gprev[3] = {0, 0, 0};
         int sl = ts.tid + 1;
-        OdomRec<UNI> rn; odom_load<UNI>(O, k0, rn);
-        for (int k = k0; k <= k1 && k < L; ++k) {
+        int es = ts.tid;
+        OdomRec<UNI> rn; odom_load<UNI>(O, es, rn);
+        for (int k = k0; k <= k1 && k < L; ++k, es += NT) {
             const double* pq = M.P(k + 1);
             P2 pb{pq[0], pq[1], pq[2]};
             Lin2 e; double t[NPRE];
             const OdomRec<UNI> r = rn;
-            if (k + 1 <= k1 && k + 1 < L) odom_load<UNI>(O, k + 1, rn);
+            if (k + 1 <= k1 && k + 1 < L) odom_load<UNI>(O, k + 1 < k1 ? es + NT : ts.tid + 1, rn);   // edge k1: first of thread tid + 1
             odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
             double gi[3], gj[3]; grad2(e, gi, gj);
             if (k > k0) {
@@ -1091,7 +1096,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     const double th = (K == 2) ? prm.slow_th : prm.fast_th;
     int max_iter = (K == 2) ? prm.slow_iter : prm.fast_iter;
     if (L + K > 100) max_iter *= 5;                        // src/consensus_utils.cpp:12-13
-    OdomView O{odom + (UNI ? 3 : 9) * (size_t)M.U()->g.lo, Du, Vu};
+    OdomView O{odom + (UNI ? 3 : 9) * (size_t)M.U()->g.lo, Du, Vu, M.Z()};
 
     ThreadState ts;
     int S = (L + NT - 1) / NT; if (S < 1) S = 1; S |= 1;   // odd segment length: conflict-free strided shared-memory access
@@ -1102,7 +1107,15 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     // ---- dead-reckoning (propagateGuess, src/consensus_utils.cpp:98-116) as two block scans --------------
     {
         double v[1] = {0};
-        for (int k = k0; k < k1; ++k) v[0] += ldg_d(odom_rec<UNI>(O, k) + 2);
+        {   // the only strided read of the odometry: the records go to the scratch in slot order
+            int es = tid;
+            for (int k = k0; k < k1; ++k, es += NT) {
+                const double* zr = odom_rec<UNI>(O, k);
+                double* zo = O.zs + (UNI ? 3 : 9) * (size_t)es;
+#pragma unroll
+                for (int q = 0; q < (UNI ? 3 : 9); ++q) { const double x = ldg_d(zr + q); zo[q] = x; if (q == 2) v[0] += x; }
+            }
+        }
         hd_block_excl_scan<NT, 1>(v, M.red());
         double acc = v[0];
         const double th0 = wrap_pi_hd(acc);                 // heading of vertex k0
@@ -1110,9 +1123,10 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         double p[2] = {0, 0};
         double s, c; ipc_sincos(th0, &s, &c);
         ts.pa.t = th0; ts.ca = c; ts.sa = s;
-        for (int k = k0; k < k1; ++k) {
-            const double* zr = odom_rec<UNI>(O, k);
-            const double zx = ldg_d(zr), zy = ldg_d(zr + 1), zt = ldg_d(zr + 2);
+        int es = tid;
+        for (int k = k0; k < k1; ++k, es += NT) {
+            const double* zr = O.zs + (UNI ? 3 : 9) * (size_t)es;
+            const double zx = zr[0], zy = zr[1], zt = zr[2];
             p[0] += c * zx - s * zy; p[1] += s * zx + c * zy;
             acc += zt;
             const double thk = wrap_pi_hd(acc);
@@ -1125,9 +1139,10 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         double ax = p[0], ay = p[1];
         ts.pa.x = ax; ts.pa.y = ay;
         c = ts.ca; s = ts.sa;
-        for (int k = k0; k < k1; ++k) {
-            const double* zr = odom_rec<UNI>(O, k);
-            const double zx = ldg_d(zr), zy = ldg_d(zr + 1);
+        es = tid;
+        for (int k = k0; k < k1; ++k, es += NT) {
+            const double* zr = O.zs + (UNI ? 3 : 9) * (size_t)es;
+            const double zx = zr[0], zy = zr[1];
             ax += c * zx - s * zy; ay += s * zx + c * zy;
             double* pq = M.P(k + 1);
             pq[0] = ax; pq[1] = ay; c = pq[3]; s = pq[4];
