@@ -12,9 +12,15 @@ dev = torch.device("cuda", 0)
 md, cd = torch.from_numpy(mem).to(dev), torch.from_numpy(cnd).to(dev)
 bits = torch.zeros((n_s + 31) // 32, dtype=torch.int32, device=dev)
 variants = {
+    "default (sd_fuse=2; 32x16, 64x8, 128x3, 128x2, 256x1)": {},
     "sd_fuse=0 (norm pass, then gradient pass)": {"sd_fuse": 0},
-    "sd_fuse=1 (always fused)": {"sd_fuse": 1},
-    "sd_fuse=2 (default: fused when bound)": {},
+    "sd_fuse=1 (always the gradient pass)": {"sd_fuse": 1},
+    "b2_cap1700": {"bucket2_cap": 1700},
+    "b2_cap1000": {"bucket2_cap": 1000},
+    "b3_192x2": {"bucket3_nt": 192, "bucket3_minb": 2},
+    "b3_256x1": {"bucket3_nt": 256, "bucket3_minb": 1},
+    "b4_384x1": {"bucket4_nt": 384, "bucket4_minb": 1},
+    "b1_64x4": {"bucket1_minb": 4},
 }
 ref = None
 for name, opts in variants.items():
