@@ -127,7 +127,8 @@ int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsign
 /* Knobs (non-reference). noise_exit: 1 (default) stops the Dogleg retry loop once a rejected trial's own predicted gain is
  * below 1e-13 * chi2 (DESIGN.md "Termination"), 0 replays all 100 retries like g2o, any other value is used as the threshold.
  * early_accept: 1 lets verdict-only batches stop as soon as sum chi2 <= threshold (same bits). speculate, use_uniform,
- * max_tries, bucket<i>_cap / bucket<i>_nt / bucket<i>_minb (launch shapes, i = 0..4): tuning, see DESIGN.md. */
+ * max_tries, sd_fuse (0 / 1 / 2: when the steepest-descent pass replaces the norm pass; results identical),
+ * bucket<i>_cap / bucket<i>_nt / bucket<i>_minb (launch shapes, i = 0..4): tuning, see DESIGN.md. */
 int ipc_set_option(ipc_handle* h, const char* name, double value);
 
 #ifdef __cplusplus
