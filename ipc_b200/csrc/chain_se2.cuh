@@ -1040,7 +1040,6 @@ struct CheckParams {
     int sd_fuse;             // when the GN norm is needed before a trial: 0 = norm pass, then the steepest-descent pass if the step
                              // does not fit; 1 = always the steepest-descent pass (it also delivers the norm); 2 (default) = the
                              // steepest-descent pass when the previous decision was trust-region bound, else the norm pass
-    double acc_gain_ratio;   // the predicted GN gain is accumulated edge by edge (extra pass) once chi2 - model < ratio * chi2 (default 1e-6)
 };
 struct CheckResult {
     int verdict;

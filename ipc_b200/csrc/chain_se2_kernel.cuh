@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_check_se2(BatchArgs A) {
     M.small = sm; M.scr = scr; M.capv = capv; M.capg = scratch_slots<NT>(capv);
     M.st = (MODE == 0) ? sm + CHAIN_SMALL_DOUBLES : scr + (size_t)CHAIN_SCRATCH_ARRAYS * M.capg;
     const LoopRec2* loops = static_cast<const LoopRec2*>(A.loops);
-    CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept, A.sd_fuse, A.acc_gain_ratio};
+    CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept, A.sd_fuse};
     const int n_work = *A.n_work;
     __shared__ int s_wi;
     for (;;) {

@@ -98,7 +98,6 @@ struct ipc_handle {
     int early_accept = 0;
     int use_uniform = 1;              // allow the uniform-information kernels when the graph qualifies
     int sd_fuse = 2;                  // see CheckParams::sd_fuse
-    double acc_gain_ratio = 1e-6;     // GN trials accumulate the predicted gain edge by edge once chi2 - model < ratio * chi2
     Bucket buckets[NB];               // launch buckets (tunable: options bucket<i>_cap / bucket<i>_nt)
     HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
     // device graph
@@ -202,7 +201,7 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         a.Lcap = (std::min(bk.cap, h->n - 1) + 1) & ~1;
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
         a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
-        a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept; a.acc_gain_ratio = h->acc_gain_ratio; a.sd_fuse = h->sd_fuse;
+        a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept; a.sd_fuse = h->sd_fuse;
         a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch;
         a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap, h->dim, bk.nt);
         size_t sm = smem_bytes(bk.mode, a.Lcap, h->dim, bk.nt);
@@ -332,7 +331,6 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
     if (!h || !name) return fail(IPC_ERR_ARG, "null argument");
     if (!strcmp(name, "noise_exit")) { h->noise_eps = value == 1.0 ? 1e-13 : value; return IPC_OK; }   // 0 = off, 1 = default eps, else eps
     if (!strcmp(name, "sd_fuse")) { if (value < 0 || value > 2) return fail(IPC_ERR_ARG, "sd_fuse: 0, 1 or 2"); h->sd_fuse = (int)value; return IPC_OK; }
-    if (!strcmp(name, "acc_gain_ratio")) { h->acc_gain_ratio = value; return IPC_OK; }
     if (!strncmp(name, "bucket", 6) && name[6] >= '0' && name[6] < '0' + NB && name[7] == '_') {
         const int b = name[6] - '0';
         if (!strcmp(name + 8, "cap")) h->buckets[b].cap = (int)value;

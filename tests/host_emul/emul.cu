@@ -25,7 +25,7 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
     std::vector<double> soa; hs.build_odom_aos(uni, n_pad, soa);
     std::vector<LoopRec2> recs(n_loops);
     for (int i = 0; i < n_loops; ++i) { recs[i].from = lfrom[i]; recs[i].to = lto[i]; HostState::se2_edge_record(lmeas + 3 * i, linfo + 9 * i, 1.0, recs[i].meas, recs[i].D); HostState::inv_sym3_host(recs[i].D, recs[i].V); }
-    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse, 1e-6};
+    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse};
     std::atomic<int> next{0};
     auto work = [&]() {
         const int capv = n_poses + 2;
@@ -82,7 +82,7 @@ extern "C" int emul_check_batch3(int n_poses, const double* odom_meas, const dou
         for (int q = 0; q < 7; ++q) recs[i].zinv[q] = r[q];
         for (int q = 0; q < 21; ++q) { recs[i].Om[q] = r[7 + q]; recs[i].V[q] = r[28 + q]; }
     }
-    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse, 1e-6};
+    CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse};
     std::atomic<int> next{0};
     auto work = [&]() {
         const int capv = n_poses + 2;
