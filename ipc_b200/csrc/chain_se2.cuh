@@ -164,16 +164,24 @@ constexpr int NPRE = 9;      // prefix quantities: PM (00 01 02 11 12 22), Pm (0
 constexpr int NSPEC = 4;     // special vertices of a check: 0, rs, re, L (all loop end points are among them)
 constexpr int SPECW = NPRE + 3;   // published per special vertex: full prefix + pose
 
+// Host build (tests/host_emul, TEST INFRASTRUCTURE): NT = 1 runs a check on the calling thread; NT > 1 emulates the CTA with NT
+// OS threads that share a barrier, so the block decomposition (segments, scratch slots, boundary vertices, collectives) is
+// exercised on a box without a GPU. The host collectives sum in thread order (the device sums in shuffle-tree order).
+struct HostCta { int tid; void (*sync)(void*); void* ctx; };
+inline HostCta*& host_cta() { static thread_local HostCta* p = nullptr; return p; }
 template <int NT> IPC_HD void bsync() {
 #ifdef __CUDA_ARCH__
     if (NT <= 32) __syncwarp(); else __syncthreads();
+#else
+    if (NT > 1) { HostCta* c = host_cta(); c->sync(c->ctx); }
 #endif
 }
 IPC_HD int hd_tid() {
 #ifdef __CUDA_ARCH__
     return threadIdx.x;
 #else
-    return 0;
+    HostCta* c = host_cta();
+    return c ? c->tid : 0;
 #endif
 }
 
@@ -231,8 +239,18 @@ template <int NT, int NS> struct ScanSumMax {
         for (int i = 1; i < NW; ++i) t = fmax(t, red[i * W + NPRE + NS]);
         mx = t;
 #else
-        for (int m = 0; m < NPRE; ++m) v[m] = 0;
-        (void)s; (void)mx; (void)red;
+        if (NT == 1) { for (int m = 0; m < NPRE; ++m) v[m] = 0; return; }
+        static_assert(NT * W <= 16 * (NPRE + 4), "host emulation: staging holds 16 threads");
+        const int t = hd_tid();
+        for (int m = 0; m < NPRE; ++m) red[t * W + m] = v[m];
+        for (int m = 0; m < NS; ++m) red[t * W + NPRE + m] = s[m];
+        red[t * W + NPRE + NS] = mx;
+        bsync<NT>();
+        for (int m = 0; m < NPRE; ++m) { double b = 0; for (int i = 0; i < t; ++i) b += red[i * W + m]; v[m] = b; }
+        for (int m = 0; m < NS; ++m) { double b = 0; for (int i = 0; i < NT; ++i) b += red[i * W + NPRE + m]; s[m] = b; }
+        double b = red[NPRE + NS];
+        for (int i = 1; i < NT; ++i) b = fmax(b, red[i * W + NPRE + NS]);
+        mx = b;
 #endif
     }
 };
@@ -260,7 +278,12 @@ template <int NT, int M> IPC_HD void hd_block_sum(double* v, double* red) {
         v[m] = s;
     }
 #else
-    (void)v; (void)red;
+    if (NT == 1) return;
+    const int t = hd_tid();
+    bsync<NT>();
+    for (int m = 0; m < M; ++m) red[t * M + m] = v[m];
+    bsync<NT>();
+    for (int m = 0; m < M; ++m) { double b = 0; for (int i = 0; i < NT; ++i) b += red[i * M + m]; v[m] = b; }
 #endif
 }
 // exclusive prefix over threads of M values (dead-reckoning): two barriers
@@ -290,8 +313,12 @@ template <int NT, int M> IPC_HD void hd_block_excl_scan(double* v, double* red) 
         v[m] = base + inc[m] - v[m];
     }
 #else
-    for (int m = 0; m < M; ++m) v[m] = 0;
-    (void)red;
+    if (NT == 1) { for (int m = 0; m < M; ++m) v[m] = 0; return; }
+    const int t = hd_tid();
+    bsync<NT>();
+    for (int m = 0; m < M; ++m) red[t * M + m] = v[m];
+    bsync<NT>();
+    for (int m = 0; m < M; ++m) { double b = 0; for (int i = 0; i < t; ++i) b += red[i * M + m]; v[m] = b; }
 #endif
 }
 
@@ -329,6 +356,7 @@ struct UniBlock {            // uniform per-check data (shared memory): read by 
 constexpr int UNI_DOUBLES = (sizeof(UniBlock) + 7) / 8;
 
 constexpr int RED_DOUBLES_ = 16 * (NPRE + 4);
+constexpr int RED2_DOUBLES_ = 16 * 4;            // 16 warps x up to 4 values
 struct ChainMem {            // three base pointers + a capacity: cheap to keep in registers and to pass by value
     double* st;              // per-vertex state, AoS of 5 doubles: x, y, theta, cos, sin. Shared memory (MODE 0) or global scratch (MODE 1)
     double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capg, (b, h_gn) AoS[6] x capg, odometry records, indexed
@@ -340,16 +368,19 @@ struct ChainMem {            // three base pointers + a capacity: cheap to keep 
     IPC_HD double* B(int sl) const { return scr + 3 * sl; }                       // pose backup: state before the last trial sweep
     IPC_HD double* G(int sl) const { return scr + 3 * (size_t)capg + 6 * sl; }    // gradient b_j (3) and h_gn,j (3), g2o vertex coordinates
     IPC_HD double* Z() const { return scr + 9 * (size_t)capg; }                  // odometry records of the window, slot order (3 or 9 / edge)
-    IPC_HD double* red() const { return small; }
-    IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_; }
-    IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + 2 * NSPEC * SPECW); }
+    IPC_HD double* red() const { return small; }                                 // sweep collective (ScanSumMax), double-buffered by the caller
+    IPC_HD double* red2() const { return small + 2 * RED_DOUBLES_; }             // two-barrier collectives (block sum, dead-reckoning scans): their
+                                                                                 // own staging, so a sweep that follows without a barrier cannot
+                                                                                 // overwrite values a slower warp is still reading
+    IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_ + RED2_DOUBLES_; }
+    IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + RED2_DOUBLES_ + 2 * NSPEC * SPECW); }
 };
 // scratch slot of vertex j for segments of S vertices per thread: vertex 0 -> 0; vertex k0 + 1 + i of thread t -> i * NT + t + 1.
 // Slots reach S * NT <= L + 2 NT, hence capg = capv + 2 NT + 2.
 template <int NT> IPC_HD int vslot(int j, int S) { return j == 0 ? 0 : ((j - 1) % S) * NT + (j - 1) / S + 1; }
 template <int NT> IPC_HD constexpr int scratch_slots(int capv) { return capv + 2 * NT + 2; }
 constexpr int RED_DOUBLES = 16 * (NPRE + 4);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 3
-constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
+constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + RED2_DOUBLES_ + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
 constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
 constexpr int CHAIN_SCRATCH_ARRAYS = 18;         // per-slot doubles in the global scratch (backup 3, b + h_gn 6, odometry record <= 9)
 
@@ -881,7 +912,7 @@ template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, int buf, double 
 #ifdef __CUDA_ARCH__
     if (threadIdx.x < 32) eval_and_solve_w0(M, buf, odom_chi, cur_chi, linearGain, force);
 #else
-    eval_and_solve_w0(M, buf, odom_chi, cur_chi, linearGain, force);
+    if (hd_tid() == 0) eval_and_solve_w0(M, buf, odom_chi, cur_chi, linearGain, force);
 #endif
     bsync<NT>();
     n_c = M.U()->n_c; n_m = M.U()->n_m;
@@ -912,7 +943,7 @@ template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const Od
         v[0] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
         pa = pb; ca = pq[3]; sa = pq[4];
     }
-    hd_block_sum<NT, 1>(v, M.red());
+    hd_block_sum<NT, 1>(v, M.red2());
     return v[0];
 }
 
@@ -1027,7 +1058,7 @@ template <int NT, bool UNI> IPC_HD void sd_fused(const ChainMem& M, const OdomVi
             dlin2(em, mf, mt, q0, q1, q2); v[3] += quad3(Lm.D, q0, q1, q2);
         }
     }
-    hd_block_sum<NT, 4>(v, M.red());
+    hd_block_sum<NT, 4>(v, M.red2());
     bb = v[0]; bh = v[1]; hh = v[2]; bHb = v[3];
 }
 
@@ -1115,7 +1146,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
                 for (int q = 0; q < (UNI ? 3 : 9); ++q) { const double x = ldg_d(zr + q); zo[q] = x; if (q == 2) v[0] += x; }
             }
         }
-        hd_block_excl_scan<NT, 1>(v, M.red());
+        hd_block_excl_scan<NT, 1>(v, M.red2());
         double acc = v[0];
         const double th0 = wrap_pi_hd(acc);                 // heading of vertex k0
         if (tid == 0) { double* p0 = M.P(0); p0[0] = 0; p0[1] = 0; p0[2] = 0; p0[3] = 1; p0[4] = 0; }
@@ -1134,7 +1165,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             pq[2] = thk; pq[3] = c; pq[4] = s;
         }
         bsync<NT>();
-        hd_block_excl_scan<NT, 2>(p, M.red());
+        hd_block_excl_scan<NT, 2>(p, M.red2());
         double ax = p[0], ay = p[1];
         ts.pa.x = ax; ts.pa.y = ay;
         c = ts.ca; s = ts.sa;

@@ -581,7 +581,7 @@ template <int NT> IPC_HD double gn_norm_sq3(const ChainMem3& M, const double* od
         for (int q = 0; q < 6; ++q) v[0] += u[q] * u[q];
         pa = pb;
     }
-    hd_block_sum<NT, 1>(v, M.red());
+    hd_block_sum<NT, 1>(v, M.stage());
     return v[0];
 }
 
@@ -652,7 +652,7 @@ template <int NT> IPC_HD void sd_sweeps3(const ChainMem3& M, const double* odom,
     if (hd_tid() == 0) { double* g0 = M.G(0);
 #pragma unroll
         for (int q = 0; q < 12; ++q) g0[q] = 0; }
-    hd_block_sum<NT, 3>(v, M.red());
+    hd_block_sum<NT, 3>(v, M.stage());
     bsync<NT>();
     bb = v[0]; bh = v[1]; hh = v[2];
     double w[1] = {0};
@@ -690,7 +690,7 @@ template <int NT> IPC_HD void sd_sweeps3(const ChainMem3& M, const double* odom,
             w[0] += sym6_quad(Lm.Om, q1);
         }
     }
-    hd_block_sum<NT, 1>(w, M.red());
+    hd_block_sum<NT, 1>(w, M.stage());
     bHb = w[0];
 }
 

@@ -58,3 +58,24 @@ def test_fused_steepest_descent_pass_equals_separate_passes():
         assert np.array_equal(out[mode][1]["iterations"], out[0][1]["iterations"])
         assert rel_err(out[mode][1]["max_chi2"], out[0][1]["max_chi2"]).max() < 1e-9
         assert out[mode][2].sum() < out[0][2].sum()      # fewer passes over the chain
+
+
+@pytest.mark.parametrize("nt", [8, 16])
+@pytest.mark.parametrize("name,use_uni", [("pairs_se2_intel.npz", 0), ("pairs_se2_m3500.npz", 1), ("pairs_se2_m3500.npz", 0)])
+def test_emulated_cta_decomposition_matches_golden(name, use_uni, nt):
+    """The block decomposition of the kernel (thread segments, scratch slots, boundary vertices, the lagged b^T H b term,
+    block collectives) on nt cooperating OS threads per check: same verdicts, chi2 at round-off distance (sums are
+    re-associated, exactly as on the device)."""
+    from tests.host_emul import emul
+    z, g, cfg = load(name)
+    assert emul.lib().emul_set_cta_threads(nt) == 0
+    try:
+        for fuse in (0, 1, 2):
+            emul.lib().emul_set_sd_fuse(fuse)
+            acc, info, _ = emul.check_batch(g, cfg, z["member"], z["cand"], use_uni=use_uni, n_threads=2 * nt)
+            assert np.array_equal(acc, z["accept"])
+            assert rel_err(info["max_chi2"], z["max_chi2"]).max() < 1e-4
+            assert np.array_equal(info["window_len"], z["hi"] - z["lo"])
+    finally:
+        emul.lib().emul_set_sd_fuse(2)
+        emul.lib().emul_set_cta_threads(1)
