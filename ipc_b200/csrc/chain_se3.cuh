@@ -319,8 +319,18 @@ template <int NT, int NS> struct ScanSumMax3 {
         for (int i = 1; i < NW; ++i) t = fmax(t, red[i * W + NP3 + NS]);
         mx = t;
 #else
-        for (int m = 0; m < NP3; ++m) v[m] = 0;
-        (void)s; (void)mx; (void)red;
+        if (NT == 1) { for (int m = 0; m < NP3; ++m) v[m] = 0; return; }
+        static_assert(NT * W <= 16 * (NP3 + 4), "host emulation: staging holds 16 threads");
+        const int t = hd_tid();          // host emulation of the CTA (chain_se2.cuh, HostCta): sums in thread order
+        for (int m = 0; m < NP3; ++m) red[t * W + m] = v[m];
+        for (int m = 0; m < NS; ++m) red[t * W + NP3 + m] = s[m];
+        red[t * W + NP3 + NS] = mx;
+        bsync<NT>();
+        for (int m = 0; m < NP3; ++m) { double b = 0; for (int i = 0; i < t; ++i) b += red[i * W + m]; v[m] = b; }
+        for (int m = 0; m < NS; ++m) { double b = 0; for (int i = 0; i < NT; ++i) b += red[i * W + NP3 + m]; s[m] = b; }
+        double b = red[NP3 + NS];
+        for (int i = 1; i < NT; ++i) b = fmax(b, red[i * W + NP3 + NS]);
+        mx = b;
 #endif
     }
 };
@@ -714,8 +724,15 @@ template <int NT> IPC_HD void se3_excl_scan(const ChainMem3& M, const P3& mine, 
     excl = acc;
     __syncthreads();
 #else
-    (void)M; (void)mine;
     excl.t[0] = excl.t[1] = excl.t[2] = 0; excl.q[0] = 1; excl.q[1] = excl.q[2] = excl.q[3] = 0;
+    if (NT > 1) {
+        double* tot = M.st;
+        const int t = hd_tid();
+        store_pose(tot + 7 * t, mine);
+        bsync<NT>();
+        for (int i = 0; i < t; ++i) { P3 nx, r; load_pose(tot + 7 * i, nx); se3_mul(excl, nx, r); excl = r; }
+        bsync<NT>();
+    }
 #endif
 }
 

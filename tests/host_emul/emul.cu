@@ -128,6 +128,36 @@ extern "C" int emul_check_batch(int n_poses, const double* odom_meas, const doub
 
 // ---- SE(3) ------------------------------------------------------------------------------------------------------------
 #include "../../ipc_b200/csrc/chain_se3.cuh"
+template <int NT, class Out>
+static void cta_group3(int n_poses, const double* odom, const ipcb::se3::LoopRec3* recs, int n_checks, const int* member, const int* cand,
+                       const CheckParams& prm, bool want_info, std::atomic<int>& next, Out&& out) {
+    using namespace ipcb::se3;
+    const int capv = std::max(n_poses + 2, NT);
+    std::vector<double> buf((size_t)(CHAIN3_STATE + CHAIN3_SCRATCH) * capv + CHAIN3_SMALL_DOUBLES, 0.0);
+    ChainMem3 M; double* p = buf.data();
+    M.small = p; M.st = p + CHAIN3_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN3_STATE * capv; M.capv = capv;
+    SpinBarrier bar; bar.n = NT;
+    int cur = 0;
+    auto body = [&](int tid) {
+        HostCta cta{tid, &SpinBarrier::sync, &bar};
+        host_cta() = &cta;
+        for (;;) {
+            if (tid == 0) cur = next.fetch_add(1);
+            bar.wait();
+            const int c = cur;
+            if (c >= n_checks) break;
+            CheckResult r;
+            run_check3<NT>(M, odom, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info, r);
+            if (tid == 0) out(c, r);
+            bar.wait();
+        }
+        host_cta() = nullptr;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < NT; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto& t : th) t.join();
+}
 extern "C" int emul_check_batch3(int n_poses, const double* odom_meas, const double* odom_info, double s_factor, int n_loops, const int* lfrom,
                                  const int* lto, const double* lmeas, const double* linfo, int n_checks, const int* member, const int* cand,
                                  double fast_th, double slow_th, int fast_iter, int slow_iter, double noise_eps, int speculate, int early_accept,
@@ -148,6 +178,21 @@ extern "C" int emul_check_batch3(int n_poses, const double* odom_meas, const dou
     }
     CheckParams prm{fast_th, slow_th, fast_iter, slow_iter, noise_eps, 100, speculate, early_accept, g_sd_fuse};
     std::atomic<int> next{0};
+    auto emit = [&](int c, const CheckResult& r) {
+        verdict[c] = (unsigned char)r.verdict;
+        if (info) { info[c].max_chi2 = r.max_chi2; info[c].cand_chi2 = r.cand_chi2; info[c].sum_chi2 = r.sum_chi2; info[c].iterations = r.iterations;
+                    info[c].evals = r.evals; info[c].window_len = r.window_len; info[c].n_loops = r.n_loops; }
+        if (sweeps) sweeps[c] = r.n_sweeps;
+    };
+    if (g_cta > 1) {
+        auto group = [&]() { if (g_cta == 8) cta_group3<8>(n_poses, rec.data(), recs.data(), n_checks, member, cand, prm, want_info != 0, next, emit);
+                             else cta_group3<16>(n_poses, rec.data(), recs.data(), n_checks, member, cand, prm, want_info != 0, next, emit); };
+        const int groups = std::max(1, (n_threads < 1 ? 1 : n_threads) / g_cta);
+        std::vector<std::thread> th;
+        for (int t = 0; t < groups; ++t) th.emplace_back(group);
+        for (auto& t : th) t.join();
+        return 0;
+    }
     auto work = [&]() {
         const int capv = n_poses + 2;
         std::vector<double> buf((size_t)(CHAIN3_STATE + CHAIN3_SCRATCH) * capv + CHAIN3_SMALL_DOUBLES, 0.0);
