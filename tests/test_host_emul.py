@@ -1,6 +1,7 @@
 """The CUDA check's arithmetic and Dogleg control flow (ipc_b200/csrc/chain_se2.cuh is __host__ __device__) compiled for the
-CPU with one thread per check and compared with the golden fixtures: catches formula / control-flow regressions on a box
-without a GPU. The block-parallel decomposition itself is only exercised by the gpu-marked tests."""
+CPU and compared with the golden fixtures: one thread per check (formula / control-flow regressions on a box without a
+GPU) and 8 / 16 cooperating threads per check (the block-parallel decomposition; the device's warp shuffles and launch
+shapes are still only exercised by the gpu-marked tests)."""
 import shutil
 
 import numpy as np
