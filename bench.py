@@ -151,6 +151,17 @@ def run_reference(args):
                       "note": "reference needs g2o/Eigen (absent offline): CPU arm is the dependency-free oracle port, one check per thread"}))
 
 
+def traffic_capture():
+    """DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/): a different launch than the
+    timed one, so it is reported beside roofline.traffic (null), not as it."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic_capture.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
 def run_ours(args):
     os.environ.setdefault("NCCL_DEBUG", "WARN")
     # keep stdout to the ONE JSON line: libraries (NCCL prints its version) write to fd 1 from C, so park fd 1 on stderr
@@ -269,6 +280,7 @@ def run_ours(args):
                "gpu_launches": n_launch * (args.steps + args.warmup + e2e_steps + 1),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes, "kernel_ms": k_ms,
+                            "traffic_capture": traffic_capture(),
                             "note": "working set is L2-resident; the kernel is fp64-pipe / latency bound, not HBM bound (DESIGN.md)"},
                "verdict_only_early_accept": {"value": ea_value, "unit": UNIT, "verdict_bits_identical": ea_same,
                                              "note": "same verdict bits, checks stop once sum chi2 <= threshold; not the headline"},
