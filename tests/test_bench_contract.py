@@ -1,0 +1,42 @@
+"""bench.py's JSON-line contract on the arm that runs without a GPU (the CPU reference arm), and the product arm's refusal
+to run without a CUDA device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_one_contract_line():
+    r = _run("--impl", "reference", "--config", "intel", "--steps", "1", "--warmup", "0", "--cpu-seconds", "2")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                   # stdout carries the JSON line and nothing else
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    assert d["metric"] == "pairwise consistency checks/sec" and d["unit"] == "checks/s"
+    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
+    assert d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="a CUDA device is present")
+def test_product_arm_refuses_to_run_without_a_gpu():
+    r = _run("--steps", "1", "--warmup", "3", "--no-cpu")
+    assert r.returncode != 0
+    assert r.stdout.strip() == ""                            # no number is ever printed from a CPU path
+    assert "no CUDA device" in r.stderr
