@@ -80,3 +80,36 @@ def test_emulated_cta_decomposition_matches_golden(name, use_uni, nt):
     finally:
         emul.lib().emul_set_sd_fuse(2)
         emul.lib().emul_set_cta_threads(1)
+
+
+@pytest.mark.parametrize("nt", [1, 8, 16])
+def test_emulated_edge_cases_match_oracle(oracle_lib, nt):
+    """The edge cases of the GPU suite on the CPU: shortest windows (L = 2, most emulated threads own nothing), reversed loop
+    direction, touching / identical / reversed-identical / disjoint intervals (src/consensus.cpp:157-159)."""
+    import os
+    from ipc_b200 import api, synth
+    from tests.host_emul import emul
+    g0 = synth.manhattan(200, 40, seed=9, noise_scale=0.5, reverse_frac=0.5)
+    rng = np.random.default_rng(1)
+    lf = [0, 5, 10, 12, 12, 20, 150, 198, 30, 60]
+    lt = [2, 3, 12, 20, 20, 12, 10, 196, 60, 30]
+    lm = np.array([oracle_lib.compose(2, oracle_lib.inverse(2, g0.gt[a]), g0.gt[b]) for a, b in zip(lf, lt)]) + rng.normal(size=(10, 3)) * 0.05
+    g = synth.Graph(2, g0.n_poses, g0.odom_meas, g0.odom_info, np.concatenate([g0.loop_from, np.array(lf, dtype=np.int32)]),
+                    np.concatenate([g0.loop_to, np.array(lt, dtype=np.int32)]), np.concatenate([g0.loop_meas, lm]),
+                    np.concatenate([g0.loop_info, np.tile(g0.loop_info[0], (10, 1, 1))]), g0.n_true)
+    cfg = dict(s_factor=10.0, fast_reject_th=6.251, fast_reject_iter_base=50, slow_reject_th=11.345, slow_reject_iter_base=100)
+    mem, cnd = api.pair_checks(g)
+    b = g0.n_loops
+    mem = np.concatenate([mem, np.array([b + 2, b + 3, b + 4, b + 0, b + 8, b + 9, b + 7], dtype=np.int32)])
+    cnd = np.concatenate([cnd, np.array([b + 3, b + 4, b + 5, b + 7, b + 9, b + 8, b + 6], dtype=np.int32)])
+    ptr, idx = api.checks_to_csr(mem, cnd)
+    oacc, orep = oracle_lib.OracleIPC(g, cfg).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert emul.lib().emul_set_cta_threads(nt) == 0
+    try:
+        for use_uni in (1, 0):
+            acc, info, _ = emul.check_batch(g, cfg, mem, cnd, use_uni=use_uni, n_threads=max(8, 2 * nt))
+            assert np.array_equal(acc, oacc)
+            assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < 1e-4
+            assert np.array_equal(info["n_loops"], orep["n_cluster"] + 1)
+    finally:
+        emul.lib().emul_set_cta_threads(1)
