@@ -8,8 +8,9 @@ Workload at N = 1 (BASELINE.json configs[1]): Manhattan3500-shaped SE(2) graph +
 (synthetic, seed 2); one STEP = every solved check of the N_c x N_c pairwise consistency matrix in
 time order — the N_c fast checks on the diagonal plus every pair (i < j) whose intervals overlap
 (src/consensus.cpp:157-159); non-overlapping pairs need no solve and are not counted.
-For N > 1 every rank runs the same-size batch on its own M3500-shaped graph (seed 2 + 100*rank): weak
-scaling, no data-path collective except one all_gather of the packed verdict words per step.
+For N > 1 the SAME check list is dealt over the ranks by window length (longest first, round robin; every rank
+holds the whole graph): strong scaling, no data-path collective except ONE all-gather of the packed verdict words
+per step, issued behind the C ABI (ipc_check_batch_sharded_dev -> ncclAllGather).
 
 One JSON line on stdout (rank 0). `value` = checks/s with the check list resident in HBM, `e2e` = the
 same through ipc_check_batch with HOST buffers (H2D of the check list and D2H of the verdict words inside
@@ -110,6 +111,23 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
 
 
+def termination_desc(noise_exit: int) -> str:
+    if noise_exit == 1:
+        return ("same rule on both arms: Dogleg retries stop once a rejected trial's own predicted gain is <= 1e-13 * chi2 "
+                "(DESIGN.md 'Termination'); the g2o-verbatim 100-retry rule is reported beside it (g2o_full_retries)")
+    if noise_exit == 0:
+        return "g2o-verbatim: up to 100 retries per iteration (OptimizationAlgorithmDogleg), same rule on both arms"
+    return f"retry loop stops at predicted gain <= {noise_exit:g} * chi2, same rule on both arms"
+
+
+def config_dict(args, g, n_checks, total):
+    """Identical on the CUDA arm and the CPU reference arm for the same command line."""
+    return {"workload": workload_desc(args.config, g, n_checks, total), "termination": termination_desc(args.noise_exit),
+            "l2": "GPU arm: flushed between timed iterations (256 MiB memset); CPU arm: n/a",
+            "sharding": "N > 1: the ONE check list is dealt over the ranks by window length (longest first, round robin), every rank holds "
+                        "the whole graph, one all-gather of the packed verdict words per step; the CPU arm runs on rank 0's host threads"}
+
+
 def cpu_leg(g, cfg, mem, cnd, budget_s: float, threads: int, noise_exit: bool):
     """Oracle port (kind "port") on a bounded, seeded sample of the same check list."""
     from ipc_b200 import api
@@ -127,6 +145,21 @@ def cpu_leg(g, cfg, mem, cnd, budget_s: float, threads: int, noise_exit: bool):
     return n / dt, n, dt, sel, acc
 
 
+def stream_leg(g, cfg, budget_s: float):
+    """BASELINE.md row B1, the reference-native number (src/simulation.cpp:36-44,87): the sequential agreementCheck stream,
+    single-threaded oracle, on a time-ordered prefix that fits the budget."""
+    from oracle import pyoracle as po
+    orc = po.OracleIPC(g, cfg)
+    order = g.time_order()
+    t0 = time.perf_counter(); done = 0
+    for li in order:
+        orc.agreement_check(g.loop_from[li], g.loop_to[li], g.loop_meas[li], g.loop_info[li]); done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,31 +168,33 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     per_step_budget = max(2.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
     rates, n_s = [], 0
+    ne = args.noise_exit != 0
     for i in range(args.warmup + args.steps):
-        r, n_s, dt, _, _ = cpu_leg(g, cfg, mem, cnd, per_step_budget, threads, noise_exit=False)
+        r, n_s, dt, _, _ = cpu_leg(g, cfg, mem, cnd, per_step_budget, threads, noise_exit=ne)
         if i >= args.warmup:
             rates.append((n_s, dt))
     n_tot = sum(n for n, _ in rates); t_tot = sum(t for _, t in rates)
     v = n_tot / t_tot
-    sample = f"seeded random sample of ~{n_s} checks per step of the same check list (full g2o retry semantics, noise_exit off)"
+    sample = f"seeded random sample of ~{n_s} checks per step of the same check list, one check per host thread"
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+                      "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                      "config": {"workload": workload_desc(args.config, g, len(cnd), total), "l2": "n/a (CPU)"},
+                      "config": config_dict(args, g, len(cnd), total),
                       "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "note": "reference needs g2o/Eigen (absent offline): CPU arm is the dependency-free oracle port, one check per thread"}))
 
 
 def traffic_capture():
-    """DRAM bytes of the dominant kernel from the committed ncu --set full capture (profiles/): a different launch than the
-    timed one, so it is reported beside roofline.traffic (null), not as it."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic_capture.json")
-    try:
-        with open(path) as f:
-            return json.load(f)
-    except (OSError, ValueError):
-        return None
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this command (profiles/)."""
+    for name in ("r02_traffic_capture.json", "r01_traffic_capture.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(path) as f:
+                return json.load(f)
+        except (OSError, ValueError):
+            continue
+    return None
 
 
 def run_ours(args):
@@ -170,36 +205,48 @@ def run_ours(args):
     os.dup2(2, 1)
     import torch
     import torch.distributed as dist
-    from ipc_b200 import api
+    from ipc_b200 import api, sharding
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE is {world}: launch N > 1 with torch.distributed.run --nproc-per-node N")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    g, cfg, mem, cnd, total = build_workload(args.config, 100 * rank, args.checks)
-    n = len(cnd)
+    # every rank builds the SAME graph and check list; the list is dealt by window length (the north-star split)
+    g, cfg, mem, cnd, total = build_workload(args.config, 0, args.checks)
+    n_total = len(cnd)
+    cost = sharding.window_lengths(g, mem, cnd)
+    parts, wpr = sharding.shard_plan(cost, world)
+    mine = parts[rank]
+    n = len(mine)
     ipc = api.IPC.from_graph(g, cfg, device=local)
     ipc.set_option("noise_exit", args.noise_exit)
+    if world > 1:
+        ipc.comm_init(dist)
     dev = torch.device("cuda", local)
-    mem_d = torch.from_numpy(mem).to(dev); cnd_d = torch.from_numpy(cnd).to(dev)
-    words = (n + 31) // 32
-    bits_d = torch.zeros(words, dtype=torch.int32, device=dev)
-    gathered = [torch.zeros_like(bits_d) for _ in range(world)] if world > 1 else None
+    mem_l, cnd_l = np.ascontiguousarray(mem[mine]), np.ascontiguousarray(cnd[mine])
+    mem_d = torch.from_numpy(mem_l).to(dev); cnd_d = torch.from_numpy(cnd_l).to(dev)
+    bits_all_d = torch.zeros(world * wpr, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def step():
-        ipc.check_batch_dev(n, mem_d.data_ptr(), cnd_d.data_ptr(), bits_d.data_ptr(), None, stream.cuda_stream)
-        if world > 1:
-            dist.all_gather(gathered, bits_d)
+    def step():     # kernels of this rank's shard + the ONE all-gather of verdict words, all on `stream`, behind the C ABI
+        ipc.check_batch_sharded_dev(n, mem_d.data_ptr(), cnd_d.data_ptr(), wpr, bits_all_d.data_ptr(), stream.cuda_stream)
 
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         flush.zero_(); step()
@@ -217,37 +264,53 @@ def run_ours(args):
         sync_all()
         t_wall = time.perf_counter() - t_wall
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
-    tot_ms = float(tot_ms.item())
+    tot_ms = max_over_ranks(sum(step_ms))
     sum_L, sum_K, n_launch = ipc.last_batch_stats()
-    value = world * n * args.steps / (tot_ms * 1e-3)
+    value = n_total * args.steps / (tot_ms * 1e-3)
+    bits_dev = bits_all_d.cpu().numpy().view(np.uint32).reshape(world, wpr).copy()
+    n_batches = args.warmup + args.steps
 
     # ---- extra: verdict-only mode with the rigorous early accept (sum chi2 <= th can no longer be rejected) -------
-    bits_full = bits_d.clone()
     ipc.set_option("early_accept", 1)
     flush.zero_(); step(); sync_all()
     ea0, ea1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ea_steps = max(1, min(args.steps, 2))
-    ea_ms = 0.0
-    for _ in range(ea_steps):
-        flush.zero_(); ea0.record(stream); step(); ea1.record(stream); torch.cuda.synchronize(); ea_ms += ea0.elapsed_time(ea1)
-    ea_t = torch.tensor([ea_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ea_t, op=dist.ReduceOp.MAX)
-    ea_value = world * n * ea_steps / (float(ea_t.item()) * 1e-3)
-    ea_same = bool((bits_full == bits_d).all().item())
+    flush.zero_(); ea0.record(stream); step(); ea1.record(stream); torch.cuda.synchronize()
+    ea_value = n_total / (max_over_ranks(ea0.elapsed_time(ea1)) * 1e-3)
+    ea_same = bool((bits_all_d.cpu().numpy().view(np.uint32).reshape(world, wpr) == bits_dev).all())
     ipc.set_option("early_accept", 0)
+    n_batches += 2
 
-    # ---- end-to-end through the host-buffer C ABI call --------------------------------------------
-    mem_h = torch.from_numpy(mem).pin_memory(); cnd_h = torch.from_numpy(cnd).pin_memory()
-    bits_h = torch.zeros(words, dtype=torch.int32).pin_memory()
+    # ---- extra: the g2o-verbatim retry rule (noise_exit = 0) on a seeded sample of this rank's shard ---------------
+    full = None
+    if args.noise_exit != 0 and not args.no_full_retries:
+        ns = min(n, max(1000, 160000 // world))
+        sel_l = np.sort(np.random.default_rng(7).choice(n, ns, replace=False))
+        sm_d, sc_d = mem_d[torch.from_numpy(sel_l).to(dev)].contiguous(), cnd_d[torch.from_numpy(sel_l).to(dev)].contiguous()
+        sb_d = torch.zeros(world * wpr, dtype=torch.int32, device=dev)
+
+        def sample_step():
+            ipc.check_batch_sharded_dev(ns, sm_d.data_ptr(), sc_d.data_ptr(), wpr, sb_d.data_ptr(), stream.cuda_stream)
+        vals = {}
+        for ne in (args.noise_exit, 0):
+            ipc.set_option("noise_exit", ne)
+            sample_step(); sync_all()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            flush.zero_(); f0.record(stream); sample_step(); f1.record(stream); torch.cuda.synchronize()
+            vals[ne] = (world * ns / (max_over_ranks(f0.elapsed_time(f1)) * 1e-3), sb_d.cpu().numpy().copy())
+            n_batches += 2
+        ipc.set_option("noise_exit", args.noise_exit)
+        full = {"gpu_value": vals[0][0], "gpu_value_default_rule_same_sample": vals[args.noise_exit][0], "unit": UNIT,
+                "sample": f"seeded sample of {ns} checks per GPU, 1 warm-up + 1 timed batch",
+                "verdict_bits_identical_to_default_rule": bool((vals[0][1] == vals[args.noise_exit][1]).all())}
+
+    # ---- end-to-end through the host-buffer C ABI call (H2D of the shard, kernels, all-gather, D2H of every word) -------
+    mem_h = torch.from_numpy(mem_l).pin_memory(); cnd_h = torch.from_numpy(cnd_l).pin_memory()
+    bits_h = torch.zeros(world * wpr, dtype=torch.int32).pin_memory()
     L = api.lib()
     import ctypes as C
 
     def e2e_step():
-        rc = L.ipc_check_batch(ipc.handle, n, C.c_void_p(mem_h.data_ptr()), C.c_void_p(cnd_h.data_ptr()), C.c_void_p(bits_h.data_ptr()), None)
+        rc = L.ipc_check_batch_sharded(ipc.handle, n, C.c_void_p(mem_h.data_ptr()), C.c_void_p(cnd_h.data_ptr()), wpr, C.c_void_p(bits_h.data_ptr()))
         if rc != 0:
             raise RuntimeError(L.ipc_last_error().decode())
     e2e_steps = max(1, min(args.steps, 3))
@@ -256,12 +319,12 @@ def run_ours(args):
     for _ in range(e2e_steps):
         e2e_step()
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(t_e2e.item())
-    # the e2e verdict words must equal the device-resident ones
-    same = bool((bits_h.to(dev) == bits_d).all().item())
+    e2e_value = n_total * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+    n_batches += e2e_steps + 1
+    bits_e2e = bits_h.numpy().view(np.uint32).reshape(world, wpr)
+    same = bool((bits_e2e == bits_dev).all())          # the e2e verdict words must equal the device-resident ones
+    verdict_all = sharding.decode_gathered(bits_e2e, parts, n_total)
+    _, _, n_coll = ipc.comm_info()
 
     out = None
     if rank == 0:
@@ -270,28 +333,40 @@ def run_ours(args):
         k_ms = float(np.mean(kern_ms)) if kern_ms else float(np.mean(step_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+               "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
-               "config": {"workload": workload_desc(args.config, g, n, total), "checks_per_gpu_per_step": n, "sum_window_len": sum_L,
-                          "sum_loops": sum_K, "l2": "flushed between timed iterations (256 MiB memset)", "noise_exit": args.noise_exit,
-                          "parallelism": f"{world} x independent check shards" + (" + all_gather of verdict words" if world > 1 else "")},
-               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": 4 * words,
-                       "matches_device_resident": same},
-               "gpu_launches": n_launch * (args.steps + args.warmup + e2e_steps + 1),
+               "config": config_dict(args, g, n_total, total),
+               "shard": {"checks_total": n_total, "checks_rank0": n, "words_per_rank": wpr, "sum_window_len_rank0": sum_L, "sum_loops_rank0": sum_K,
+                         "collectives_per_step": (1 if world > 1 else 0), "nccl_all_gathers_issued_rank0": n_coll,
+                         "collective_bytes_per_step": 4 * wpr * world if world > 1 else 0},
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * n_total, "d2h_bytes_per_step": 4 * wpr * world * world,
+                       "matches_device_resident": same,
+                       "note": "ipc_check_batch_sharded with pinned host buffers: H2D of every rank's shard, kernels, all-gather, D2H of all verdict words on every rank"},
+               "gpu_launches": n_launch * n_batches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes, "kernel_ms": k_ms,
+                            "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes, "kernel_ms": k_ms, "scope": "rank 0's shard on one GPU",
                             "traffic_capture": traffic_capture(),
                             "note": "working set is L2-resident; the kernel is fp64-pipe / latency bound, not HBM bound (DESIGN.md)"},
                "verdict_only_early_accept": {"value": ea_value, "unit": UNIT, "verdict_bits_identical": ea_same,
                                              "note": "same verdict bits, checks stop once sum chi2 <= threshold; not the headline"},
                "clocks": clk.summary(), "wall_s_timed_region": t_wall}
+        if full is not None:
+            out["g2o_full_retries"] = full
         if not args.no_cpu:
-            v, ns, dt, sel, oacc = cpu_leg(g, cfg, mem, cnd, args.cpu_seconds, os.cpu_count() or 1, noise_exit=False)
-            bits = bits_h.numpy().view(np.uint32)
-            gacc = ((bits[sel >> 5] >> (sel & 31).astype(np.uint32)) & 1).astype(bool)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                                   "sample": f"seeded random sample of {ns} checks of the same list, {dt:.1f} s, one check per thread",
-                                   "verdict_mismatches_vs_gpu": int((gacc != oacc).sum())}
+            cores = os.cpu_count() or 1
+            ne = args.noise_exit != 0
+            v, ns, dt, sel, oacc = cpu_leg(g, cfg, mem, cnd, args.cpu_seconds, cores, noise_exit=ne)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"seeded random sample of {ns} checks of the same list, {dt:.1f} s, one check per thread, same termination rule as the GPU arm",
+                                   "verdict_mismatches_vs_gpu": int((verdict_all[sel] != oacc).sum())}
+            if full is not None:
+                v0, ns0, dt0, sel0, oacc0 = cpu_leg(g, cfg, mem, cnd, max(3.0, args.cpu_seconds / 3), cores, noise_exit=False)
+                full.update({"cpu_value": v0, "cpu_sample": f"{ns0} checks, {dt0:.1f} s, {cores} threads",
+                             "verdict_mismatches_vs_gpu": int((verdict_all[sel0] != oacc0).sum())})
+            if args.stream_seconds > 0:
+                sv, sn, sdt = stream_leg(g, cfg, args.stream_seconds)
+                out["stream_cpu_B1"] = {"value": sv, "unit": "agreementCheck calls/s", "cores": 1, "kind": "port",
+                                        "sample": f"first {sn} time-ordered candidates of the sequential stream, {sdt:.1f} s (BASELINE.md row B1)"}
         sys.stdout.flush()
         os.dup2(_saved_fd1, 1)
         print(json.dumps(out), flush=True)
@@ -313,6 +388,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
+    ap.add_argument("--no-full-retries", action="store_true", help="skip the g2o-verbatim (noise_exit = 0) side measurement")
+    ap.add_argument("--stream-seconds", type=float, default=0.0, help="also time the single-threaded sequential stream (oracle) for this long")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)

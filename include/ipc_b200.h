@@ -102,7 +102,10 @@ int ipc_set_candidates(ipc_handle* h, int n_loops, const int* from, const int* t
 int ipc_check_batch(ipc_handle* h, int n_checks, const int* member, const int* cand,
                     uint32_t* out_bits, ipc_check_info* out_info);
 /* Device-resident variant: all pointers are device pointers; kernels are enqueued on `stream`
- * (a cudaStream_t, may be NULL) and the call does not synchronise. */
+ * (a cudaStream_t, may be NULL) and the call does not synchronise. ONE batch may be in flight per handle: the
+ * work lists, verdict bytes and per-CTA scratch belong to the handle, so the caller must not enqueue a second
+ * batch (on any stream) before the previous one has finished, and member/cand must index the candidate table
+ * (not checked here — the host-buffer entry point validates). */
 int ipc_check_batch_dev(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev,
                         uint32_t* out_bits_dev, ipc_check_info* out_info_dev, void* stream);
 /* Plan for ipc_check_batch_dev: the call sorts checks by window length into launch buckets on the
@@ -119,6 +122,32 @@ int ipc_last_kernel_ms(ipc_handle* h, float* ms);
  * rows_bits: [n_loops][ceil(n_loops/32)] words, symmetric. order_out (may be NULL): the time order
  * used, n_loops ints. n_solved (may be NULL): number of checks actually solved. */
 int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved);
+
+/* ---- multi-GPU: the check batch sharded over the GPUs of one box ----------------------------------
+ * The reference is single-process (its only parallelism is independent OS processes,
+ * bash/ipc_experiments_2D.sh:34-37); fast and pair checks are independent units, so a batch is dealt across
+ * one handle per GPU (one process or thread each) and the ONLY exchange is one NCCL all-gather of the packed
+ * verdict words. NCCL is bound at run time (dlopen of libnccl.so.2); single-GPU use never
+ * touches it. */
+#define IPC_COMM_ID_BYTES 128
+/* Rank 0 creates the rendezvous id (an ncclUniqueId) and ships it to the other ranks by any means. */
+int ipc_comm_unique_id(unsigned char id[IPC_COMM_ID_BYTES]);
+/* Collective over the `world` handles (ncclCommInitRank on the handle's device). */
+int ipc_comm_init(ipc_handle* h, const unsigned char id[IPC_COMM_ID_BYTES], int rank, int world);
+/* rank / world of the handle (0 / 1 without a communicator) and the number of all-gathers issued so far. Any may be NULL. */
+int ipc_comm_info(ipc_handle* h, int* rank, int* world, int64_t* n_collectives);
+/* Sharded batch: this rank solves ITS n_local checks, then one in-place all-gather makes out_bits_all
+ * [world][words_per_rank] identical on every rank: bit i%32 of word i/32 of row r = verdict of rank r's check i.
+ * words_per_rank >= ceil(n_local/32) must be the same on every rank (pad to the largest shard). Without a
+ * communicator the call is the single-rank batch (world = 1). Host buffers, end to end: */
+int ipc_check_batch_sharded(ipc_handle* h, int n_local, const int* member, const int* cand, int words_per_rank,
+                            uint32_t* out_bits_all);
+/* ... and device-resident, enqueued on `stream` (kernels and the all-gather), no synchronisation. */
+int ipc_check_batch_sharded_dev(ipc_handle* h, int n_local, const int* member_dev, const int* cand_dev,
+                                int words_per_rank, uint32_t* out_bits_all_dev, void* stream);
+/* ipc_consistency_matrix with the solved checks dealt round robin over the communicator's ranks (check c of the
+ * time-ordered list belongs to rank c % world) and one all-gather; every rank receives the same rows. */
+int ipc_consistency_matrix_sharded(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved);
 
 /* Greedy consensus-set growth over a consistency matrix (row-AND + popcount): candidate k (in the
  * matrix's order) joins iff it is consistent with every current member. in_set: n_loops bytes. */

@@ -22,7 +22,9 @@ _LIB = None
 # every symbol include/ipc_b200.h declares
 SYMBOLS = ["ipc_last_error", "ipc_device_count", "ipc_create", "ipc_destroy", "ipc_agreement_check", "ipc_remove_edge",
            "ipc_add_edge", "ipc_consensus_size", "ipc_get_consensus", "ipc_get_poses", "ipc_final_optimize", "ipc_set_candidates", "ipc_check_batch",
-           "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_last_kernel_ms", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option"]
+           "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_last_kernel_ms", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option",
+           "ipc_comm_unique_id", "ipc_comm_init", "ipc_comm_info", "ipc_check_batch_sharded", "ipc_check_batch_sharded_dev",
+           "ipc_consistency_matrix_sharded"]
 
 
 class IpcError(RuntimeError):
@@ -71,6 +73,12 @@ def lib():
         L.ipc_consistency_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.ipc_greedy_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ipc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.ipc_comm_unique_id.argtypes = [C.c_void_p]
+        L.ipc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ipc_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        L.ipc_check_batch_sharded.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ipc_check_batch_sharded_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ipc_consistency_matrix_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         _LIB = L
     return _LIB
 
@@ -202,14 +210,49 @@ class IPC:
         _chk(lib().ipc_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
-    def consistency_matrix(self):
+    def consistency_matrix(self, sharded: bool = False):
+        """Rows of the N_c x N_c consistency matrix (time order). sharded=True deals the solved checks over the ranks of the
+        handle's communicator (comm_init) and all-gathers the verdict words: every rank gets the same rows."""
         n = self.n_candidates
         words = (n + 31) // 32
         rows = np.zeros((n, words), dtype=np.uint32)
         order = np.zeros(n, dtype=np.int32)
         solved = C.c_int64(0)
-        _chk(lib().ipc_consistency_matrix(self._h, _p(rows), _p(order), C.byref(solved)))
+        fn = lib().ipc_consistency_matrix_sharded if sharded else lib().ipc_consistency_matrix
+        _chk(fn(self._h, _p(rows), _p(order), C.byref(solved)))
         return rows, order, solved.value
+
+    # ---- multi-GPU: one IPC object per GPU / process, NCCL all-gather behind the C ABI -----------
+    def comm_init(self, dist=None, rank: int = 0, world: int = 1, uid: bytes | None = None):
+        """Create the handle's NCCL communicator. With a torch.distributed module the id made on rank 0 travels by
+        broadcast_object_list (any backend); otherwise pass the 128-byte `uid` from comm_unique_id() yourself."""
+        if dist is not None:
+            rank, world = dist.get_rank(), dist.get_world_size()
+            box = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            uid = box[0]
+        if uid is None or len(uid) != 128:
+            raise IpcError("comm_init needs a torch.distributed module or a 128-byte id")
+        buf = (C.c_ubyte * 128).from_buffer_copy(uid)
+        _chk(lib().ipc_comm_init(self._h, buf, int(rank), int(world)))
+
+    def comm_info(self):
+        r, w, n = C.c_int(0), C.c_int(1), C.c_int64(0)
+        _chk(lib().ipc_comm_info(self._h, C.byref(r), C.byref(w), C.byref(n)))
+        return r.value, w.value, n.value
+
+    def check_batch_sharded(self, member, cand, words_per_rank: int, out=None):
+        """This rank's shard (host buffers) + ONE all-gather: returns uint32 [world, words_per_rank], same on every rank."""
+        mb, cd = _i32(member), _i32(cand)
+        _, world, _ = self.comm_info()
+        if out is None:
+            out = np.zeros((world, words_per_rank), dtype=np.uint32)
+        _chk(lib().ipc_check_batch_sharded(self._h, cd.shape[0], _p(mb), _p(cd), int(words_per_rank), _p(out)))
+        return out
+
+    def check_batch_sharded_dev(self, n_local, member_ptr, cand_ptr, words_per_rank, bits_all_ptr, stream=None):
+        _chk(lib().ipc_check_batch_sharded_dev(self._h, int(n_local), C.c_void_p(member_ptr), C.c_void_p(cand_ptr), int(words_per_rank),
+                                               C.c_void_p(bits_all_ptr), C.c_void_p(stream) if stream else None))
 
     def greedy_consensus(self, rows_bits) -> np.ndarray:
         rows = np.ascontiguousarray(rows_bits, dtype=np.uint32)
@@ -217,6 +260,12 @@ class IPC:
         out = np.zeros(n, dtype=np.uint8)
         _chk(lib().ipc_greedy_consensus(self._h, _p(rows), n, _p(out)))
         return out.astype(bool)
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_ubyte * 128)()
+    _chk(lib().ipc_comm_unique_id(buf))
+    return bytes(buf)
 
 
 def pair_checks(graph, order=None):

@@ -1,0 +1,64 @@
+// handle.hpp — the handle behind include/ipc_b200.h: IPC<EDGE,VERTEX> state of
+// /root/reference/include/ipc/consensus.hpp:23-32 kept as flat arrays, with the graph resident in HBM.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "launch_common.hpp"
+#include "host_state.hpp"
+#include "cluster_se2.cuh"
+#include "cluster_se3.cuh"
+#include "comm.hpp"
+#include <cusolverDn.h>
+
+using namespace ipcb;
+
+struct ipc_handle {
+    int dim = 2, d = 3, mw = 3;
+    int n = 0, n_pad = 0;
+    int device = 0;
+    int n_sm = 148;
+    ipc_config cfg{};
+    double noise_eps = 1e-13;         // DESIGN.md "Termination"; 0 = replay every retry like g2o
+    int max_tries = 100;
+    int speculate = 1;
+    int early_accept = 0;
+    int use_uniform = 1;              // allow the uniform-information kernels when the graph qualifies
+    int sd_fuse = 2;                  // see CheckParams::sd_fuse
+    Bucket buckets[NB];               // launch buckets (tunable: options bucket<i>_cap / bucket<i>_nt)
+    HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
+    // device graph
+    double* d_odom9 = nullptr;        // AoS odometry records, general (9 doubles / edge)
+    double* d_odom49 = nullptr;       // SE(3) AoS odometry records (Z^-1, Omega, Omega^-1: 49 doubles / edge)
+    double* d_odom3 = nullptr;        // AoS odometry records, uniform isotropic information (3 doubles / edge); null if not applicable
+    void* d_loops = nullptr;  int n_loops = 0;
+    std::vector<int> h_lfrom, h_lto;  // host copy of candidate endpoints
+    std::vector<double> h_lmeas, h_linfo;
+    // batch work buffers (grown on demand)
+    int cap_checks = 0;
+    int *d_member = nullptr, *d_cand = nullptr, *d_work = nullptr, *d_counts = nullptr, *d_bucket_cap = nullptr;
+    unsigned char* d_verdict = nullptr;
+    uint32_t* d_bits = nullptr;
+    ipc_check_info* d_info = nullptr;
+    unsigned long long* d_stats = nullptr;
+    double* d_scratch = nullptr; size_t scratch_doubles = 0;   // per-CTA scratch, shared by the (serialised) bucket launches
+    int last_launches = 0;
+    cudaStream_t stream = nullptr;
+    // ---- sequential stream (stateful agreementCheck): global pose state + cluster-solve work buffers
+    double* d_pose = nullptr;         // AoS[5] x n: x y theta cos sin — the vertex estimates of the IPC object
+    double* d_odom9_raw = nullptr;    // odometry records with the information as given (final optimisation only)
+    const double* cl_odom = nullptr;  // records the cluster kernels read: d_odom9, or d_odom9_raw during ipc_final_optimize
+    cusolverDnHandle_t solver = nullptr;
+    int cl_Lcap = 0, cl_Kcap = 0, cl_work_n = 0;
+    ClBuffers clB[2] = {};
+    double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_work = nullptr;
+    int* cl_info = nullptr;
+    void* cl_loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the current cluster
+    double* cl_stage = nullptr;       // SE(3) dead-reckoning staging (CL_NT poses)
+    double* d_odom49_raw = nullptr;   // SE(3) records with the information as given (final optimisation)
+    double* cl_hres = nullptr;        // pinned
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
+    bool ev_valid = false;
+    uint32_t* d_gather = nullptr; size_t gather_words = 0;   // [world][words_per_rank] verdict words of a sharded batch
+    Comm* comm = nullptr;             // multi-GPU (comm.hpp): NCCL communicator created by ipc_comm_init, one handle per GPU
+};

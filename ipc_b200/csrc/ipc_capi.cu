@@ -8,14 +8,8 @@
 #include <string>
 #include <vector>
 
-#include "launch_common.hpp"
-#include "host_state.hpp"
+#include "handle.hpp"
 #include "matrix.cuh"
-#include "cluster_se2.cuh"
-#include "cluster_se3.cuh"
-#include <cusolverDn.h>
-
-using namespace ipcb;
 
 namespace ipcb {
 thread_local std::string g_err;
@@ -62,6 +56,18 @@ __global__ void pack_bits(const unsigned char* __restrict__ verdict, int n, uint
     if ((threadIdx.x & 31) == 0 && c < n) bits[c >> 5] = w;
 }
 
+// sharded batches: rank r owns the checks r, r + world, ... of a list
+__global__ void shard_take(const int* __restrict__ member, const int* __restrict__ cand, int rank, int world, int n_local, int* __restrict__ lm,
+                           int* __restrict__ lc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_local) { const size_t c = (size_t)rank + (size_t)i * world; lm[i] = member[c]; lc[i] = cand[c]; }
+}
+// gathered words [world][wpr] -> verdict byte per check of the whole list
+__global__ void shard_spread(const uint32_t* __restrict__ gathered, size_t wpr, int world, int n_checks, unsigned char* __restrict__ verdict) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n_checks) { const int r = c % world, i = c / world; verdict[c] = (gathered[(size_t)r * wpr + (i >> 5)] >> (i & 31)) & 1u; }
+}
+
 }  // namespace ipcb
 
 // ------------------------------------------------------------------------------------------------
@@ -82,57 +88,9 @@ const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
 
 }  // namespace
 
-struct ipc_handle;
 namespace { int size_scratch(ipc_handle* h); }
 extern "C" { namespace { int cl_ensure(ipc_handle* h, int L, int K); } }
 
-struct ipc_handle {
-    int dim = 2, d = 3, mw = 3;
-    int n = 0, n_pad = 0;
-    int device = 0;
-    int n_sm = 148;
-    ipc_config cfg{};
-    double noise_eps = 1e-13;         // DESIGN.md "Termination"; 0 = replay every retry like g2o
-    int max_tries = 100;
-    int speculate = 1;
-    int early_accept = 0;
-    int use_uniform = 1;              // allow the uniform-information kernels when the graph qualifies
-    int sd_fuse = 2;                  // see CheckParams::sd_fuse
-    Bucket buckets[NB];               // launch buckets (tunable: options bucket<i>_cap / bucket<i>_nt)
-    HostState hs;                     // host mirror: odometry, consensus set (integer logic of consensus.cpp)
-    // device graph
-    double* d_odom9 = nullptr;        // AoS odometry records, general (9 doubles / edge)
-    double* d_odom49 = nullptr;       // SE(3) AoS odometry records (Z^-1, Omega, Omega^-1: 49 doubles / edge)
-    double* d_odom3 = nullptr;        // AoS odometry records, uniform isotropic information (3 doubles / edge); null if not applicable
-    void* d_loops = nullptr;  int n_loops = 0;
-    std::vector<int> h_lfrom, h_lto;  // host copy of candidate endpoints
-    std::vector<double> h_lmeas, h_linfo;
-    // batch work buffers (grown on demand)
-    int cap_checks = 0;
-    int *d_member = nullptr, *d_cand = nullptr, *d_work = nullptr, *d_counts = nullptr, *d_bucket_cap = nullptr;
-    unsigned char* d_verdict = nullptr;
-    uint32_t* d_bits = nullptr;
-    ipc_check_info* d_info = nullptr;
-    unsigned long long* d_stats = nullptr;
-    double* d_scratch = nullptr; size_t scratch_doubles = 0;   // per-CTA scratch, shared by the (serialised) bucket launches
-    int last_launches = 0;
-    cudaStream_t stream = nullptr;
-    // ---- sequential stream (stateful agreementCheck): global pose state + cluster-solve work buffers
-    double* d_pose = nullptr;         // AoS[5] x n: x y theta cos sin — the vertex estimates of the IPC object
-    double* d_odom9_raw = nullptr;    // odometry records with the information as given (final optimisation only)
-    const double* cl_odom = nullptr;  // records the cluster kernels read: d_odom9, or d_odom9_raw during ipc_final_optimize
-    cusolverDnHandle_t solver = nullptr;
-    int cl_Lcap = 0, cl_Kcap = 0, cl_work_n = 0;
-    ClBuffers clB[2] = {};
-    double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_work = nullptr;
-    int* cl_info = nullptr;
-    void* cl_loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the current cluster
-    double* cl_stage = nullptr;       // SE(3) dead-reckoning staging (CL_NT poses)
-    double* d_odom49_raw = nullptr;   // SE(3) records with the information as given (final optimisation)
-    double* cl_hres = nullptr;        // pinned
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
-    bool ev_valid = false;
-};
 
 namespace {
 
@@ -249,17 +207,18 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     if (device < 0 || device >= ndev) return fail(IPC_ERR_ARG, "bad device ordinal");
     CUDA_TRY(cudaSetDevice(device));
     ipc_handle* h = new ipc_handle();
+    struct Guard { ipc_handle* h; ~Guard() { if (h) ipc_destroy(h); } } guard{h};     // any early return below frees the handle and its buffers
     h->dim = dim; h->d = dim == 2 ? 3 : 6; h->mw = dim == 2 ? 3 : 7;
     h->n = n_poses; h->n_pad = (n_poses + 3) & ~1; h->device = device; h->cfg = *cfg;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     h->n_sm = prop.multiProcessorCount;
     std::string err;
-    if (!h->hs.init(dim, n_poses, odom_meas, odom_info, cfg->s_factor, err)) { delete h; return fail(IPC_ERR_ARG, err); }
+    if (!h->hs.init(dim, n_poses, odom_meas, odom_info, cfg->s_factor, err)) return fail(IPC_ERR_ARG, err);
     // device odometry records
     std::vector<double> rec;
     if (dim == 3) {
-        if (!h->hs.build_odom_aos3(h->n_pad, rec)) { delete h; return fail(IPC_ERR_ARG, "odometry edge with a zero quaternion or a singular information matrix"); }
+        if (!h->hs.build_odom_aos3(h->n_pad, rec)) { return fail(IPC_ERR_ARG, "odometry edge with a zero quaternion or a singular information matrix"); }
         CUDA_TRY(cudaMalloc(&h->d_odom49, rec.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(h->d_odom49, rec.data(), rec.size() * sizeof(double), cudaMemcpyHostToDevice));
     } else {
@@ -307,6 +266,7 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     }
     CUDA_TRY(cudaEventCreate(&h->ev_k0));
     CUDA_TRY(cudaEventCreate(&h->ev_k1));
+    guard.h = nullptr;
     *out = h;
     return IPC_OK;
 }
@@ -315,10 +275,11 @@ void ipc_destroy(ipc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_odom49); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
-    cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch);
+    cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch); cudaFree(h->d_gather);
     cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
     cudaFree(h->cl_info); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
     for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
+    delete h->comm;
     if (h->cl_hres) cudaFreeHost(h->cl_hres);
     if (h->solver) cusolverDnDestroy(h->solver);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -763,10 +724,16 @@ int ipc_get_poses(ipc_handle* h, double* out) {
     return IPC_OK;
 }
 
-int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved) {
+namespace {
+// Pairwise consistency matrix. With a communicator (ipc_comm_init) the solved checks are dealt round robin over the ranks
+// (check c belongs to rank c % world: neighbours in the list have similar windows, so the deal is cost balanced), every rank
+// solves its shard, ONE all-gather of the packed verdict words follows, and every rank assembles the same rows.
+int consistency_matrix_impl(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved, bool sharded) {
     if (!h || !rows_bits) return fail(IPC_ERR_ARG, "null argument");
     if (!h->d_loops || h->n_loops <= 0) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");
+    if (sharded && !h->comm) return fail(IPC_ERR_STATE, "no communicator: call ipc_comm_init first");
     CUDA_TRY(cudaSetDevice(h->device));
+    const int world = sharded ? h->comm->world() : 1, rank = sharded ? h->comm->rank() : 0;
     const int n = h->n_loops, words = (n + 31) / 32;
     // candidate order of src/simulation.cpp:26 (cmpTime), stable over file order
     std::vector<int> order(n), lo(n), hi(n);
@@ -775,10 +742,11 @@ int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, i
     for (int i = 0; i < n; ++i) { lo[i] = std::min(h->h_lfrom[order[i]], h->h_lto[order[i]]); hi[i] = std::max(h->h_lfrom[order[i]], h->h_lto[order[i]]); }
     cudaStream_t st = h->stream;
     int *d_lo = nullptr, *d_hi = nullptr, *d_order = nullptr, *d_cnt = nullptr, *d_rowptr = nullptr, *d_total = nullptr;
-    int *d_member = nullptr, *d_cand = nullptr, *d_pi = nullptr, *d_pj = nullptr, *d_work = nullptr;
-    unsigned char* d_verdict = nullptr; uint32_t* d_rows = nullptr;
+    int *d_member = nullptr, *d_cand = nullptr, *d_pi = nullptr, *d_pj = nullptr, *d_work = nullptr, *d_lmember = nullptr, *d_lcand = nullptr;
+    unsigned char *d_verdict = nullptr, *d_lverdict = nullptr; uint32_t *d_rows = nullptr, *d_gather = nullptr;
     auto cleanup = [&]() { cudaFree(d_lo); cudaFree(d_hi); cudaFree(d_order); cudaFree(d_cnt); cudaFree(d_rowptr); cudaFree(d_total); cudaFree(d_member);
-                           cudaFree(d_cand); cudaFree(d_pi); cudaFree(d_pj); cudaFree(d_work); cudaFree(d_verdict); cudaFree(d_rows); };
+                           cudaFree(d_cand); cudaFree(d_pi); cudaFree(d_pj); cudaFree(d_work); cudaFree(d_verdict); cudaFree(d_rows);
+                           cudaFree(d_lmember); cudaFree(d_lcand); cudaFree(d_lverdict); cudaFree(d_gather); };
 #define MTRY(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { cleanup(); return fail(IPC_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(_e)); } } while (0)
     MTRY(cudaMalloc(&d_lo, sizeof(int) * n)); MTRY(cudaMalloc(&d_hi, sizeof(int) * n)); MTRY(cudaMalloc(&d_order, sizeof(int) * n));
     MTRY(cudaMalloc(&d_cnt, sizeof(int) * n)); MTRY(cudaMalloc(&d_rowptr, sizeof(int) * n)); MTRY(cudaMalloc(&d_total, sizeof(int)));
@@ -793,16 +761,35 @@ int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, i
     const int n_checks = total;           // n diagonal checks + overlapping pairs
     MTRY(cudaMalloc(&d_member, sizeof(int) * n_checks)); MTRY(cudaMalloc(&d_cand, sizeof(int) * n_checks));
     MTRY(cudaMalloc(&d_pi, sizeof(int) * n_checks)); MTRY(cudaMalloc(&d_pj, sizeof(int) * n_checks));
-    MTRY(cudaMalloc(&d_work, sizeof(int) * (size_t)n_checks * NB)); MTRY(cudaMalloc(&d_verdict, n_checks));
+    MTRY(cudaMalloc(&d_verdict, n_checks));
     MTRY(cudaMalloc(&d_rows, sizeof(uint32_t) * (size_t)n * words));
     overlap_fill<<<n, 256, 0, st>>>(d_lo, d_hi, d_order, n, d_rowptr, d_member, d_cand, d_pi, d_pj);
     MTRY(cudaGetLastError());
-    // only verdict bits leave this call: the rigorous early accept (sum chi2 <= th can no longer be rejected) applies
-    const int saved_ea = h->early_accept;
-    h->early_accept = 1;
-    int rc = enqueue_batch(h, n_checks, d_member, d_cand, d_work, n_checks, d_verdict, nullptr, nullptr, st);
-    h->early_accept = saved_ea;
-    if (rc != IPC_OK) { cleanup(); return rc; }
+    int rc = IPC_OK;
+    if (world == 1) {
+        MTRY(cudaMalloc(&d_work, sizeof(int) * (size_t)n_checks * NB));
+        rc = enqueue_batch(h, n_checks, d_member, d_cand, d_work, n_checks, d_verdict, nullptr, nullptr, st);
+        if (rc != IPC_OK) { cleanup(); return rc; }
+    } else {
+        const int n_local = (n_checks - rank + world - 1) / world;             // checks rank, rank + world, ...
+        const int per = (n_checks + world - 1) / world;                         // the largest shard
+        const size_t wpr = ((size_t)per + 31) / 32;                             // words per rank, equal on every rank
+        MTRY(cudaMalloc(&d_lmember, sizeof(int) * std::max(n_local, 1))); MTRY(cudaMalloc(&d_lcand, sizeof(int) * std::max(n_local, 1)));
+        MTRY(cudaMalloc(&d_lverdict, std::max(n_local, 1))); MTRY(cudaMalloc(&d_work, sizeof(int) * (size_t)std::max(n_local, 1) * NB));
+        MTRY(cudaMalloc(&d_gather, sizeof(uint32_t) * wpr * world));
+        MTRY(cudaMemsetAsync(d_gather + (size_t)rank * wpr, 0, sizeof(uint32_t) * wpr, st));
+        if (n_local > 0) {
+            shard_take<<<(n_local + 255) / 256, 256, 0, st>>>(d_member, d_cand, rank, world, n_local, d_lmember, d_lcand);
+            MTRY(cudaGetLastError());
+            rc = enqueue_batch(h, n_local, d_lmember, d_lcand, d_work, n_local, d_lverdict, d_gather + (size_t)rank * wpr, nullptr, st);
+            if (rc != IPC_OK) { cleanup(); return rc; }
+        }
+        std::string err;
+        if (!h->comm->all_gather_words(d_gather, wpr, st, err)) { cleanup(); return fail(IPC_ERR_CUDA, err); }
+        shard_spread<<<(n_checks + 255) / 256, 256, 0, st>>>(d_gather, wpr, world, n_checks, d_verdict);
+        MTRY(cudaGetLastError());
+        h->last_launches += 2;
+    }
     {
         const long long warps = (long long)n * words;
         const int threads = 256;
@@ -818,6 +805,87 @@ int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, i
     cleanup();
     if (order_out) std::copy(order.begin(), order.end(), order_out);
     if (n_solved) *n_solved = n_checks;
+    return IPC_OK;
+}
+}  // namespace
+
+int ipc_consistency_matrix(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved) {
+    return consistency_matrix_impl(h, rows_bits, order_out, n_solved, false);
+}
+int ipc_consistency_matrix_sharded(ipc_handle* h, uint32_t* rows_bits, int* order_out, int64_t* n_solved) {
+    return consistency_matrix_impl(h, rows_bits, order_out, n_solved, true);
+}
+
+// ---- multi-GPU: communicator + sharded batch (shard the independent checks, one all-gather) -------------
+int ipc_comm_unique_id(unsigned char* id128) {
+    if (!id128) return fail(IPC_ERR_ARG, "null argument");
+    std::string err;
+    if (!Comm::unique_id(id128, err)) return fail(IPC_ERR_CUDA, err);
+    return IPC_OK;
+}
+int ipc_comm_init(ipc_handle* h, const unsigned char* id128, int rank, int world) {
+    if (!h || !id128) return fail(IPC_ERR_ARG, "null argument");
+    if (h->comm) return fail(IPC_ERR_STATE, "the handle already has a communicator");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::string err;
+    h->comm = Comm::create(id128, rank, world, err);
+    if (!h->comm) return fail(IPC_ERR_CUDA, err);
+    return IPC_OK;
+}
+int ipc_comm_info(ipc_handle* h, int* rank, int* world, int64_t* n_collectives) {
+    if (!h) return fail(IPC_ERR_ARG, "null handle");
+    if (rank) *rank = h->comm ? h->comm->rank() : 0;
+    if (world) *world = h->comm ? h->comm->world() : 1;
+    if (n_collectives) *n_collectives = h->comm ? h->comm->n_collectives() : 0;
+    return IPC_OK;
+}
+
+int ipc_check_batch_sharded_dev(ipc_handle* h, int n_local, const int* member_dev, const int* cand_dev, int words_per_rank,
+                                uint32_t* out_bits_all_dev, void* stream) {
+    if (!h || n_local < 0 || !out_bits_all_dev || words_per_rank < (n_local + 31) / 32) return fail(IPC_ERR_ARG, "bad arguments");
+    if (!h->d_loops) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rank = h->comm ? h->comm->rank() : 0;
+    uint32_t* mine = out_bits_all_dev + (size_t)rank * words_per_rank;
+    if (words_per_rank > n_local / 32) CUDA_TRY(cudaMemsetAsync(mine + n_local / 32, 0, sizeof(uint32_t) * (words_per_rank - n_local / 32), st));   // padding bits are zero
+    if (n_local > 0) {
+        int rc = ensure_batch_buffers(h, n_local);
+        if (rc != IPC_OK) return rc;
+        rc = enqueue_batch(h, n_local, member_dev, cand_dev, h->d_work, h->cap_checks, h->d_verdict, mine, nullptr, st);
+        if (rc != IPC_OK) return rc;
+    }
+    if (h->comm && h->comm->world() > 1) {
+        std::string err;
+        if (!h->comm->all_gather_words(out_bits_all_dev, (size_t)words_per_rank, st, err)) return fail(IPC_ERR_CUDA, err);
+    }
+    return IPC_OK;
+}
+
+int ipc_check_batch_sharded(ipc_handle* h, int n_local, const int* member, const int* cand, int words_per_rank, uint32_t* out_bits_all) {
+    if (!h || n_local < 0 || (n_local && (!member || !cand)) || !out_bits_all || words_per_rank < (n_local + 31) / 32) return fail(IPC_ERR_ARG, "bad arguments");
+    if (!h->d_loops) return fail(IPC_ERR_STATE, "no candidate table: call ipc_set_candidates first");
+    for (int i = 0; i < n_local; ++i)
+        if (cand[i] < 0 || cand[i] >= h->n_loops || member[i] >= h->n_loops) return fail(IPC_ERR_ARG, "check " + std::to_string(i) + " indexes outside the candidate table");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int world = h->comm ? h->comm->world() : 1;
+    int rc = ensure_batch_buffers(h, std::max(n_local, 1));
+    if (rc != IPC_OK) return rc;
+    const size_t all_words = (size_t)words_per_rank * world;
+    if (all_words > h->gather_words) {
+        cudaFree(h->d_gather); h->d_gather = nullptr; h->gather_words = 0;
+        CUDA_TRY(cudaMalloc(&h->d_gather, sizeof(uint32_t) * all_words));
+        h->gather_words = all_words;
+    }
+    cudaStream_t st = h->stream;
+    if (n_local) {
+        CUDA_TRY(cudaMemcpyAsync(h->d_member, member, sizeof(int) * n_local, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(h->d_cand, cand, sizeof(int) * n_local, cudaMemcpyHostToDevice, st));
+    }
+    rc = ipc_check_batch_sharded_dev(h, n_local, h->d_member, h->d_cand, words_per_rank, h->d_gather, st);
+    if (rc != IPC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_bits_all, h->d_gather, sizeof(uint32_t) * all_words, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return IPC_OK;
 }
 

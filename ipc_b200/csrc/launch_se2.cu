@@ -1,4 +1,6 @@
 // launch_se2.cu — instantiations of the SE(2) chain-check kernel (own translation unit: built in parallel with the rest)
+#include <atomic>
+
 #include "launch_common.hpp"
 #include "chain_se2_kernel.cuh"
 
@@ -6,10 +8,13 @@ namespace ipcb {
 
 template <int NT, int MODE, bool UNI, int MINB> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
     size_t sm = smem_bytes(MODE, a.Lcap);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in is per device (a process may hold handles on several GPUs): one flag per ordinal, set under the launch that needs it
+    static std::atomic<bool> attr_done[64];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
         CUDA_TRY(cudaFuncSetAttribute(chain_check_se2<NT, MODE, UNI, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev].store(true, std::memory_order_release);
     }
     chain_check_se2<NT, MODE, UNI, MINB><<<grid, NT, sm, st>>>(a);
     CUDA_TRY(cudaGetLastError());

@@ -1,4 +1,6 @@
 // launch_se3.cu — instantiations of the SE(3) chain-check kernel (own translation unit)
+#include <atomic>
+
 #include "launch_common.hpp"
 #include "chain_se3_kernel.cuh"
 
@@ -6,10 +8,13 @@ namespace ipcb {
 
 template <int NT, int MODE> int launch_se3(const BatchArgs& a, int grid, cudaStream_t st) {
     size_t sm = smem_bytes(MODE, a.Lcap, 3, NT);
-    static bool attr_done = false;
-    if (!attr_done) {
+    // the opt-in is per device (a process may hold handles on several GPUs): one flag per ordinal, set under the launch that needs it
+    static std::atomic<bool> attr_done[64];
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev].load(std::memory_order_acquire)) {
         CUDA_TRY(cudaFuncSetAttribute(chain_check_se3<NT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev].store(true, std::memory_order_release);
     }
     chain_check_se3<NT, MODE><<<grid, NT, sm, st>>>(a);
     CUDA_TRY(cudaGetLastError());

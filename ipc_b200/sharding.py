@@ -42,6 +42,23 @@ def unpack_bits(words: np.ndarray, n: int) -> np.ndarray:
     return ((words[i >> 5] >> (i & 31).astype(np.uint32)) & 1).astype(bool)
 
 
+def shard_plan(cost, world: int):
+    """(parts, words_per_rank): parts[r] = check indices of rank r (partition), words_per_rank = 32-bit words that hold the
+    largest shard — EVERY rank pads its verdict words to this count so the all-gather has equal contributions."""
+    parts = [partition(cost, world, r) for r in range(world)]
+    per = max((len(p) for p in parts), default=0)
+    return parts, max(1, (per + 31) // 32)
+
+
+def decode_gathered(gathered, parts, n: int) -> np.ndarray:
+    """Verdict of every check of the whole list from the gathered words [world][words_per_rank]."""
+    gathered = np.asarray(gathered).view(np.uint32).reshape(len(parts), -1)
+    out = np.zeros(n, dtype=bool)
+    for r, idx in enumerate(parts):
+        out[idx] = unpack_bits(gathered[r], len(idx))
+    return out
+
+
 def sharded_verdicts(cost, compute_local, world: int, rank: int, dist=None, device=None):
     """Run `compute_local(indices) -> bool verdicts` on this rank's shard and all_gather the packed words.
     Returns the verdict of every check (same array on every rank)."""
@@ -53,17 +70,12 @@ def sharded_verdicts(cost, compute_local, world: int, rank: int, dist=None, devi
         out[mine] = local
         return out
     import torch
-    per = (n + world - 1) // world                       # every shard has per or per - 1 entries: pad to `per`
-    words = (per + 31) // 32
+    parts, words = shard_plan(cost, world)               # shards differ in size by at most one check: pad to the largest
     buf = torch.zeros(words, dtype=torch.int32, device=device)
     buf[: (len(local) + 31) // 32] = torch.from_numpy(pack_bits(local).view(np.int32)).to(device)
     gathered = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(gathered, buf)                       # the single collective of the path
-    out = np.zeros(n, dtype=bool)
-    for r in range(world):
-        idx = partition(cost, world, r)
-        out[idx] = unpack_bits(gathered[r].cpu().numpy().view(np.uint32), len(idx))
-    return out
+    return decode_gathered(np.stack([t.cpu().numpy() for t in gathered]), parts, n)
 
 
 def matrix_from_verdicts(graph, member, cand, verdict, order=None):

@@ -23,10 +23,12 @@ def test_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference"
     assert d["metric"] == "pairwise consistency checks/sec" and d["unit"] == "checks/s"
-    assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["higher_is_better"] is True and d["scaling"] == "strong" and d["vs_baseline"] is None
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
     assert d["dtype"] == "f64" and d["data"] == "synthetic"
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the config record is built by ONE function for both arms: same keys and strings for the same command line
+    assert set(d["config"]) == {"workload", "termination", "l2", "sharding"}
     assert d["value"] > 0 and d["ms_per_step"] > 0
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
