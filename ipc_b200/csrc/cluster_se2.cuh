@@ -1,21 +1,21 @@
-// cluster_se2.cuh — SE(2) window solve with ANY number of loop edges (the slow path of the sequential stream).
+// cluster_se2.cuh — SE(2) window solve with ANY number of loop edges (the slow path of the sequential stream): the per-phase
+// device functions of the persistent stream solver (stream_solver.cuh).
 //
 // Replaces isAgreeingWithCurrentState (/root/reference/src/consensus_utils.cpp:6-22) as driven by
 // IPC::agreementCheck (/root/reference/src/consensus.cpp:42-75) when the candidate's cluster holds K - 1 >= 0 accepted
 // loops. Same twist-coordinate formulation as chain_se2.cuh (DESIGN.md "Chain solve"), generalised:
 //   * per odometry edge k: terms M_k = Q_k V_k Q_k^T, m_k = -Q_k d_k; prefix sums PM, Pm over the window;
 //   * per loop l on the edge interval [a_l, b_l): W_l = Q_l V_l Q_l^T, sigma_l, d_l;
-//   * forces: (P(I_l ∩ I_l') + delta_ll' W_l) z_l' = Pm(b_l) - Pm(a_l) + sigma_l Q_l d_l  — dense SPD, 3K x 3K, factorised
-//     with cuSOLVER potrf (a plain library Cholesky; everything else here is hand written);
+//   * forces: (P(I_l ∩ I_l') + delta_ll' W_l) z_l' = Pm(b_l) - Pm(a_l) + sigma_l Q_l d_l  — dense SPD, 3K x 3K, factorised by the
+//     hand-written blocked Cholesky of stream_solver.cuh (no library call anywhere on this path);
 //   * step: f_k = sum of z_l over the loops covering edge k, xi_k = m_k - M_k f_k, Xi = prefix(xi), h_j = T_j Xi_j.
-// The Dogleg control flow runs on the host (one stream of sequential checks: latency bound by construction), every
-// vector operation is a kernel; scalars come back through one small pinned buffer per decision.
+// Every function here is executed by ONE CTA of CL_NT threads (CTA 0 of the cooperative grid) unless it says "grid".
 #pragma once
 #include "chain_se2.cuh"
 
 namespace ipcb {
 
-constexpr int CL_NT = 1024;     // one CTA walks the window
+constexpr int CL_NT = 1024;     // threads per CTA of the stream solver
 constexpr int CL_NRES = 16;     // doubles in the result buffer
 
 struct ClLoop {                 // one loop edge of the cluster, local indices
@@ -25,12 +25,17 @@ struct ClLoop {                 // one loop edge of the cluster, local indices
 };
 
 struct ClBuffers {
-    double* W;                  // window state AoS[5] x (L + 1): x y theta cos sin
-    double* T;                  // per-edge terms, SoA [9][Lcap]
-    double* P;                  // inclusive prefix per vertex, SoA [9][Lcap + 1] (P[.][0] = 0)
+    double* W;                  // window state AoS[5] x (L + 1): x y theta cos sin  (SE(3): AoS[7], t + quaternion)
+    double* T;                  // per-edge terms, SoA [NPRE][Lcap]
+    double* P;                  // inclusive prefix per vertex, SoA [NPRE][Lcap + 1] (P[.][0] = 0)
     double* chi_e;              // per-edge chi2 [Lcap]
-    double* lt;                 // per-loop terms [K][12]: t(9), sigma, chi, pad
+    double* lt;                 // per-loop terms [K][12]: t(9), sigma, chi, pad   (SE(3): [K][32])
 };
+
+// Loop end points by window position (CSR over local vertices 0..L, built on the host once per check): entry = loop index l
+// shifted left by one, low bit set when the position is the START a_l of the loop's interval (else its END b_l). Within a
+// position the entries are in increasing l: per-vertex sums run in loop order, i.e. deterministic.
+struct ClEvents { const int* ptr; const int* idx; };
 
 template <int M> __device__ __forceinline__ void cl_block_sum(double* v, double* red) {
 #pragma unroll
@@ -76,19 +81,16 @@ template <int M> __device__ __forceinline__ void cl_block_excl_scan(double* v, d
     for (int m = 0; m < M; ++m) { double base = 0; for (int i = 0; i < w; ++i) base += red[i * M + m]; v[m] = base + inc[m] - v[m]; }
 }
 
-// copy the window out of the global pose array (cos / sin included)
-__global__ void cl_load_window(const double* __restrict__ pose, int lo, int L, double* __restrict__ W) {
-    for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < 5 * (L + 1); i += blockDim.x * gridDim.x) W[i] = pose[5 * (size_t)lo + i];
-}
-__global__ void cl_store_window(double* __restrict__ pose, int lo, int L, const double* __restrict__ W) {
-    for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < 5 * (L + 1); i += blockDim.x * gridDim.x) pose[5 * (size_t)lo + i] = W[i];
+// block-strided copy (one CTA)
+__device__ __forceinline__ void cl_copy_cta(const double* src, double* dst, long long n) {
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
 }
 
 // linearise every odometry edge of the window: terms, prefix sums, chi2. res[0] = sum chi2, res[1] = max chi2.
-__global__ void __launch_bounds__(CL_NT) cl_linearize(const double* __restrict__ odom9, int lo, int L, int Lcap, ClBuffers B, double* __restrict__ res) {
-    __shared__ double red[32 * NPRE];
+__device__ __noinline__ void cl_linearize(const double* __restrict__ odom9, int lo, int L, int Lcap, ClBuffers B, double* res, double* red) {
     const int S = (L + CL_NT - 1) / CL_NT;
-    const int k0 = min(threadIdx.x * S, L), k1 = min(k0 + S, L);
+    const int k0 = min((int)threadIdx.x * S, L), k1 = min(k0 + S, L);
     double run[NPRE];
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) run[m] = 0;
@@ -114,11 +116,11 @@ __global__ void __launch_bounds__(CL_NT) cl_linearize(const double* __restrict__
     cl_block_sum<1>(s, red);
     mx = cl_block_max(mx, red);
     if (threadIdx.x == 0) { res[0] = s[0]; res[1] = mx; }
+    __syncthreads();
 }
 
 // loop edges at the window state: terms, sigma, chi2. res[2] = sum of loop chi2, res[3] = max, res[4] = chi2 of the LAST loop (the candidate)
-__global__ void cl_loops(const ClLoop* __restrict__ loops, int K, ClBuffers B, double* __restrict__ res) {
-    __shared__ double red[32 * 2];
+__device__ __noinline__ void cl_loops(const ClLoop* __restrict__ loops, int K, ClBuffers B, double* res, double* red) {
     double chi = 0, mx = 0;
     for (int l = threadIdx.x; l < K; l += blockDim.x) {
         const ClLoop& Lp = loops[l];
@@ -136,49 +138,68 @@ __global__ void cl_loops(const ClLoop* __restrict__ loops, int K, ClBuffers B, d
     cl_block_sum<1>(s, red);
     mx = cl_block_max(mx, red);
     if (threadIdx.x == 0) { res[2] = s[0]; res[3] = mx; }
+    __syncthreads();
 }
 
-// S (3K x 3K, column-major, lower triangle filled — symmetric anyway) and rhs r (3K)
-__global__ void cl_assemble(const ClLoop* __restrict__ loops, int K, int Lcap, ClBuffers B, double* __restrict__ Smat, double* __restrict__ rhs) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)K * K) return;
-    const int l = (int)(idx / K), m = (int)(idx % K);
-    const int a = max(loops[l].a, loops[m].a), b = min(loops[l].b, loops[m].b);
-    double blk[6] = {0, 0, 0, 0, 0, 0};
-    if (b > a) {
+// GRID: lower block triangle of S (3K x 3K, column-major with leading dimension ld) and the right-hand side, stored as the extra
+// matrix row `rhs_row` (the factorisation then forward-substitutes it for free, stream_solver.cuh).
+__device__ __forceinline__ void cl_assemble_grid(const ClLoop* __restrict__ loops, int K, int Lcap, ClBuffers B, double* Smat, int ld, int rhs_row) {
+    const long long total = (long long)K * (K + 1) / 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        // idx -> (l, m) with l >= m: row block l, column block m
+        int l = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+        while ((long long)l * (l + 1) / 2 > idx) --l;
+        while ((long long)(l + 1) * (l + 2) / 2 <= idx) ++l;
+        const int m = (int)(idx - (long long)l * (l + 1) / 2);
+        const int a = max(loops[l].a, loops[m].a), b = min(loops[l].b, loops[m].b);
+        double blk[6] = {0, 0, 0, 0, 0, 0};
+        if (b > a) {
 #pragma unroll
-        for (int q = 0; q < 6; ++q) blk[q] = B.P[(size_t)q * (Lcap + 1) + b] - B.P[(size_t)q * (Lcap + 1) + a];
+            for (int q = 0; q < 6; ++q) blk[q] = B.P[(size_t)q * (Lcap + 1) + b] - B.P[(size_t)q * (Lcap + 1) + a];
+        }
+        if (l == m) {
+            const double* t = B.lt + 12 * (size_t)l;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) blk[q] += t[q];
+            const int la = loops[l].a, lb = loops[l].b;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                Smat[(size_t)(3 * l + q) * ld + rhs_row] = B.P[(size_t)(6 + q) * (Lcap + 1) + lb] - B.P[(size_t)(6 + q) * (Lcap + 1) + la] - t[9] * t[6 + q];
+        }
+        const double full[9] = {blk[0], blk[1], blk[2], blk[1], blk[3], blk[4], blk[2], blk[4], blk[5]};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Smat[(size_t)(3 * m + c) * ld + (3 * l + r)] = full[r * 3 + c];
     }
-    if (l == m) {
-        const double* t = B.lt + 12 * (size_t)l;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) blk[q] += t[q];
-        const int la = loops[l].a, lb = loops[l].b;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) rhs[3 * l + q] = B.P[(size_t)(6 + q) * (Lcap + 1) + lb] - B.P[(size_t)(6 + q) * (Lcap + 1) + la] - t[9] * t[6 + q];
+}
+
+// force on edge k0 = sum of z_l over the loops covering it (loop order), then advanced edge by edge with the end-point events
+__device__ __forceinline__ void cl_force_at(const ClLoop* __restrict__ loops, int K, const double* z, int k, double* f) {
+    f[0] = f[1] = f[2] = 0;
+    for (int l = 0; l < K; ++l)
+        if (loops[l].a <= k && k < loops[l].b) { f[0] += z[3 * l]; f[1] += z[3 * l + 1]; f[2] += z[3 * l + 2]; }
+}
+__device__ __forceinline__ void cl_force_step(const ClEvents& E, const double* z, int k, double* f) {   // f(edge k-1) -> f(edge k)
+    for (int q = E.ptr[k]; q < E.ptr[k + 1]; ++q) {
+        const int l = E.idx[q] >> 1; const double sg = (E.idx[q] & 1) ? 1.0 : -1.0;
+        f[0] += sg * z[3 * l]; f[1] += sg * z[3 * l + 1]; f[2] += sg * z[3 * l + 2];
     }
-    const int n = 3 * K;
-    const double full[9] = {blk[0], blk[1], blk[2], blk[1], blk[3], blk[4], blk[2], blk[4], blk[5]};
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) Smat[(size_t)(3 * m + c) * n + (3 * l + r)] = full[r * 3 + c];
 }
 
 // GN step from the forces z: f_k = sum_{l covers k} z_l, xi_k = m_k - M_k f_k, Xi = prefix(xi), h_j = T_j Xi_j.
 // H: AoS[3] x (L + 1). res[5] = |h|^2, res[6] = predicted gain h^T H h = sum over edges |J h|^2_Omega, accumulated edge by
 // edge from non-negative terms (chi2 - model cancels catastrophically for gross outliers): an odometry edge contributes
 // xi_k^T M_k^-1 xi_k, a loop eta^T W_l^-1 eta with eta = sigma W_l z_l - Q_l d_l.
-__global__ void __launch_bounds__(CL_NT) cl_gn_step(const ClLoop* __restrict__ loops, int K, int L, int Lcap, ClBuffers B, const double* __restrict__ z,
-                                                    double* __restrict__ H, double* __restrict__ res) {
-    __shared__ double red[32 * 3];
+__device__ __noinline__ void cl_gn_step(const ClLoop* __restrict__ loops, int K, ClEvents E, int L, int Lcap, ClBuffers B, const double* z,
+                                        double* H, double* res, double* red) {
     const int S = (L + CL_NT - 1) / CL_NT;
-    const int k0 = min(threadIdx.x * S, L), k1 = min(k0 + S, L);
+    const int k0 = min((int)threadIdx.x * S, L), k1 = min(k0 + S, L);
     double tot[3] = {0, 0, 0}, model = 0;
+    double f[3] = {0, 0, 0};
+    if (k0 < k1) cl_force_at(loops, K, z, k0, f);
     for (int k = k0; k < k1; ++k) {
-        double f[3] = {0, 0, 0};
-        for (int l = 0; l < K; ++l)
-            if (loops[l].a <= k && k < loops[l].b) { f[0] += z[3 * l]; f[1] += z[3 * l + 1]; f[2] += z[3 * l + 2]; }
+        if (k > k0) cl_force_step(E, z, k, f);
         double t[NPRE];
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) t[m] = B.T[(size_t)m * Lcap + k];
@@ -210,10 +231,20 @@ __global__ void __launch_bounds__(CL_NT) cl_gn_step(const ClLoop* __restrict__ l
     double s[2] = {hh, model};
     cl_block_sum<2>(s, red);
     if (threadIdx.x == 0) { res[5] = s[0]; res[6] = s[1]; }
+    __syncthreads();
 }
 
-// gradient b_j in g2o vertex coordinates (odometry part), G: AoS[3] x (L + 1)
-__global__ void __launch_bounds__(CL_NT) cl_grad_odom(const double* __restrict__ odom9, int lo, int L, ClBuffers B, double* __restrict__ G) {
+// gradient b_j in g2o vertex coordinates, G: AoS[3] x (L + 1): odometry part, then the loop edges incident to j in loop order.
+// lg: per-loop staging [K][6] (gi, gj of every loop at the current state).
+__device__ __noinline__ void cl_gradient(const double* __restrict__ odom9, const ClLoop* __restrict__ loops, int K, ClEvents E, int lo, int L, ClBuffers B,
+                                         double* G, double* lg) {
+    for (int l = threadIdx.x; l < K; l += blockDim.x) {
+        const ClLoop& Lp = loops[l];
+        const double* pf = B.W + 5 * Lp.jf; const double* pt = B.W + 5 * Lp.jt;
+        Lin2 e; lin2cs(pf[3], pf[4], P2{pf[0], pf[1], pf[2]}, P2{pt[0], pt[1], pt[2]}, Lp.meas[0], Lp.meas[1], Lp.meas[2], Lp.D, e);
+        grad2(e, lg + 6 * (size_t)l, lg + 6 * (size_t)l + 3);
+    }
+    __syncthreads();
     for (int j = threadIdx.x; j <= L; j += blockDim.x) {
         double b[3] = {0, 0, 0};
         if (j > 0) {
@@ -229,27 +260,19 @@ __global__ void __launch_bounds__(CL_NT) cl_grad_odom(const double* __restrict__
                 grad2(e2, gi, gj);
                 b[0] -= gi[0]; b[1] -= gi[1]; b[2] -= gi[2];
             }
+            for (int q = E.ptr[j]; q < E.ptr[j + 1]; ++q) {
+                const int l = E.idx[q] >> 1;
+                const double* g = lg + 6 * (size_t)l + (loops[l].jf == j ? 0 : 3);
+                b[0] -= g[0]; b[1] -= g[1]; b[2] -= g[2];
+            }
         }
-        G[3 * j] = b[0]; G[3 * j + 1] = b[1]; G[3 * j + 2] = b[2];
+        G[3 * j] = b[0]; G[3 * j + 1] = b[1]; G[3 * j + 2] = b[2];     // vertex 0 of the window is fixed: zero
     }
-}
-// loop contributions to b, in loop order (deterministic), one thread
-__global__ void cl_grad_loops(const ClLoop* __restrict__ loops, int K, ClBuffers B, double* __restrict__ G) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int l = 0; l < K; ++l) {
-        const ClLoop& Lp = loops[l];
-        const double* pf = B.W + 5 * Lp.jf; const double* pt = B.W + 5 * Lp.jt;
-        Lin2 e; lin2cs(pf[3], pf[4], P2{pf[0], pf[1], pf[2]}, P2{pt[0], pt[1], pt[2]}, Lp.meas[0], Lp.meas[1], Lp.meas[2], Lp.D, e);
-        double gi[3], gj[3]; grad2(e, gi, gj);
-        if (Lp.jf > 0) { G[3 * Lp.jf] -= gi[0]; G[3 * Lp.jf + 1] -= gi[1]; G[3 * Lp.jf + 2] -= gi[2]; }
-        if (Lp.jt > 0) { G[3 * Lp.jt] -= gj[0]; G[3 * Lp.jt + 1] -= gj[1]; G[3 * Lp.jt + 2] -= gj[2]; }
-    }
-    G[0] = 0; G[1] = 0; G[2] = 0;     // vertex 0 of the window is fixed
+    __syncthreads();
 }
 // res[7] = |b|^2, res[8] = b . h_gn, res[9] = b^T H b
-__global__ void __launch_bounds__(CL_NT) cl_sd_scalars(const double* __restrict__ odom9, const ClLoop* __restrict__ loops, int K, int lo, int L, ClBuffers B,
-                                                       const double* __restrict__ G, const double* __restrict__ H, double* __restrict__ res) {
-    __shared__ double red[32 * 3];
+__device__ __noinline__ void cl_sd_scalars(const double* __restrict__ odom9, const ClLoop* __restrict__ loops, int K, int lo, int L, ClBuffers B,
+                                           const double* G, const double* H, double* res, double* red) {
     double v[3] = {0, 0, 0};
     for (int j = threadIdx.x; j <= L; j += blockDim.x) {
         const double* b = G + 3 * j; const double* h = H + 3 * j;
@@ -272,11 +295,11 @@ __global__ void __launch_bounds__(CL_NT) cl_sd_scalars(const double* __restrict_
     }
     cl_block_sum<3>(v, red);
     if (threadIdx.x == 0) { res[7] = v[0]; res[8] = v[1]; res[9] = v[2]; }
+    __syncthreads();
 }
 // trial state W1 = W0 (+) (c1 b + c2 h_gn); res[10] = |h|^2
-__global__ void __launch_bounds__(CL_NT) cl_apply(int L, const double* __restrict__ W0, const double* __restrict__ G, const double* __restrict__ H, double c1,
-                                                  double c2, double* __restrict__ W1, double* __restrict__ res) {
-    __shared__ double red[32];
+__device__ __noinline__ void cl_apply(int L, const double* W0, const double* G, const double* H, double c1,
+                                      double c2, double* W1, double* res, double* red) {
     double hh[1] = {0};
     for (int j = threadIdx.x; j <= L; j += blockDim.x) {
         double h[3] = {c2 * H[3 * j], c2 * H[3 * j + 1], c2 * H[3 * j + 2]};
@@ -290,16 +313,16 @@ __global__ void __launch_bounds__(CL_NT) cl_apply(int L, const double* __restric
     }
     cl_block_sum<1>(hh, red);
     if (threadIdx.x == 0) res[10] = hh[0];
+    __syncthreads();
 }
 
 // pose[j] for j = start+1 .. n-1 re-dead-reckoned from pose[start] (propagateCurrentGuess / propagateGuess,
-// src/consensus_utils.cpp:60-71, 98-116): two block scans (headings, then rotated translations).
-__global__ void __launch_bounds__(CL_NT) cl_dead_reckon(const double* __restrict__ odom9, int start, int n, double* __restrict__ pose) {
-    __shared__ double red[32 * 2];
+// src/consensus_utils.cpp:60-71, 98-116): two block scans (headings, then rotated translations). One CTA of CL_NT threads.
+__device__ __noinline__ void cl_dead_reckon_cta(const double* __restrict__ odom9, int start, int n, double* pose, double* red) {
     const int L = n - 1 - start;
     if (L <= 0) return;
     const int S = (L + CL_NT - 1) / CL_NT;
-    const int k0 = min(threadIdx.x * S, L), k1 = min(k0 + S, L);
+    const int k0 = min((int)threadIdx.x * S, L), k1 = min(k0 + S, L);
     const double th_s = pose[5 * (size_t)start + 2], x_s = pose[5 * (size_t)start], y_s = pose[5 * (size_t)start + 1];
     double v[1] = {0};
     for (int k = k0; k < k1; ++k) v[0] += odom9[9 * (size_t)(start + k) + 2];
@@ -325,9 +348,14 @@ __global__ void __launch_bounds__(CL_NT) cl_dead_reckon(const double* __restrict
         double* q = pose + 5 * (size_t)(start + k + 1);
         q[0] = ax; q[1] = ay; c = q[3]; s = q[4];
     }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(CL_NT) cl_dead_reckon(const double* __restrict__ odom9, int start, int n, double* pose) {
+    __shared__ double red[32 * 2];
+    cl_dead_reckon_cta(odom9, start, n, pose, red);
 }
 __global__ void cl_set_origin(double* pose) { if (threadIdx.x == 0) { pose[0] = 0; pose[1] = 0; pose[2] = 0; pose[3] = 1; pose[4] = 0; } }
-__global__ void cl_export_poses(const double* __restrict__ pose, int n, double* __restrict__ out) {
+__global__ void cl_export_poses(const double* pose, int n, double* out) {
     for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < n; i += blockDim.x * gridDim.x) { out[3 * i] = pose[5 * i]; out[3 * i + 1] = pose[5 * i + 1]; out[3 * i + 2] = pose[5 * i + 2]; }
 }
 

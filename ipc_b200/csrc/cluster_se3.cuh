@@ -1,7 +1,8 @@
 // cluster_se3.cuh — SE(3) window solve with any number of loop edges: the 6-dimensional copy of cluster_se2.cuh
 // (sequential stream of IPC<EdgeSE3, VertexSE3>::agreementCheck, /root/reference/src/consensus.cpp:42-75,175) built on
 // the device functions of chain_se3.cuh. Forces: (P(I_l ∩ I_l') + delta W_l) z_l' = Pm(b) - Pm(a) + sigma Q_l e_l, 6K x 6K
-// dense SPD, factorised with cuSOLVER potrf; Dogleg control flow on the host.
+// dense SPD, factorised by the hand-written blocked Cholesky of stream_solver.cuh; the Dogleg runs on the device.
+// Every function here is executed by ONE CTA of CL_NT threads (CTA 0 of the cooperative grid) unless it says "grid".
 #pragma once
 #include "chain_se3.cuh"
 #include "cluster_se2.cuh"
@@ -14,16 +15,11 @@ struct ClLoop3 {
 };
 constexpr int CL3_LT = 32;      // per-loop terms: t(27), sigma, chi, pad
 
-__global__ void cl_copy(const double* __restrict__ src, double* __restrict__ dst, long long n) {
-    for (long long i = threadIdx.x + (long long)blockIdx.x * blockDim.x; i < n; i += (long long)blockDim.x * gridDim.x) dst[i] = src[i];
-}
-
 // res[0] = sum chi2, res[1] = max chi2 over the odometry edges
-__global__ void __launch_bounds__(CL_NT) cl3_linearize(const double* __restrict__ odom49, int lo, int L, int Lcap, ClBuffers B, double* __restrict__ res) {
+__device__ __noinline__ void cl3_linearize(const double* __restrict__ odom49, int lo, int L, int Lcap, ClBuffers B, double* res, double* red) {
     using namespace se3;
-    __shared__ double red[32 * NP3];
     const int S = (L + CL_NT - 1) / CL_NT;
-    const int k0 = min(threadIdx.x * S, L), k1 = min(k0 + S, L);
+    const int k0 = min((int)threadIdx.x * S, L), k1 = min(k0 + S, L);
     double run[NP3];
     for (int m = 0; m < NP3; ++m) run[m] = 0;
     double chi = 0, mx = 0;
@@ -43,11 +39,11 @@ __global__ void __launch_bounds__(CL_NT) cl3_linearize(const double* __restrict_
     cl_block_sum<1>(s, red);
     mx = cl_block_max(mx, red);
     if (threadIdx.x == 0) { res[0] = s[0]; res[1] = mx; }
+    __syncthreads();
 }
 
-__global__ void cl3_loops(const ClLoop3* __restrict__ loops, int K, ClBuffers B, double* __restrict__ res) {
+__device__ __noinline__ void cl3_loops(const ClLoop3* __restrict__ loops, int K, ClBuffers B, double* res, double* red) {
     using namespace se3;
-    __shared__ double red[32 * 2];
     double chi = 0, mx = 0;
     for (int l = threadIdx.x; l < K; l += blockDim.x) {
         const ClLoop3& Lp = loops[l];
@@ -64,39 +60,56 @@ __global__ void cl3_loops(const ClLoop3* __restrict__ loops, int K, ClBuffers B,
     cl_block_sum<1>(s, red);
     mx = cl_block_max(mx, red);
     if (threadIdx.x == 0) { res[2] = s[0]; res[3] = mx; }
+    __syncthreads();
 }
 
-__global__ void cl3_assemble(const ClLoop3* __restrict__ loops, int K, int Lcap, ClBuffers B, double* __restrict__ Smat, double* __restrict__ rhs) {
+// GRID: lower block triangle of S (6K x 6K, column-major, leading dimension ld) + the right-hand side as matrix row `rhs_row`
+__device__ __forceinline__ void cl3_assemble_grid(const ClLoop3* __restrict__ loops, int K, int Lcap, ClBuffers B, double* Smat, int ld, int rhs_row) {
     using namespace se3;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)K * K) return;
-    const int l = (int)(idx / K), m = (int)(idx % K);
-    const int a = max(loops[l].a, loops[m].a), b = min(loops[l].b, loops[m].b);
-    double blk[NS6];
-    for (int q = 0; q < NS6; ++q) blk[q] = (b > a) ? B.P[(size_t)q * (Lcap + 1) + b] - B.P[(size_t)q * (Lcap + 1) + a] : 0.0;
-    if (l == m) {
-        const double* t = B.lt + CL3_LT * (size_t)l;
-        for (int q = 0; q < NS6; ++q) blk[q] += t[q];
-        const int la = loops[l].a, lb = loops[l].b;
-        for (int q = 0; q < 6; ++q) rhs[6 * l + q] = B.P[(size_t)(NS6 + q) * (Lcap + 1) + lb] - B.P[(size_t)(NS6 + q) * (Lcap + 1) + la] - t[27] * t[NS6 + q];
+    const long long total = (long long)K * (K + 1) / 2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        int l = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
+        while ((long long)l * (l + 1) / 2 > idx) --l;
+        while ((long long)(l + 1) * (l + 2) / 2 <= idx) ++l;
+        const int m = (int)(idx - (long long)l * (l + 1) / 2);
+        const int a = max(loops[l].a, loops[m].a), b = min(loops[l].b, loops[m].b);
+        double blk[NS6];
+        for (int q = 0; q < NS6; ++q) blk[q] = (b > a) ? B.P[(size_t)q * (Lcap + 1) + b] - B.P[(size_t)q * (Lcap + 1) + a] : 0.0;
+        if (l == m) {
+            const double* t = B.lt + CL3_LT * (size_t)l;
+            for (int q = 0; q < NS6; ++q) blk[q] += t[q];
+            const int la = loops[l].a, lb = loops[l].b;
+            for (int q = 0; q < 6; ++q)
+                Smat[(size_t)(6 * l + q) * ld + rhs_row] = B.P[(size_t)(NS6 + q) * (Lcap + 1) + lb] - B.P[(size_t)(NS6 + q) * (Lcap + 1) + la] - t[27] * t[NS6 + q];
+        }
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) Smat[(size_t)(6 * m + c) * ld + (6 * l + r)] = blk[sidx(r, c)];
     }
-    const int n = 6 * K;
-    for (int r = 0; r < 6; ++r)
-        for (int c = 0; c < 6; ++c) Smat[(size_t)(6 * m + c) * n + (6 * l + r)] = blk[sidx(r, c)];
+}
+
+__device__ __forceinline__ void cl3_force_at(const ClLoop3* __restrict__ loops, int K, const double* z, int k, double* f) {
+    for (int q = 0; q < 6; ++q) f[q] = 0;
+    for (int l = 0; l < K; ++l)
+        if (loops[l].a <= k && k < loops[l].b) for (int q = 0; q < 6; ++q) f[q] += z[6 * l + q];
+}
+__device__ __forceinline__ void cl3_force_step(const ClEvents& E, const double* z, int k, double* f) {
+    for (int e = E.ptr[k]; e < E.ptr[k + 1]; ++e) {
+        const int l = E.idx[e] >> 1; const double sg = (E.idx[e] & 1) ? 1.0 : -1.0;
+        for (int q = 0; q < 6; ++q) f[q] += sg * z[6 * l + q];
+    }
 }
 
 // H: AoS[6] x (L + 1), g2o vertex coordinates. res[5] = |h|^2, res[6] = predicted gain (sum of xi^T M^-1 xi and loop terms)
-__global__ void __launch_bounds__(CL_NT) cl3_gn_step(const ClLoop3* __restrict__ loops, int K, int L, int Lcap, ClBuffers B, const double* __restrict__ z,
-                                                     double* __restrict__ H, double* __restrict__ res) {
+__device__ __noinline__ void cl3_gn_step(const ClLoop3* __restrict__ loops, int K, ClEvents E, int L, int Lcap, ClBuffers B, const double* z,
+                                         double* H, double* res, double* red) {
     using namespace se3;
-    __shared__ double red[32 * 6];
     const int S = (L + CL_NT - 1) / CL_NT;
-    const int k0 = min(threadIdx.x * S, L), k1 = min(k0 + S, L);
+    const int k0 = min((int)threadIdx.x * S, L), k1 = min(k0 + S, L);
     double tot[6] = {0, 0, 0, 0, 0, 0}, gain = 0;
+    double f[6] = {0, 0, 0, 0, 0, 0};
+    if (k0 < k1) cl3_force_at(loops, K, z, k0, f);
     for (int k = k0; k < k1; ++k) {
-        double f[6] = {0, 0, 0, 0, 0, 0};
-        for (int l = 0; l < K; ++l)
-            if (loops[l].a <= k && k < loops[l].b) for (int q = 0; q < 6; ++q) f[q] += z[6 * l + q];
+        if (k > k0) cl3_force_step(E, z, k, f);
         double t[NP3];
         for (int m = 0; m < NP3; ++m) t[m] = B.T[(size_t)m * Lcap + k];
         double Mf[6]; sym6_vec(t, f, Mf);
@@ -138,11 +151,21 @@ __global__ void __launch_bounds__(CL_NT) cl3_gn_step(const ClLoop3* __restrict__
     double s[2] = {hh, gain};
     cl_block_sum<2>(s, red);
     if (threadIdx.x == 0) { res[5] = s[0]; res[6] = s[1]; }
+    __syncthreads();
 }
 
-// gradient b_j (odometry part), G: AoS[6] x (L + 1)
-__global__ void __launch_bounds__(CL_NT) cl3_grad_odom(const double* __restrict__ odom49, int lo, int L, ClBuffers B, double* __restrict__ G) {
+// gradient b_j, G: AoS[6] x (L + 1): odometry part, then the loop edges incident to j in loop order. lg: staging [K][12]
+__device__ __noinline__ void cl3_gradient(const double* __restrict__ odom49, const ClLoop3* __restrict__ loops, int K, ClEvents E, int lo, int L, ClBuffers B,
+                                          double* G, double* lg) {
     using namespace se3;
+    for (int l = threadIdx.x; l < K; l += blockDim.x) {
+        const ClLoop3& Lp = loops[l];
+        P3 pf, pt; load_pose(B.W + 7 * Lp.jf, pf); load_pose(B.W + 7 * Lp.jt, pt);
+        Lin3 e; lin3(Lp.zinv, pf, pt, Lp.Om, e);
+        double Ji[36], Jj[36]; jac3(Lp.zinv, e, Ji, Jj);
+        m6t_vec(Ji, e.we, lg + 12 * (size_t)l); m6t_vec(Jj, e.we, lg + 12 * (size_t)l + 6);
+    }
+    __syncthreads();
     for (int j = threadIdx.x; j <= L; j += blockDim.x) {
         double b[6] = {0, 0, 0, 0, 0, 0};
         if (j > 0) {
@@ -160,29 +183,20 @@ __global__ void __launch_bounds__(CL_NT) cl3_grad_odom(const double* __restrict_
                 m6t_vec(Ji, e2.we, g);
                 for (int q = 0; q < 6; ++q) b[q] -= g[q];
             }
+            for (int e2 = E.ptr[j]; e2 < E.ptr[j + 1]; ++e2) {
+                const int l = E.idx[e2] >> 1;
+                const double* gl = lg + 12 * (size_t)l + (loops[l].jf == j ? 0 : 6);
+                for (int q = 0; q < 6; ++q) b[q] -= gl[q];
+            }
         }
         for (int q = 0; q < 6; ++q) G[6 * j + q] = b[q];
     }
-}
-__global__ void cl3_grad_loops(const ClLoop3* __restrict__ loops, int K, ClBuffers B, double* __restrict__ G) {
-    using namespace se3;
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    for (int l = 0; l < K; ++l) {
-        const ClLoop3& Lp = loops[l];
-        P3 pf, pt; load_pose(B.W + 7 * Lp.jf, pf); load_pose(B.W + 7 * Lp.jt, pt);
-        Lin3 e; lin3(Lp.zinv, pf, pt, Lp.Om, e);
-        double Ji[36], Jj[36], gi[6], gj[6]; jac3(Lp.zinv, e, Ji, Jj);
-        m6t_vec(Ji, e.we, gi); m6t_vec(Jj, e.we, gj);
-        if (Lp.jf > 0) for (int q = 0; q < 6; ++q) G[6 * Lp.jf + q] -= gi[q];
-        if (Lp.jt > 0) for (int q = 0; q < 6; ++q) G[6 * Lp.jt + q] -= gj[q];
-    }
-    for (int q = 0; q < 6; ++q) G[q] = 0;
+    __syncthreads();
 }
 // res[7] = |b|^2, res[8] = b . h_gn, res[9] = b^T H b
-__global__ void __launch_bounds__(CL_NT) cl3_sd_scalars(const double* __restrict__ odom49, const ClLoop3* __restrict__ loops, int K, int lo, int L, ClBuffers B,
-                                                        const double* __restrict__ G, const double* __restrict__ H, double* __restrict__ res) {
+__device__ __noinline__ void cl3_sd_scalars(const double* __restrict__ odom49, const ClLoop3* __restrict__ loops, int K, int lo, int L, ClBuffers B,
+                                            const double* G, const double* H, double* res, double* red) {
     using namespace se3;
-    __shared__ double red[32 * 3];
     double v[3] = {0, 0, 0};
     for (int j = threadIdx.x; j <= L; j += blockDim.x) {
         const double* b = G + 6 * j; const double* h = H + 6 * j;
@@ -208,11 +222,11 @@ __global__ void __launch_bounds__(CL_NT) cl3_sd_scalars(const double* __restrict
     }
     cl_block_sum<3>(v, red);
     if (threadIdx.x == 0) { res[7] = v[0]; res[8] = v[1]; res[9] = v[2]; }
+    __syncthreads();
 }
-__global__ void __launch_bounds__(CL_NT) cl3_apply(int L, const double* __restrict__ W0, const double* __restrict__ G, const double* __restrict__ H, double c1,
-                                                   double c2, double* __restrict__ W1, double* __restrict__ res) {
+__device__ __noinline__ void cl3_apply(int L, const double* W0, const double* G, const double* H, double c1,
+                                       double c2, double* W1, double* res, double* red) {
     using namespace se3;
-    __shared__ double red[32];
     double hh[1] = {0};
     for (int j = threadIdx.x; j <= L; j += blockDim.x) {
         double u[6];
@@ -224,14 +238,15 @@ __global__ void __launch_bounds__(CL_NT) cl3_apply(int L, const double* __restri
     }
     cl_block_sum<1>(hh, red);
     if (threadIdx.x == 0) res[10] = hh[0];
+    __syncthreads();
 }
-// pose[j], j = start+1 .. n-1, re-dead-reckoned from pose[start]; `stage` holds CL_NT x 7 doubles
-__global__ void __launch_bounds__(CL_NT) cl3_dead_reckon(const double* __restrict__ odom49, int start, int n, double* __restrict__ pose, double* __restrict__ stage) {
+// pose[j], j = start+1 .. n-1, re-dead-reckoned from pose[start]; `stage` holds CL_NT x 7 doubles (global). One CTA of CL_NT threads.
+__device__ __noinline__ void cl3_dead_reckon_cta(const double* __restrict__ odom49, int start, int n, double* pose, double* stage) {
     using namespace se3;
     const int L = n - 1 - start;
     if (L <= 0) return;
     const int S = (L + CL_NT - 1) / CL_NT;
-    const int k0 = min(threadIdx.x * S, L), k1 = min(k0 + S, L);
+    const int k0 = min((int)threadIdx.x * S, L), k1 = min(k0 + S, L);
     P3 id; id.t[0] = id.t[1] = id.t[2] = 0; id.q[0] = 1; id.q[1] = id.q[2] = id.q[3] = 0;
     P3 mine = id;
     for (int k = k0; k < k1; ++k) {
@@ -255,10 +270,14 @@ __global__ void __launch_bounds__(CL_NT) cl3_dead_reckon(const double* __restric
         P3 zz, r; se3_rel(zi, id, zz); se3_mul(cur, zz, r); q_normalize(r.q); cur = r;
         store_pose(pose + 7 * (size_t)(start + k + 1), cur);
     }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(CL_NT) cl3_dead_reckon(const double* __restrict__ odom49, int start, int n, double* pose, double* stage) {
+    cl3_dead_reckon_cta(odom49, start, n, pose, stage);
 }
 __global__ void cl3_set_origin(double* pose) { if (threadIdx.x == 0) { pose[0] = 0; pose[1] = 0; pose[2] = 0; pose[3] = 1; pose[4] = 0; pose[5] = 0; pose[6] = 0; } }
 // (t, q = w x y z) -> g2o order x y z qx qy qz qw
-__global__ void cl3_export_poses(const double* __restrict__ pose, int n, double* __restrict__ out) {
+__global__ void cl3_export_poses(const double* pose, int n, double* out) {
     for (int i = threadIdx.x + blockIdx.x * blockDim.x; i < n; i += blockDim.x * gridDim.x) {
         const double* p = pose + 7 * (size_t)i; double* o = out + 7 * (size_t)i;
         const double sg = p[3] < 0 ? -1.0 : 1.0;      // same rotation, w >= 0 like g2o's writer

@@ -6,10 +6,8 @@
 
 #include "launch_common.hpp"
 #include "host_state.hpp"
-#include "cluster_se2.cuh"
-#include "cluster_se3.cuh"
+#include "stream_solver.cuh"
 #include "comm.hpp"
-#include <cusolverDn.h>
 
 using namespace ipcb;
 
@@ -48,15 +46,15 @@ struct ipc_handle {
     double* d_pose = nullptr;         // AoS[5] x n: x y theta cos sin — the vertex estimates of the IPC object
     double* d_odom9_raw = nullptr;    // odometry records with the information as given (final optimisation only)
     const double* cl_odom = nullptr;  // records the cluster kernels read: d_odom9, or d_odom9_raw during ipc_final_optimize
-    cusolverDnHandle_t solver = nullptr;
-    int cl_Lcap = 0, cl_Kcap = 0, cl_work_n = 0;
+    int cl_Lcap = 0, cl_Kcap = 0, cl_grid = 0;                // capacities (window edges, loops) and the cooperative grid (one CTA per SM)
     ClBuffers clB[2] = {};
-    double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_work = nullptr;
-    int* cl_info = nullptr;
+    double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_lg = nullptr;
+    int *cl_ev_ptr = nullptr, *cl_ev_idx = nullptr;           // loop end points by window position (ClEvents)
+    unsigned* cl_bar = nullptr;                               // grid barrier counter + control words of the persistent solver
+    double *cl_out = nullptr, *cl_hout = nullptr;             // per-check results (device / pinned host)
     void* cl_loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the current cluster
     double* cl_stage = nullptr;       // SE(3) dead-reckoning staging (CL_NT poses)
     double* d_odom49_raw = nullptr;   // SE(3) records with the information as given (final optimisation)
-    double* cl_hres = nullptr;        // pinned
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)
     bool ev_valid = false;
     uint32_t* d_gather = nullptr; size_t gather_words = 0;   // [world][words_per_rank] verdict words of a sharded batch

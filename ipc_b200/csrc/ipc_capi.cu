@@ -89,7 +89,7 @@ const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
 }  // namespace
 
 namespace { int size_scratch(ipc_handle* h); }
-extern "C" { namespace { int cl_ensure(ipc_handle* h, int L, int K); } }
+extern "C" { namespace { int stream_solver_setup(ipc_handle* h); } }
 
 
 namespace {
@@ -248,20 +248,12 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
             cl3_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom49, 0, n_poses, h->d_pose, h->cl_stage);
         }
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMallocHost(&h->cl_hres, sizeof(double) * CL_NRES));
         CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES));
-        CUDA_TRY(cudaMalloc(&h->cl_info, sizeof(int)));
-        if (cusolverDnCreate(&h->solver) != CUSOLVER_STATUS_SUCCESS) return fail(IPC_ERR_CUDA, "cusolverDnCreate failed");
-        cusolverDnSetStream(h->solver, h->stream);
-        {   // warm cuSOLVER up here (its first potrf loads modules for seconds) so that the first agreementCheck is not charged for it
-            int rcw = cl_ensure(h, 16, 1);
-            if (rcw != IPC_OK) return rcw;
-            const double eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-            CUDA_TRY(cudaMemcpyAsync(h->cl_S, eye, sizeof(eye), cudaMemcpyHostToDevice, h->stream));
-            CUDA_TRY(cudaMemcpyAsync(h->cl_z, eye, 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-            cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, 3, h->cl_S, 3, h->cl_work, h->cl_work_n, h->cl_info);
-            cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, 3, 1, h->cl_S, 3, h->cl_z, 3, h->cl_info);
-        }
+        CUDA_TRY(cudaMalloc(&h->cl_bar, sizeof(unsigned) * 4));
+        CUDA_TRY(cudaMalloc(&h->cl_out, sizeof(double) * 8));
+        CUDA_TRY(cudaMallocHost(&h->cl_hout, sizeof(double) * 8));
+        int rcs = stream_solver_setup(h);
+        if (rcs != IPC_OK) return rcs;
         CUDA_TRY(cudaStreamSynchronize(h->stream));
     }
     CUDA_TRY(cudaEventCreate(&h->ev_k0));
@@ -276,12 +268,11 @@ void ipc_destroy(ipc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_odom49); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch); cudaFree(h->d_gather);
-    cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_work);
-    cudaFree(h->cl_info); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
+    cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_lg);
+    cudaFree(h->cl_bar); cudaFree(h->cl_out); cudaFree(h->cl_ev_ptr); cudaFree(h->cl_ev_idx); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
     for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
     delete h->comm;
-    if (h->cl_hres) cudaFreeHost(h->cl_hres);
-    if (h->solver) cusolverDnDestroy(h->solver);
+    if (h->cl_hout) cudaFreeHost(h->cl_hout);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ev_k0) cudaEventDestroy(h->ev_k0);
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
@@ -426,12 +417,23 @@ int ipc_get_consensus(ipc_handle* h, int* from_to, int capacity) {
 
 namespace {
 
+// the persistent stream-solver kernels (stream_solver.cuh): opt in to the shared memory they may need, size the cooperative grid
+int stream_solver_setup(ipc_handle* h) {
+    CUDA_TRY(cudaFuncSetAttribute(stream_check_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(stream_check_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+    if (!coop) return fail(IPC_ERR_UNSUPPORTED, "device does not support cooperative launches");
+    h->cl_grid = h->n_sm;          // one CTA of CL_NT threads per SM
+    return IPC_OK;
+}
+
 int cl_ensure(ipc_handle* h, int L, int K) {
     const int PW = h->dim == 2 ? 5 : 7, NPQ = h->dim == 2 ? NPRE : se3::NP3, DQ = h->dim == 2 ? 3 : 6, LTW = h->dim == 2 ? 12 : CL3_LT;
     if (L > h->cl_Lcap) {
         int cap = std::max(L, 256);
         for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); h->clB[q].W = h->clB[q].T = h->clB[q].P = h->clB[q].chi_e = nullptr; }
-        cudaFree(h->cl_G); cudaFree(h->cl_H); h->cl_G = h->cl_H = nullptr; h->cl_Lcap = 0;
+        cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_ev_ptr); h->cl_G = h->cl_H = nullptr; h->cl_ev_ptr = nullptr; h->cl_Lcap = 0;
         for (int q = 0; q < 2; ++q) {
             CUDA_TRY(cudaMalloc(&h->clB[q].W, sizeof(double) * PW * (size_t)(cap + 1)));
             CUDA_TRY(cudaMalloc(&h->clB[q].T, sizeof(double) * NPQ * (size_t)cap));
@@ -440,142 +442,71 @@ int cl_ensure(ipc_handle* h, int L, int K) {
         }
         CUDA_TRY(cudaMalloc(&h->cl_G, sizeof(double) * DQ * (size_t)(cap + 1)));
         CUDA_TRY(cudaMalloc(&h->cl_H, sizeof(double) * DQ * (size_t)(cap + 1)));
+        CUDA_TRY(cudaMalloc(&h->cl_ev_ptr, sizeof(int) * (size_t)(cap + 3)));
         h->cl_Lcap = cap;
     }
     if (K > h->cl_Kcap) {
         int cap = std::max(K + K / 2, 64);
-        for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].lt); h->clB[q].lt = nullptr; }
-        cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_loops); cudaFree(h->cl_work); h->cl_S = h->cl_z = h->cl_work = nullptr; h->cl_loops = nullptr; h->cl_Kcap = 0;
-        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&h->clB[q].lt, sizeof(double) * LTW * (size_t)cap));
-        CUDA_TRY(cudaMalloc(&h->cl_S, sizeof(double) * DQ * DQ * (size_t)cap * cap));
-        CUDA_TRY(cudaMalloc(&h->cl_z, sizeof(double) * DQ * (size_t)cap));
-        CUDA_TRY(cudaMalloc(&h->cl_loops, std::max(sizeof(ClLoop), sizeof(ClLoop3)) * (size_t)cap));
-        int lwork = 0;
-        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, DQ * cap, h->cl_S, DQ * cap, &lwork) != CUSOLVER_STATUS_SUCCESS)
-            return fail(IPC_ERR_CUDA, "cusolverDnDpotrf_bufferSize failed");
-        CUDA_TRY(cudaMalloc(&h->cl_work, sizeof(double) * (size_t)std::max(lwork, 1)));
-        h->cl_work_n = lwork; h->cl_Kcap = cap;
-    }
-    return IPC_OK;
-}
-
-int cl_read(ipc_handle* h) {   // device scalars -> pinned host buffer
-    CUDA_TRY(cudaMemcpyAsync(h->cl_hres, h->cl_res, sizeof(double) * CL_NRES, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
-    return IPC_OK;
-}
-
-// isAgreeingWithCurrentState on the window [lo, hi] with the K loops already uploaded (the candidate is the last one)
-int cl_window_check(ipc_handle* h, int lo, int hi, int K, double th, int iter_base, bool* ok_out, ipc_check_info* info, int* cur_buf, bool exact_iters = false) {
-    const bool d2 = h->dim == 2;
-    const double* odom9 = h->cl_odom ? h->cl_odom : (d2 ? h->d_odom9 : h->d_odom49);
-    const ClLoop* loops2 = static_cast<const ClLoop*>(h->cl_loops);
-    const ClLoop3* loops3 = static_cast<const ClLoop3*>(h->cl_loops);
-    const int L = hi - lo, Lcap = h->cl_Lcap;
-    cudaStream_t st = h->stream;
-    int cur = 0;
-    double* res = h->cl_res;
-    const double* hr = h->cl_hres;
-    if (d2) {
-        cl_load_window<<<16, 256, 0, st>>>(h->d_pose, lo, L, h->clB[0].W);
-        cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[cur], res);
-        cl_loops<<<1, 256, 0, st>>>(loops2, K, h->clB[cur], res);
-    } else {
-        cl_copy<<<16, 256, 0, st>>>(h->d_pose + 7 * (size_t)lo, h->clB[0].W, 7LL * (L + 1));
-        cl3_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[cur], res);
-        cl3_loops<<<1, 256, 0, st>>>(loops3, K, h->clB[cur], res);
-    }
-    CUDA_TRY(cudaGetLastError());
-    int rc = cl_read(h); if (rc != IPC_OK) return rc;
-    double cur_chi = hr[0] + hr[2], cur_max = std::max(hr[1], hr[3]), cand_chi = hr[4];
-    int max_iter = iter_base;
-    if (!exact_iters && L + K > 100) max_iter *= 5;        // src/consensus_utils.cpp:12-13
-    double delta = 1e4;
-    int iterations = 0, evals = 0;
-    bool ok = true;
-    const int n3 = (d2 ? 3 : 6) * K;
-    for (int it = 0; it < max_iter && ok; ++it) {
-        // ---- Gauss-Newton step of the current linearisation
-        {
-            const long long nb = ((long long)K * K + 255) / 256;
-            if (d2) cl_assemble<<<(unsigned)nb, 256, 0, st>>>(loops2, K, Lcap, h->clB[cur], h->cl_S, h->cl_z);
-            else cl3_assemble<<<(unsigned)nb, 256, 0, st>>>(loops3, K, Lcap, h->clB[cur], h->cl_S, h->cl_z);
-            if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, n3, h->cl_S, n3, h->cl_work, h->cl_work_n, h->cl_info) != CUSOLVER_STATUS_SUCCESS)
-                return fail(IPC_ERR_CUDA, "cusolverDnDpotrf failed");
-            if (cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, n3, 1, h->cl_S, n3, h->cl_z, n3, h->cl_info) != CUSOLVER_STATUS_SUCCESS)
-                return fail(IPC_ERR_CUDA, "cusolverDnDpotrs failed");
-            if (d2) cl_gn_step<<<1, CL_NT, 0, st>>>(loops2, K, L, Lcap, h->clB[cur], h->cl_z, h->cl_H, res);
-            else cl3_gn_step<<<1, CL_NT, 0, st>>>(loops3, K, L, Lcap, h->clB[cur], h->cl_z, h->cl_H, res);
-            CUDA_TRY(cudaGetLastError());
-            rc = cl_read(h); if (rc != IPC_OK) return rc;
+        const size_t n_pad = ((size_t)DQ * cap + CH_NB - 1) / CH_NB * CH_NB;
+        if (stream_smem_bytes((int)n_pad) > 226 * 1024) {
+            cap = K; 
+            const size_t np2 = ((size_t)DQ * cap + CH_NB - 1) / CH_NB * CH_NB;
+            if (stream_smem_bytes((int)np2) > 226 * 1024) return fail(IPC_ERR_UNSUPPORTED, "cluster of " + std::to_string(K) + " loops exceeds the dense force-system solver (DESIGN.md)");
         }
-        const double hh = hr[5], hgnNorm = std::sqrt(hh), gn_gain = hr[6];
-        if (!std::isfinite(hgnNorm)) { ok = false; ++iterations; break; }     // factorisation broke down (g2o: Fail)
-        bool have_sd = false, good = false;
-        double bb = 0, bh = 0, bHb = 0, alpha = 0, hsdNorm = 0;
-        int tries = 0;
-        do {
-            ++tries;
-            double c1 = 0, c2 = 1, linearGain = gn_gain;
-            const bool trial_gn = hgnNorm < delta;
-            if (!trial_gn) {
-                if (!have_sd) {
-                    if (d2) {
-                        cl_grad_odom<<<1, CL_NT, 0, st>>>(odom9, lo, L, h->clB[cur], h->cl_G);
-                        cl_grad_loops<<<1, 32, 0, st>>>(loops2, K, h->clB[cur], h->cl_G);
-                        cl_sd_scalars<<<1, CL_NT, 0, st>>>(odom9, loops2, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
-                    } else {
-                        cl3_grad_odom<<<1, CL_NT, 0, st>>>(odom9, lo, L, h->clB[cur], h->cl_G);
-                        cl3_grad_loops<<<1, 32, 0, st>>>(loops3, K, h->clB[cur], h->cl_G);
-                        cl3_sd_scalars<<<1, CL_NT, 0, st>>>(odom9, loops3, K, lo, L, h->clB[cur], h->cl_G, h->cl_H, res);
-                    }
-                    CUDA_TRY(cudaGetLastError());
-                    rc = cl_read(h); if (rc != IPC_OK) return rc;
-                    bb = hr[7]; bh = hr[8]; bHb = hr[9];
-                    alpha = bb / bHb; hsdNorm = alpha * std::sqrt(bb); have_sd = true;
-                }
-                if (hsdNorm > delta) { c1 = delta / hsdNorm * alpha; c2 = 0; }
-                else {
-                    const double hsdSq = alpha * alpha * bb;
-                    const double c = alpha * bh - hsdSq, bma = hh - 2 * alpha * bh + hsdSq;
-                    double beta;
-                    if (c <= 0) beta = (-c + std::sqrt(c * c + bma * (delta * delta - hsdSq))) / bma;
-                    else beta = (delta * delta - hsdSq) / (c + std::sqrt(c * c + bma * (delta * delta - hsdSq)));
-                    c1 = alpha * (1 - beta); c2 = beta;
-                }
-                linearGain = -(c1 * c1 * bHb + 2 * c1 * c2 * bb + c2 * c2 * bh) + 2 * (c1 * bb + c2 * bh);
-            }
-            const int nxt = cur ^ 1;
-            if (d2) {
-                cl_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
-                cl_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[nxt], res);
-                cl_loops<<<1, 256, 0, st>>>(loops2, K, h->clB[nxt], res);
-            } else {
-                cl3_apply<<<1, CL_NT, 0, st>>>(L, h->clB[cur].W, h->cl_G, h->cl_H, c1, c2, h->clB[nxt].W, res);
-                cl3_linearize<<<1, CL_NT, 0, st>>>(odom9, lo, L, Lcap, h->clB[nxt], res);
-                cl3_loops<<<1, 256, 0, st>>>(loops3, K, h->clB[nxt], res);
-            }
-            CUDA_TRY(cudaGetLastError());
-            rc = cl_read(h); if (rc != IPC_OK) return rc;
-            ++evals;
-            const double newChi = hr[0] + hr[2], hdlNorm = std::sqrt(hr[10]);
-            const double rawGain = linearGain;
-            if (std::fabs(linearGain) < 1e-12) linearGain = 1e-12;
-            const double rho = (cur_chi - newChi) / linearGain;
-            if (rho > 0) { good = true; cur = nxt; cur_chi = newChi; cur_max = std::max(hr[1], hr[3]); cand_chi = hr[4]; }
-            if (rho > 0.75) delta = std::max(delta, 3 * hdlNorm);
-            else if (rho < 0.25) delta *= 0.5;
-            if (!good) {
-                if (trial_gn) while (tries < h->max_tries && hgnNorm < delta) { ++tries; ++evals; delta *= 0.5; }
-                if (h->noise_eps > 0 && rawGain <= h->noise_eps * cur_chi + 1e-300) tries = h->max_tries;
-            }
-        } while (!good && tries < h->max_tries);
-        ++iterations;
-        if (tries >= h->max_tries || !good) ok = false;
+        for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].lt); h->clB[q].lt = nullptr; }
+        cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_loops); cudaFree(h->cl_lg); cudaFree(h->cl_ev_idx);
+        h->cl_S = h->cl_z = h->cl_lg = nullptr; h->cl_loops = nullptr; h->cl_ev_idx = nullptr; h->cl_Kcap = 0;
+        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&h->clB[q].lt, sizeof(double) * LTW * (size_t)cap));
+        const size_t np = ((size_t)DQ * cap + CH_NB - 1) / CH_NB * CH_NB;
+        CUDA_TRY(cudaMalloc(&h->cl_S, sizeof(double) * (np + CH_NB) * np));
+        CUDA_TRY(cudaMalloc(&h->cl_z, sizeof(double) * np));
+        CUDA_TRY(cudaMalloc(&h->cl_lg, sizeof(double) * 2 * DQ * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&h->cl_ev_idx, sizeof(int) * 2 * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&h->cl_loops, std::max(sizeof(ClLoop), sizeof(ClLoop3)) * (size_t)cap));
+        h->cl_Kcap = cap;
     }
-    *ok_out = !(cur_max > th);
-    *cur_buf = cur;
-    if (info) { info->max_chi2 = cur_max; info->cand_chi2 = cand_chi; info->sum_chi2 = cur_chi; info->iterations = iterations; info->evals = evals; info->window_len = L; info->n_loops = K; }
+    return IPC_OK;
+}
+
+// isAgreeingWithCurrentState on the window [lo, hi] with the K loops already uploaded (the candidate is the last one): one
+// cooperative launch of the persistent solver, one synchronisation. ab: interval [a, b) of every loop in local vertex indices.
+// commit: 1 = agreementCheck (store the window + propagateCurrentGuess on accept), 2 = final optimisation (always store).
+int cl_window_check(ipc_handle* h, int lo, int hi, int K, const std::vector<std::pair<int, int>>& ab, double th, int iter_base, bool* ok_out,
+                    ipc_check_info* info, int commit, bool exact_iters = false) {
+    const bool d2 = h->dim == 2;
+    const int L = hi - lo, DQ = d2 ? 3 : 6;
+    cudaStream_t st = h->stream;
+    // loop end points by window position, loop order within a position (ClEvents)
+    std::vector<int> ptr(L + 3, 0), idx(2 * (size_t)K);
+    for (int l = 0; l < K; ++l) { ++ptr[ab[l].first + 1]; ++ptr[ab[l].second + 1]; }
+    for (int j = 0; j <= L + 1; ++j) ptr[j + 1] += ptr[j];
+    {
+        std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+        for (int l = 0; l < K; ++l) { idx[fill[ab[l].first]++] = (l << 1) | 1; idx[fill[ab[l].second]++] = (l << 1); }
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->cl_ev_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->cl_ev_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(h->cl_bar, 0, sizeof(unsigned) * 4, st));
+    StreamArgs A{};
+    A.dim = h->dim; A.lo = lo; A.L = L; A.K = K; A.n_poses = h->n; A.Lcap = h->cl_Lcap;
+    A.odom = h->cl_odom ? h->cl_odom : (d2 ? h->d_odom9 : h->d_odom49);
+    A.odom_commit = d2 ? h->d_odom9 : h->d_odom49;
+    A.pose = h->d_pose; A.loops = h->cl_loops; A.ev = ClEvents{h->cl_ev_ptr, h->cl_ev_idx};
+    A.B[0] = h->clB[0]; A.B[1] = h->clB[1]; A.G = h->cl_G; A.H = h->cl_H; A.lg = h->cl_lg;
+    A.n_pad = (DQ * K + CH_NB - 1) / CH_NB * CH_NB; A.ld = A.n_pad + CH_NB; A.S = h->cl_S; A.z = h->cl_z;
+    A.res = h->cl_res; A.stage3 = h->cl_stage; A.bar = h->cl_bar; A.ctl = reinterpret_cast<int*>(h->cl_bar + 1);
+    A.th = th; A.max_iter = iter_base;
+    if (!exact_iters && L + K > 100) A.max_iter *= 5;          // src/consensus_utils.cpp:12-13
+    A.max_tries = h->max_tries; A.noise_eps = h->noise_eps; A.commit = commit; A.out = h->cl_out;
+    void* args[] = {&A};
+    const size_t smem = stream_smem_bytes(A.n_pad);
+    const void* fn = d2 ? (const void*)stream_check_kernel<2> : (const void*)stream_check_kernel<3>;
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(h->cl_grid), dim3(CL_NT), args, smem, st));
+    CUDA_TRY(cudaMemcpyAsync(h->cl_hout, h->cl_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const double* o = h->cl_hout;
+    *ok_out = o[0] != 0.0;
+    if (info) { info->max_chi2 = o[1]; info->cand_chi2 = o[2]; info->sum_chi2 = o[3]; info->iterations = (int)o[4]; info->evals = (int)o[5]; info->window_len = L; info->n_loops = K; }
     return IPC_OK;
 }
 
@@ -622,20 +553,16 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
         if (!okf) return fail(IPC_ERR_ARG, "loop edge with a zero quaternion or a singular information matrix");
         CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops3v.data(), sizeof(ClLoop3) * K, cudaMemcpyHostToDevice, h->stream));
     }
-    bool ok = false; int cur = 0;
-    rc = cl_window_check(h, lo, hi, K, th, ib, &ok, out_info, &cur);
+    std::vector<std::pair<int, int>> ab(K);
+    for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; ab[i] = {std::min(e.from, e.to) - lo, std::max(e.from, e.to) - lo}; }
+    ab[K - 1] = {std::min(from, to) - lo, std::max(from, to) - lo};
+    bool ok = false;
+    // accept = discard + push_back + propagateCurrentGuess (src/consensus.cpp:69-71), done by the kernel; a rejection leaves d_pose
+    // untouched (restore): the solve works on a copy of the window
+    rc = cl_window_check(h, lo, hi, K, ab, th, ib, &ok, out_info, /*commit=*/1);
     if (rc != IPC_OK) return rc;
     *accepted = ok ? 1 : 0;
-    if (ok) {   // discard + push_back + propagateCurrentGuess (src/consensus.cpp:69-71); a rejection leaves d_pose untouched (restore)
-        if (h->dim == 2) {
-            cl_store_window<<<16, 256, 0, h->stream>>>(h->d_pose, lo, hi - lo, h->clB[cur].W);
-            cl_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom9, hi, h->n, h->d_pose);
-        } else {
-            cl_copy<<<16, 256, 0, h->stream>>>(h->clB[cur].W, h->d_pose + 7 * (size_t)lo, 7LL * (hi - lo + 1));
-            cl3_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom49, hi, h->n, h->d_pose, h->cl_stage);
-        }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (ok) {
         HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + h->mw); e.info.assign(info, info + h->d * h->d);
         h->hs.cns.push_back(std::move(e));
     }
@@ -697,14 +624,13 @@ int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* ite
         }
         CUDA_TRY(cudaMemcpy(h->cl_loops, loops.data(), sizeof(ClLoop3) * K, cudaMemcpyHostToDevice));
     }
-    bool ok = false; int cur = 0; ipc_check_info ci{};
+    std::vector<std::pair<int, int>> ab(K);
+    for (int i = 0; i < K; ++i) { const HostEdge& e = h->hs.cns[i]; ab[i] = {std::min(e.from, e.to) - lo, std::max(e.from, e.to) - lo}; }
+    bool ok = false; ipc_check_info ci{};
     h->cl_odom = d2 ? h->d_odom9_raw : h->d_odom49_raw;        // odometry information / s_factor (src/simulation.cpp:55-56)
-    rc = cl_window_check(h, lo, hi, K, 0.0, max_iterations, &ok, &ci, &cur, /*exact_iters=*/true);
+    rc = cl_window_check(h, lo, hi, K, ab, 0.0, max_iterations, &ok, &ci, /*commit=*/2, /*exact_iters=*/true);
     h->cl_odom = nullptr;
     if (rc != IPC_OK) return rc;
-    cl_copy<<<16, 256, 0, h->stream>>>(h->clB[cur].W, h->d_pose, (long long)(d2 ? 5 : 7) * (hi - lo + 1));
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
     if (chi2) *chi2 = ci.sum_chi2;
     if (iterations) *iterations = ci.iterations;
     return IPC_OK;
