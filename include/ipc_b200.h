@@ -86,6 +86,12 @@ int ipc_get_poses(ipc_handle* h, double* out);
  * chain + the consensus set. chi2 / iterations may be NULL. */
 int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* iterations);
 
+/* Diagnostics of the sequential stream (ipc_agreement_check / ipc_final_optimize run as one persistent kernel per call):
+ * out16[0..7] = seconds (nominal SM clock) spent by the window CTA in: setup, assembly of the force system, Cholesky
+ * factorisation, back-substitution, Gauss-Newton step, steepest-descent pass, trial states, commit; out16[8..10] = calls,
+ * factorisations, trial states since the last reset. Non-reference. */
+int ipc_stream_profile(ipc_handle* h, double* out16, int reset);
+
 /* ---- batched, independent checks: the throughput path --------------------------------------
  * A check is one isAgreeingWithCurrentState test (src/consensus_utils.cpp:6-22) on a window that
  * starts from the dead-reckoned state of a fresh IPC object: with member < 0 it is exactly

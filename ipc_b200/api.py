@@ -24,7 +24,7 @@ SYMBOLS = ["ipc_last_error", "ipc_device_count", "ipc_create", "ipc_destroy", "i
            "ipc_add_edge", "ipc_consensus_size", "ipc_get_consensus", "ipc_get_poses", "ipc_final_optimize", "ipc_set_candidates", "ipc_check_batch",
            "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_last_kernel_ms", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option",
            "ipc_comm_unique_id", "ipc_comm_init", "ipc_comm_info", "ipc_check_batch_sharded", "ipc_check_batch_sharded_dev",
-           "ipc_consistency_matrix_sharded"]
+           "ipc_consistency_matrix_sharded", "ipc_stream_profile"]
 
 
 class IpcError(RuntimeError):
@@ -73,6 +73,7 @@ def lib():
         L.ipc_consistency_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.ipc_greedy_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ipc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.ipc_stream_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ipc_comm_unique_id.argtypes = [C.c_void_p]
         L.ipc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ipc_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
@@ -178,6 +179,15 @@ class IPC:
         chi2, it = C.c_double(0), C.c_int(0)
         _chk(lib().ipc_final_optimize(self._h, int(max_iterations), C.byref(chi2), C.byref(it)))
         return chi2.value, it.value
+
+    def stream_profile(self, reset: bool = False) -> dict:
+        o = np.zeros(16)
+        _chk(lib().ipc_stream_profile(self._h, _p(o), int(reset)))
+        names = ["setup", "assemble", "factor", "back_substitute", "gn_step", "steepest_descent", "trial_states", "commit"]
+        d = {f"{k}_s": float(o[i]) for i, k in enumerate(names)}
+        d.update(calls=int(o[8]), factorisations=int(o[9]), trial_states=int(o[10]))
+        d.update({f"factor_{k}_s": float(o[11 + i]) for i, k in enumerate(["diag", "panel", "barrier1", "update", "barrier2"])})
+        return d
 
     # ---- batched path --------------------------------------------------------------------------
     def set_candidates(self, frm, to, meas, info):

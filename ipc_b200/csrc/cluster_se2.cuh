@@ -15,7 +15,7 @@
 
 namespace ipcb {
 
-constexpr int CL_NT = 1024;     // threads per CTA of the stream solver
+constexpr int CL_NT = 512;      // threads per CTA of the stream solver (128 registers per thread)
 constexpr int CL_NRES = 16;     // doubles in the result buffer
 
 struct ClLoop {                 // one loop edge of the cluster, local indices
@@ -143,9 +143,9 @@ __device__ __noinline__ void cl_loops(const ClLoop* __restrict__ loops, int K, C
 
 // GRID: lower block triangle of S (3K x 3K, column-major with leading dimension ld) and the right-hand side, stored as the extra
 // matrix row `rhs_row` (the factorisation then forward-substitutes it for free, stream_solver.cuh).
-__device__ __forceinline__ void cl_assemble_grid(const ClLoop* __restrict__ loops, int K, int Lcap, ClBuffers B, double* Smat, int ld, int rhs_row) {
+__device__ __forceinline__ void cl_assemble_grid(const ClLoop* __restrict__ loops, int K, int Lcap, ClBuffers B, double* Smat, int ld, int rhs_row, int grank, int gsize) {
     const long long total = (long long)K * (K + 1) / 2;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (long long idx = (long long)grank * blockDim.x + threadIdx.x; idx < total; idx += (long long)gsize * blockDim.x) {
         // idx -> (l, m) with l >= m: row block l, column block m
         int l = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
         while ((long long)l * (l + 1) / 2 > idx) --l;

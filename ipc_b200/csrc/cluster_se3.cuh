@@ -64,10 +64,10 @@ __device__ __noinline__ void cl3_loops(const ClLoop3* __restrict__ loops, int K,
 }
 
 // GRID: lower block triangle of S (6K x 6K, column-major, leading dimension ld) + the right-hand side as matrix row `rhs_row`
-__device__ __forceinline__ void cl3_assemble_grid(const ClLoop3* __restrict__ loops, int K, int Lcap, ClBuffers B, double* Smat, int ld, int rhs_row) {
+__device__ __forceinline__ void cl3_assemble_grid(const ClLoop3* __restrict__ loops, int K, int Lcap, ClBuffers B, double* Smat, int ld, int rhs_row, int grank, int gsize) {
     using namespace se3;
     const long long total = (long long)K * (K + 1) / 2;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    for (long long idx = (long long)grank * blockDim.x + threadIdx.x; idx < total; idx += (long long)gsize * blockDim.x) {
         int l = (int)((sqrt(8.0 * (double)idx + 1.0) - 1.0) * 0.5);
         while ((long long)l * (l + 1) / 2 > idx) --l;
         while ((long long)(l + 1) * (l + 2) / 2 <= idx) ++l;

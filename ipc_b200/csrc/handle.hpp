@@ -51,6 +51,9 @@ struct ipc_handle {
     double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_lg = nullptr;
     int *cl_ev_ptr = nullptr, *cl_ev_idx = nullptr;           // loop end points by window position (ClEvents)
     unsigned* cl_bar = nullptr;                               // grid barrier counter + control words of the persistent solver
+    StreamArgs* cl_args = nullptr;                            // kernel arguments of the persistent solver, one record per group
+    unsigned long long* cl_prof = nullptr;                    // phase cycle counters of the persistent solver (ipc_stream_profile)
+    long long cl_n_checks = 0, cl_n_fact = 0, cl_n_trial = 0;
     double *cl_out = nullptr, *cl_hout = nullptr;             // per-check results (device / pinned host)
     void* cl_loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the current cluster
     double* cl_stage = nullptr;       // SE(3) dead-reckoning staging (CL_NT poses)

@@ -250,8 +250,11 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES));
         CUDA_TRY(cudaMalloc(&h->cl_bar, sizeof(unsigned) * 4));
-        CUDA_TRY(cudaMalloc(&h->cl_out, sizeof(double) * 8));
-        CUDA_TRY(cudaMallocHost(&h->cl_hout, sizeof(double) * 8));
+        CUDA_TRY(cudaMalloc(&h->cl_prof, sizeof(unsigned long long) * 16));
+        CUDA_TRY(cudaMemset(h->cl_prof, 0, sizeof(unsigned long long) * 16));
+        CUDA_TRY(cudaMalloc(&h->cl_out, sizeof(double) * 16));
+        CUDA_TRY(cudaMallocHost(&h->cl_hout, sizeof(double) * 16));
+        CUDA_TRY(cudaMalloc(&h->cl_args, sizeof(StreamArgs) * 16));
         int rcs = stream_solver_setup(h);
         if (rcs != IPC_OK) return rcs;
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -269,7 +272,7 @@ void ipc_destroy(ipc_handle* h) {
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_odom49); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch); cudaFree(h->d_gather);
     cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_lg);
-    cudaFree(h->cl_bar); cudaFree(h->cl_out); cudaFree(h->cl_ev_ptr); cudaFree(h->cl_ev_idx); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
+    cudaFree(h->cl_bar); cudaFree(h->cl_args); cudaFree(h->cl_prof); cudaFree(h->cl_out); cudaFree(h->cl_ev_ptr); cudaFree(h->cl_ev_idx); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
     for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
     delete h->comm;
     if (h->cl_hout) cudaFreeHost(h->cl_hout);
@@ -497,15 +500,18 @@ int cl_window_check(ipc_handle* h, int lo, int hi, int K, const std::vector<std:
     A.res = h->cl_res; A.stage3 = h->cl_stage; A.bar = h->cl_bar; A.ctl = reinterpret_cast<int*>(h->cl_bar + 1);
     A.th = th; A.max_iter = iter_base;
     if (!exact_iters && L + K > 100) A.max_iter *= 5;          // src/consensus_utils.cpp:12-13
-    A.max_tries = h->max_tries; A.noise_eps = h->noise_eps; A.commit = commit; A.out = h->cl_out;
-    void* args[] = {&A};
+    A.max_tries = h->max_tries; A.noise_eps = h->noise_eps; A.commit = commit; A.out = h->cl_out; A.prof = h->cl_prof;
+    CUDA_TRY(cudaMemcpyAsync(h->cl_args, &A, sizeof(A), cudaMemcpyHostToDevice, st));
+    const StreamArgs* d_args = h->cl_args; int group_size = h->cl_grid;
+    void* args[] = {&d_args, &group_size};
     const size_t smem = stream_smem_bytes(A.n_pad);
     const void* fn = d2 ? (const void*)stream_check_kernel<2> : (const void*)stream_check_kernel<3>;
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(h->cl_grid), dim3(CL_NT), args, smem, st));
-    CUDA_TRY(cudaMemcpyAsync(h->cl_hout, h->cl_out, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(h->cl_hout, h->cl_out, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const double* o = h->cl_hout;
     *ok_out = o[0] != 0.0;
+    h->cl_n_fact += (long long)o[6]; h->cl_n_trial += (long long)o[7]; ++h->cl_n_checks;
     if (info) { info->max_chi2 = o[1]; info->cand_chi2 = o[2]; info->sum_chi2 = o[3]; info->iterations = (int)o[4]; info->evals = (int)o[5]; info->window_len = L; info->n_loops = K; }
     return IPC_OK;
 }
@@ -633,6 +639,20 @@ int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* ite
     if (rc != IPC_OK) return rc;
     if (chi2) *chi2 = ci.sum_chi2;
     if (iterations) *iterations = ci.iterations;
+    return IPC_OK;
+}
+
+int ipc_stream_profile(ipc_handle* h, double* out16, int reset) {
+    if (!h || !out16) return fail(IPC_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long c[16];
+    CUDA_TRY(cudaMemcpy(c, h->cl_prof, sizeof(c), cudaMemcpyDeviceToHost));
+    int khz = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+    for (int i = 0; i < 8; ++i) out16[i] = (double)c[i] / ((double)khz * 1e3);      // seconds at the nominal SM clock
+    out16[8] = (double)h->cl_n_checks; out16[9] = (double)h->cl_n_fact; out16[10] = (double)h->cl_n_trial;
+    for (int i = 11; i < 16; ++i) out16[i] = (double)c[i - 3] / ((double)khz * 1e3);    // factorisation sub-phases: diagonal block, panel solve, barrier, update, barrier
+    if (reset) { CUDA_TRY(cudaMemset(h->cl_prof, 0, sizeof(c))); h->cl_n_checks = h->cl_n_fact = h->cl_n_trial = 0; }
     return IPC_OK;
 }
 

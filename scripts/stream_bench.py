@@ -10,6 +10,9 @@ scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
 with_oracle = "--oracle" in sys.argv
 g, cfg = synth.make_config(name, scale=scale)
 order = g.time_order()
+for a in sys.argv:
+    if a.startswith("--limit="):
+        order = order[: int(a.split("=")[1])]
 t = time.perf_counter()
 ipc = api.IPC.from_graph(g, cfg, candidates=False)
 create_s = time.perf_counter() - t
@@ -25,6 +28,7 @@ tp = int((acc & truth).sum()); fp = int((acc & ~truth).sum()); fn = int((~acc & 
 out = {"config": name, "scale": scale, "create_s": create_s, "n_poses": g.n_poses, "candidates": len(order), "gpu_stream_s": dt, "gpu_checks_per_s": len(order) / dt,
        "accepted": int(acc.sum()), "precision": tp / max(1, tp + fp), "recall": tp / max(1, tp + fn), "K_median": float(np.median(K)), "K_max": int(K.max()),
        "L_median": float(np.median(L)), "evals_mean": float(ev.mean())}
+out["profile"] = ipc.stream_profile()
 if with_oracle:
     from oracle import pyoracle as po
     t = time.perf_counter(); oacc, orep = po.OracleIPC(g, cfg, noise_exit=True).run_stream(order); odt = time.perf_counter() - t
