@@ -173,7 +173,7 @@ struct SimResult { int tp = 0, fp = 0, tn = 0, fn = 0; float precision = 0, reca
 inline void check(int rc) { if (rc != IPC_OK) throw std::runtime_error(std::string("ipc_b200: ") + ipc_last_error()); }
 
 // simulating_incremental_data (src/simulation.cpp:8-108) over the C ABI
-inline SimResult simulate(const Config& cfg, const Problem& p, int device, bool final_pgo, bool quiet) {
+inline SimResult simulate(const Config& cfg, const Problem& p, int device, bool final_pgo, bool quiet, bool one_by_one = false) {
     (void)readSolutionFile(cfg.ground_truth, p.dim);                         // :14-15
     const int n_loops = (int)p.loops.size();
     std::vector<int> order(n_loops);
@@ -184,18 +184,36 @@ inline SimResult simulate(const Config& cfg, const Problem& p, int device, bool 
     ipc_handle* h = nullptr;
     check(ipc_create(p.dim, p.n_poses, p.odom_meas.data(), p.odom_info.data(), &c, device, &h));   // IPC ipc(problem, cfg), :28
     SimResult r; r.n_candidates = n_loops; r.accepted.assign(n_loops, 0);
-    for (int k = 0; k < n_loops; ++k) {                                      // :34-47
-        const EdgeRec& e = p.loops[order[k]];
-        int acc = 0;
+    std::vector<int> acc_k(n_loops, 0);
+    if (one_by_one) {
+        for (int k = 0; k < n_loops; ++k) {                                  // :34-47, one ipc_agreement_check per candidate
+            const EdgeRec& e = p.loops[order[k]];
+            auto t0 = std::chrono::steady_clock::now();
+            check(ipc_agreement_check(h, e.from, e.to, e.meas.data(), e.info.data(), &acc_k[k], nullptr));
+            r.total_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (!quiet && (k % 50 == 0 || k + 1 == n_loops)) { std::fprintf(stderr, "\r[%d / %d]", k + 1, n_loops); std::fflush(stderr); }
+        }
+        if (!quiet) std::fprintf(stderr, "\n");
+    } else {                                                                 // :34-47, the whole loop in one call (same results)
+        const int w = p.dim == 2 ? 3 : 7, dd = p.dim == 2 ? 9 : 36;
+        std::vector<int> from(n_loops), to(n_loops);
+        std::vector<double> meas((size_t)n_loops * w), info((size_t)n_loops * dd);
+        for (int k = 0; k < n_loops; ++k) {
+            const EdgeRec& e = p.loops[order[k]];
+            from[k] = e.from; to[k] = e.to;
+            std::copy(e.meas.begin(), e.meas.end(), meas.begin() + (size_t)k * w);
+            std::copy(e.info.begin(), e.info.end(), info.begin() + (size_t)k * dd);
+        }
         auto t0 = std::chrono::steady_clock::now();
-        check(ipc_agreement_check(h, e.from, e.to, e.meas.data(), e.info.data(), &acc, nullptr));
-        r.total_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        check(ipc_agreement_check_stream(h, n_loops, from.data(), to.data(), meas.data(), info.data(), acc_k.data(), nullptr));
+        r.total_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    for (int k = 0; k < n_loops; ++k) {
+        const int acc = acc_k[k];
         r.accepted[order[k]] = acc;
         const bool truth = order[k] < cfg.canonic_inliers;
         if (acc && truth) ++r.tp; else if (acc && !truth) ++r.fp; else if (!acc && truth) ++r.fn; else ++r.tn;
-        if (!quiet && (k % 50 == 0 || k + 1 == n_loops)) { std::fprintf(stderr, "\r[%d / %d]", k + 1, n_loops); std::fflush(stderr); }
     }
-    if (!quiet) std::fprintf(stderr, "\n");
     r.precision = (r.tp + r.fp) > 0 ? (float)r.tp / (float)(r.tp + r.fp) : 0.f;   // float, :80-81
     r.recall = (r.tp + r.fn) > 0 ? (float)r.tp / (float)(r.tp + r.fn) : 0.f;
     const int w = p.dim == 2 ? 3 : 7;
@@ -215,7 +233,7 @@ inline SimResult simulate(const Config& cfg, const Problem& p, int device, bool 
 }
 
 inline int tester_main(int argc, char** argv, int dim) {
-    std::string cfg_path; int device = 0; bool parse_only = false, quiet = false, final_pgo = true;
+    std::string cfg_path; int device = 0; bool parse_only = false, quiet = false, final_pgo = true, one_by_one = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-c" && i + 1 < argc) cfg_path = argv[++i];
@@ -223,7 +241,8 @@ inline int tester_main(int argc, char** argv, int dim) {
         else if (a == "--parse-only") parse_only = true;
         else if (a == "--no-final-pgo") final_pgo = false;
         else if (a == "--quiet") quiet = true;
-        else { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [--device N] [--parse-only] [--no-final-pgo] [--quiet]\n"; return 2; }
+        else if (a == "--one-by-one") one_by_one = true;
+        else { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [--device N] [--parse-only] [--no-final-pgo] [--quiet] [--one-by-one]\n"; return 2; }
     }
     if (cfg_path.empty()) { std::cerr << "usage: " << argv[0] << " -c <config.yaml>\n"; return 2; }
     try {
@@ -237,7 +256,7 @@ inline int tester_main(int argc, char** argv, int dim) {
                       << cfg.slow_reject_iter_base << "\n";
             return 0;
         }
-        SimResult r = simulate(cfg, p, device, final_pgo, quiet);
+        SimResult r = simulate(cfg, p, device, final_pgo, quiet, one_by_one);
         std::cout << "TP " << r.tp << " FP " << r.fp << " TN " << r.tn << " FN " << r.fn << "\n";
         std::cout << "Precision = " << r.precision << "  Recall = " << r.recall << "\n";
         std::cout << "Total time = " << r.total_s << " s  Avg Time x test = " << (r.n_candidates ? r.total_s / r.n_candidates : 0.0) << " s\n";

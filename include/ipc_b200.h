@@ -72,6 +72,14 @@ void ipc_destroy(ipc_handle* h);
  * window re-dead-reckoned) or rollback. *accepted = 1/0. info may be NULL. */
 int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, const double* info,
                         int* accepted, ipc_check_info* out_info);
+/* The candidate loop of simulating_incremental_data — src/simulation.cpp:34-47: `for (edge : loops) ipc.agreementCheck(edge)` over
+ * n candidates in the given order, with exactly the sequential semantics (and results) of n ipc_agreement_check calls. A rejection
+ * leaves the IPC object untouched, so up to `stream_depth` (option, default 8) following candidates are solved speculatively side
+ * by side, one group of SMs each; results are consumed in order up to the first accept, which is committed and invalidates the
+ * rest of the round (those candidates are solved again against the new state). from/to: [n]; meas: [n][3|7]; info: [n][d*d];
+ * accepted: [n] 1/0; out_info: [n] or NULL. */
+int ipc_agreement_check_stream(ipc_handle* h, int n, const int* from, const int* to, const double* meas,
+                               const double* info, int* accepted, ipc_check_info* out_info);
 /* bool IPC::removeEdgeFromCnS(EDGE*) — src/consensus.cpp:77-98. *removed = 1/0. */
 int ipc_remove_edge(ipc_handle* h, int from, int to, int* removed);
 /* void IPC::addEdgeToCnS(EDGE*) — src/consensus.cpp:100-121. */
@@ -161,7 +169,8 @@ int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsign
 
 /* Knobs (non-reference). noise_exit: 1 (default) stops the Dogleg retry loop once a rejected trial's own predicted gain is
  * below 1e-13 * chi2 (DESIGN.md "Termination"), 0 replays all 100 retries like g2o, any other value is used as the threshold.
- * early_accept: 1 lets verdict-only batches stop as soon as sum chi2 <= threshold (same bits). speculate, use_uniform,
+ * early_accept: 1 lets verdict-only batches stop as soon as sum chi2 <= threshold (same bits). stream_depth (1..8): candidates
+ * ipc_agreement_check_stream solves side by side. speculate, use_uniform,
  * max_tries, sd_fuse (0 / 1 / 2: when the steepest-descent pass replaces the norm pass; results identical),
  * bucket<i>_cap / bucket<i>_nt / bucket<i>_minb (launch shapes, i = 0..4): tuning, see DESIGN.md. */
 int ipc_set_option(ipc_handle* h, const char* name, double value);

@@ -24,7 +24,7 @@ SYMBOLS = ["ipc_last_error", "ipc_device_count", "ipc_create", "ipc_destroy", "i
            "ipc_add_edge", "ipc_consensus_size", "ipc_get_consensus", "ipc_get_poses", "ipc_final_optimize", "ipc_set_candidates", "ipc_check_batch",
            "ipc_check_batch_dev", "ipc_last_batch_stats", "ipc_last_kernel_ms", "ipc_consistency_matrix", "ipc_greedy_consensus", "ipc_set_option",
            "ipc_comm_unique_id", "ipc_comm_init", "ipc_comm_info", "ipc_check_batch_sharded", "ipc_check_batch_sharded_dev",
-           "ipc_consistency_matrix_sharded", "ipc_stream_profile"]
+           "ipc_consistency_matrix_sharded", "ipc_stream_profile", "ipc_agreement_check_stream"]
 
 
 class IpcError(RuntimeError):
@@ -74,6 +74,7 @@ def lib():
         L.ipc_greedy_consensus.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ipc_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.ipc_stream_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ipc_agreement_check_stream.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ipc_comm_unique_id.argtypes = [C.c_void_p]
         L.ipc_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ipc_comm_info.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
@@ -150,6 +151,16 @@ class IPC:
         ci = CheckInfo()
         _chk(lib().ipc_agreement_check(self._h, int(frm), int(to), _p(m), _p(i), C.byref(acc), C.byref(ci)))
         return bool(acc.value), ci
+
+    def agreementCheckStream(self, frm, to, meas, info):
+        """The candidate loop of simulating_incremental_data (src/simulation.cpp:34-47) over the given candidates in order:
+        same results as calling agreementCheck one by one. Returns (accepted[bool], info[INFO_DTYPE])."""
+        f, t, m, i = _i32(frm), _i32(to), _f64(meas), _f64(info)
+        n = f.shape[0]
+        acc = np.zeros(n, dtype=np.int32)
+        out = np.zeros(n, dtype=INFO_DTYPE)
+        _chk(lib().ipc_agreement_check_stream(self._h, n, _p(f), _p(t), _p(m), _p(i), _p(acc), _p(out)))
+        return acc.astype(bool), out
 
     def removeEdgeFromCnS(self, edge) -> bool:
         r = C.c_int(0)

@@ -11,6 +11,15 @@
 
 using namespace ipcb;
 
+constexpr int CL_MAX_SLOTS = 8;
+struct ClSlot {                    // work buffers of one concurrent check of the sequential stream
+    int Lcap = 0, Kcap = 0;        // capacities: window edges, loops
+    ClBuffers B[2] = {};
+    double *G = nullptr, *H = nullptr, *S = nullptr, *z = nullptr, *lg = nullptr;
+    int *ev_ptr = nullptr, *ev_idx = nullptr;
+    void* loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the cluster
+};
+
 struct ipc_handle {
     int dim = 2, d = 3, mw = 3;
     int n = 0, n_pad = 0;
@@ -46,16 +55,16 @@ struct ipc_handle {
     double* d_pose = nullptr;         // AoS[5] x n: x y theta cos sin — the vertex estimates of the IPC object
     double* d_odom9_raw = nullptr;    // odometry records with the information as given (final optimisation only)
     const double* cl_odom = nullptr;  // records the cluster kernels read: d_odom9, or d_odom9_raw during ipc_final_optimize
-    int cl_Lcap = 0, cl_Kcap = 0, cl_grid = 0;                // capacities (window edges, loops) and the cooperative grid (one CTA per SM)
-    ClBuffers clB[2] = {};
-    double *cl_G = nullptr, *cl_H = nullptr, *cl_S = nullptr, *cl_z = nullptr, *cl_res = nullptr, *cl_lg = nullptr;
-    int *cl_ev_ptr = nullptr, *cl_ev_idx = nullptr;           // loop end points by window position (ClEvents)
-    unsigned* cl_bar = nullptr;                               // grid barrier counter + control words of the persistent solver
-    StreamArgs* cl_args = nullptr;                            // kernel arguments of the persistent solver, one record per group
-    unsigned long long* cl_prof = nullptr;                    // phase cycle counters of the persistent solver (ipc_stream_profile)
-    long long cl_n_checks = 0, cl_n_fact = 0, cl_n_trial = 0;
-    double *cl_out = nullptr, *cl_hout = nullptr;             // per-check results (device / pinned host)
-    void* cl_loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the current cluster
+    int cl_grid = 0;                                          // cooperative grid of the persistent solver: one CTA per SM
+    int stream_depth = CL_MAX_SLOTS;                          // candidates solved side by side by ipc_agreement_check_stream (option stream_depth)
+    std::vector<ClSlot> slots;                                // work buffers of the concurrent checks (slot 0: single checks, final optimisation)
+    std::vector<std::vector<unsigned char>> staging;         // host blobs of uploads in flight (freed after the round's synchronisation)
+    double* cl_res = nullptr;                                 // CL_NRES scalars per slot
+    unsigned* cl_bar = nullptr;                               // per slot: group barrier counter + control words
+    StreamArgs* cl_args = nullptr;                            // kernel arguments, one record per group
+    unsigned long long* cl_prof = nullptr;                    // phase cycle counters of slot 0's window CTA (ipc_stream_profile)
+    long long cl_n_checks = 0, cl_n_fact = 0, cl_n_trial = 0, cl_n_wasted = 0;
+    double *cl_out = nullptr, *cl_hout = nullptr;             // per-slot results (device / pinned host)
     double* cl_stage = nullptr;       // SE(3) dead-reckoning staging (CL_NT poses)
     double* d_odom49_raw = nullptr;   // SE(3) records with the information as given (final optimisation)
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // bracket the check kernels of the last batch (roofline timing)

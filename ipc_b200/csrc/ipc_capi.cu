@@ -89,7 +89,7 @@ const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
 }  // namespace
 
 namespace { int size_scratch(ipc_handle* h); }
-extern "C" { namespace { int stream_solver_setup(ipc_handle* h); } }
+extern "C" { namespace { int stream_solver_setup(ipc_handle* h); void slot_free(ClSlot& s); } }
 
 
 namespace {
@@ -248,13 +248,6 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
             cl3_dead_reckon<<<1, CL_NT, 0, h->stream>>>(h->d_odom49, 0, n_poses, h->d_pose, h->cl_stage);
         }
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES));
-        CUDA_TRY(cudaMalloc(&h->cl_bar, sizeof(unsigned) * 4));
-        CUDA_TRY(cudaMalloc(&h->cl_prof, sizeof(unsigned long long) * 16));
-        CUDA_TRY(cudaMemset(h->cl_prof, 0, sizeof(unsigned long long) * 16));
-        CUDA_TRY(cudaMalloc(&h->cl_out, sizeof(double) * 16));
-        CUDA_TRY(cudaMallocHost(&h->cl_hout, sizeof(double) * 16));
-        CUDA_TRY(cudaMalloc(&h->cl_args, sizeof(StreamArgs) * 16));
         int rcs = stream_solver_setup(h);
         if (rcs != IPC_OK) return rcs;
         CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -271,9 +264,9 @@ void ipc_destroy(ipc_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_odom9); cudaFree(h->d_odom3); cudaFree(h->d_odom49); cudaFree(h->d_loops); cudaFree(h->d_member); cudaFree(h->d_cand); cudaFree(h->d_work); cudaFree(h->d_counts);
     cudaFree(h->d_bucket_cap); cudaFree(h->d_verdict); cudaFree(h->d_bits); cudaFree(h->d_info); cudaFree(h->d_stats); cudaFree(h->d_scratch); cudaFree(h->d_gather);
-    cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_res); cudaFree(h->cl_lg);
-    cudaFree(h->cl_bar); cudaFree(h->cl_args); cudaFree(h->cl_prof); cudaFree(h->cl_out); cudaFree(h->cl_ev_ptr); cudaFree(h->cl_ev_idx); cudaFree(h->cl_loops); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
-    for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); cudaFree(h->clB[q].lt); }
+    cudaFree(h->d_pose); cudaFree(h->d_odom9_raw); cudaFree(h->cl_res);
+    cudaFree(h->cl_bar); cudaFree(h->cl_args); cudaFree(h->cl_prof); cudaFree(h->cl_out); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
+    for (ClSlot& sl : h->slots) slot_free(sl);
     delete h->comm;
     if (h->cl_hout) cudaFreeHost(h->cl_hout);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -300,6 +293,7 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
     if (!strcmp(name, "speculate")) { h->speculate = value != 0; return IPC_OK; }
     if (!strcmp(name, "early_accept")) { h->early_accept = value != 0; return IPC_OK; }
     if (!strcmp(name, "max_tries")) { h->max_tries = (int)value; return IPC_OK; }
+    if (!strcmp(name, "stream_depth")) { if (value < 1 || value > CL_MAX_SLOTS) return fail(IPC_ERR_ARG, "stream_depth: 1 .. 8"); h->stream_depth = (int)value; return IPC_OK; }
     return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
 }
 
@@ -428,92 +422,159 @@ int stream_solver_setup(ipc_handle* h) {
     CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
     if (!coop) return fail(IPC_ERR_UNSUPPORTED, "device does not support cooperative launches");
     h->cl_grid = h->n_sm;          // one CTA of CL_NT threads per SM
+    h->slots.resize(CL_MAX_SLOTS);
+    CUDA_TRY(cudaMalloc(&h->cl_bar, sizeof(unsigned) * 4 * CL_MAX_SLOTS));
+    CUDA_TRY(cudaMalloc(&h->cl_prof, sizeof(unsigned long long) * 16));
+    CUDA_TRY(cudaMemset(h->cl_prof, 0, sizeof(unsigned long long) * 16));
+    CUDA_TRY(cudaMalloc(&h->cl_out, sizeof(double) * 16 * CL_MAX_SLOTS));
+    CUDA_TRY(cudaMallocHost(&h->cl_hout, sizeof(double) * 16 * CL_MAX_SLOTS));
+    CUDA_TRY(cudaMalloc(&h->cl_args, sizeof(StreamArgs) * CL_MAX_SLOTS));
+    CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES * CL_MAX_SLOTS));
     return IPC_OK;
 }
 
-int cl_ensure(ipc_handle* h, int L, int K) {
+void slot_free(ClSlot& s) {
+    for (int q = 0; q < 2; ++q) { cudaFree(s.B[q].W); cudaFree(s.B[q].T); cudaFree(s.B[q].P); cudaFree(s.B[q].chi_e); cudaFree(s.B[q].lt); s.B[q] = ClBuffers{}; }
+    cudaFree(s.G); cudaFree(s.H); cudaFree(s.S); cudaFree(s.z); cudaFree(s.lg); cudaFree(s.ev_ptr); cudaFree(s.ev_idx); cudaFree(s.loops);
+    s = ClSlot{};
+}
+
+int slot_ensure(ipc_handle* h, ClSlot& s, int L, int K) {
     const int PW = h->dim == 2 ? 5 : 7, NPQ = h->dim == 2 ? NPRE : se3::NP3, DQ = h->dim == 2 ? 3 : 6, LTW = h->dim == 2 ? 12 : CL3_LT;
-    if (L > h->cl_Lcap) {
+    if (L > s.Lcap) {
         int cap = std::max(L, 256);
-        for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].W); cudaFree(h->clB[q].T); cudaFree(h->clB[q].P); cudaFree(h->clB[q].chi_e); h->clB[q].W = h->clB[q].T = h->clB[q].P = h->clB[q].chi_e = nullptr; }
-        cudaFree(h->cl_G); cudaFree(h->cl_H); cudaFree(h->cl_ev_ptr); h->cl_G = h->cl_H = nullptr; h->cl_ev_ptr = nullptr; h->cl_Lcap = 0;
+        for (int q = 0; q < 2; ++q) { cudaFree(s.B[q].W); cudaFree(s.B[q].T); cudaFree(s.B[q].P); cudaFree(s.B[q].chi_e); s.B[q].W = s.B[q].T = s.B[q].P = s.B[q].chi_e = nullptr; }
+        cudaFree(s.G); cudaFree(s.H); cudaFree(s.ev_ptr); s.G = s.H = nullptr; s.ev_ptr = nullptr; s.Lcap = 0;
         for (int q = 0; q < 2; ++q) {
-            CUDA_TRY(cudaMalloc(&h->clB[q].W, sizeof(double) * PW * (size_t)(cap + 1)));
-            CUDA_TRY(cudaMalloc(&h->clB[q].T, sizeof(double) * NPQ * (size_t)cap));
-            CUDA_TRY(cudaMalloc(&h->clB[q].P, sizeof(double) * NPQ * (size_t)(cap + 1)));
-            CUDA_TRY(cudaMalloc(&h->clB[q].chi_e, sizeof(double) * (size_t)cap));
+            CUDA_TRY(cudaMalloc(&s.B[q].W, sizeof(double) * PW * (size_t)(cap + 1)));
+            CUDA_TRY(cudaMalloc(&s.B[q].T, sizeof(double) * NPQ * (size_t)cap));
+            CUDA_TRY(cudaMalloc(&s.B[q].P, sizeof(double) * NPQ * (size_t)(cap + 1)));
+            CUDA_TRY(cudaMalloc(&s.B[q].chi_e, sizeof(double) * (size_t)cap));
         }
-        CUDA_TRY(cudaMalloc(&h->cl_G, sizeof(double) * DQ * (size_t)(cap + 1)));
-        CUDA_TRY(cudaMalloc(&h->cl_H, sizeof(double) * DQ * (size_t)(cap + 1)));
-        CUDA_TRY(cudaMalloc(&h->cl_ev_ptr, sizeof(int) * (size_t)(cap + 3)));
-        h->cl_Lcap = cap;
+        CUDA_TRY(cudaMalloc(&s.G, sizeof(double) * DQ * (size_t)(cap + 1)));
+        CUDA_TRY(cudaMalloc(&s.H, sizeof(double) * DQ * (size_t)(cap + 1)));
+        CUDA_TRY(cudaMalloc(&s.ev_ptr, sizeof(int) * (size_t)(cap + 3)));
+        s.Lcap = cap;
     }
-    if (K > h->cl_Kcap) {
+    if (K > s.Kcap) {
         int cap = std::max(K + K / 2, 64);
-        const size_t n_pad = ((size_t)DQ * cap + CH_NB - 1) / CH_NB * CH_NB;
-        if (stream_smem_bytes((int)n_pad) > 226 * 1024) {
-            cap = K; 
-            const size_t np2 = ((size_t)DQ * cap + CH_NB - 1) / CH_NB * CH_NB;
-            if (stream_smem_bytes((int)np2) > 226 * 1024) return fail(IPC_ERR_UNSUPPORTED, "cluster of " + std::to_string(K) + " loops exceeds the dense force-system solver (DESIGN.md)");
+        auto pad_of = [&](int k) { return ((size_t)DQ * k + CH_NB - 1) / CH_NB * CH_NB; };
+        if (stream_smem_bytes((int)pad_of(cap)) > 226 * 1024) {
+            cap = K;
+            if (stream_smem_bytes((int)pad_of(cap)) > 226 * 1024)
+                return fail(IPC_ERR_UNSUPPORTED, "cluster of " + std::to_string(K) + " loops exceeds the dense force-system solver (DESIGN.md)");
         }
-        for (int q = 0; q < 2; ++q) { cudaFree(h->clB[q].lt); h->clB[q].lt = nullptr; }
-        cudaFree(h->cl_S); cudaFree(h->cl_z); cudaFree(h->cl_loops); cudaFree(h->cl_lg); cudaFree(h->cl_ev_idx);
-        h->cl_S = h->cl_z = h->cl_lg = nullptr; h->cl_loops = nullptr; h->cl_ev_idx = nullptr; h->cl_Kcap = 0;
-        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&h->clB[q].lt, sizeof(double) * LTW * (size_t)cap));
-        const size_t np = ((size_t)DQ * cap + CH_NB - 1) / CH_NB * CH_NB;
-        CUDA_TRY(cudaMalloc(&h->cl_S, sizeof(double) * (np + CH_NB) * np));
-        CUDA_TRY(cudaMalloc(&h->cl_z, sizeof(double) * np));
-        CUDA_TRY(cudaMalloc(&h->cl_lg, sizeof(double) * 2 * DQ * (size_t)cap));
-        CUDA_TRY(cudaMalloc(&h->cl_ev_idx, sizeof(int) * 2 * (size_t)cap));
-        CUDA_TRY(cudaMalloc(&h->cl_loops, std::max(sizeof(ClLoop), sizeof(ClLoop3)) * (size_t)cap));
-        h->cl_Kcap = cap;
+        for (int q = 0; q < 2; ++q) { cudaFree(s.B[q].lt); s.B[q].lt = nullptr; }
+        cudaFree(s.S); cudaFree(s.z); cudaFree(s.loops); cudaFree(s.lg); cudaFree(s.ev_idx);
+        s.S = s.z = s.lg = nullptr; s.loops = nullptr; s.ev_idx = nullptr; s.Kcap = 0;
+        for (int q = 0; q < 2; ++q) CUDA_TRY(cudaMalloc(&s.B[q].lt, sizeof(double) * LTW * (size_t)cap));
+        const size_t np = pad_of(cap);
+        CUDA_TRY(cudaMalloc(&s.S, sizeof(double) * (np + CH_NB) * np));
+        CUDA_TRY(cudaMalloc(&s.z, sizeof(double) * np));
+        CUDA_TRY(cudaMalloc(&s.lg, sizeof(double) * 2 * DQ * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&s.ev_idx, sizeof(int) * 2 * (size_t)cap));
+        CUDA_TRY(cudaMalloc(&s.loops, std::max(sizeof(ClLoop), sizeof(ClLoop3)) * (size_t)cap));
+        s.Kcap = cap;
     }
     return IPC_OK;
 }
 
-// isAgreeingWithCurrentState on the window [lo, hi] with the K loops already uploaded (the candidate is the last one): one
-// cooperative launch of the persistent solver, one synchronisation. ab: interval [a, b) of every loop in local vertex indices.
-// commit: 1 = agreementCheck (store the window + propagateCurrentGuess on accept), 2 = final optimisation (always store).
-int cl_window_check(ipc_handle* h, int lo, int hi, int K, const std::vector<std::pair<int, int>>& ab, double th, int iter_base, bool* ok_out,
-                    ipc_check_info* info, int commit, bool exact_iters = false) {
+struct LoopRef { int from, to; const double* meas; const double* info; };
+
+// Upload the sub-problem of one check into slot `si` (loop records, end-point events) and fill its kernel arguments.
+// loops: the K loop edges, the candidate last. commit: see StreamArgs::commit.
+int slot_prepare(ipc_handle* h, int si, int lo, int hi, const std::vector<LoopRef>& loops, double th, int iter_base, int commit, bool exact_iters,
+                 StreamArgs& A) {
+    ClSlot& s = h->slots[si];
     const bool d2 = h->dim == 2;
-    const int L = hi - lo, DQ = d2 ? 3 : 6;
+    const int L = hi - lo, K = (int)loops.size(), DQ = d2 ? 3 : 6;
+    int rc = slot_ensure(h, s, L, K);
+    if (rc != IPC_OK) return rc;
     cudaStream_t st = h->stream;
-    // loop end points by window position, loop order within a position (ClEvents)
-    std::vector<int> ptr(L + 3, 0), idx(2 * (size_t)K);
-    for (int l = 0; l < K; ++l) { ++ptr[ab[l].first + 1]; ++ptr[ab[l].second + 1]; }
-    for (int j = 0; j <= L + 1; ++j) ptr[j + 1] += ptr[j];
-    {
-        std::vector<int> fill(ptr.begin(), ptr.end() - 1);
-        for (int l = 0; l < K; ++l) { idx[fill[ab[l].first]++] = (l << 1) | 1; idx[fill[ab[l].second]++] = (l << 1); }
+    // pinned-free staging: the vectors live until the synchronisation at the end of the round (h->staging keeps them)
+    h->staging.emplace_back();
+    std::vector<unsigned char>& blob = h->staging.back();
+    const size_t rec = d2 ? sizeof(ClLoop) : sizeof(ClLoop3);
+    blob.resize(rec * K + sizeof(int) * ((size_t)L + 3 + 2 * (size_t)K));
+    int* ptr = reinterpret_cast<int*>(blob.data() + rec * K);
+    int* idx = ptr + (L + 3);
+    std::fill(ptr, ptr + L + 3, 0);
+    for (int l = 0; l < K; ++l) {
+        const LoopRef& e = loops[l];
+        const int jf = e.from - lo, jt = e.to - lo, a = std::min(jf, jt), b = std::max(jf, jt);
+        if (d2) {
+            ClLoop& o = reinterpret_cast<ClLoop*>(blob.data())[l];
+            o.jf = jf; o.jt = jt; o.a = a; o.b = b;
+            HostState::se2_edge_record(e.meas, e.info, 1.0, o.meas, o.D);
+            HostState::inv_sym3_host(o.D, o.V);
+        } else {
+            ClLoop3& o = reinterpret_cast<ClLoop3*>(blob.data())[l];
+            o.jf = jf; o.jt = jt; o.a = a; o.b = b;
+            double r[49];
+            if (!HostState::se3_edge_record(e.meas, e.info, 1.0, r)) return fail(IPC_ERR_ARG, "loop edge with a zero quaternion or a singular information matrix");
+            for (int q = 0; q < 7; ++q) o.zinv[q] = r[q];
+            for (int q = 0; q < 21; ++q) { o.Om[q] = r[7 + q]; o.V[q] = r[28 + q]; }
+        }
+        ++ptr[a + 1]; ++ptr[b + 1];
     }
-    CUDA_TRY(cudaMemcpyAsync(h->cl_ev_ptr, ptr.data(), sizeof(int) * ptr.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(h->cl_ev_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(h->cl_bar, 0, sizeof(unsigned) * 4, st));
-    StreamArgs A{};
-    A.dim = h->dim; A.lo = lo; A.L = L; A.K = K; A.n_poses = h->n; A.Lcap = h->cl_Lcap;
+    for (int j = 0; j <= L + 1; ++j) ptr[j + 1] += ptr[j];
+    {   // loop end points by window position, loop order within a position (ClEvents)
+        std::vector<int> fill(ptr, ptr + L + 2);
+        for (int l = 0; l < K; ++l) {
+            const int a = std::min(loops[l].from, loops[l].to) - lo, b = std::max(loops[l].from, loops[l].to) - lo;
+            idx[fill[a]++] = (l << 1) | 1; idx[fill[b]++] = (l << 1);
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(s.loops, blob.data(), rec * K, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.ev_ptr, ptr, sizeof(int) * (L + 3), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.ev_idx, idx, sizeof(int) * 2 * (size_t)K, cudaMemcpyHostToDevice, st));
+    A = StreamArgs{};
+    A.dim = h->dim; A.lo = lo; A.L = L; A.K = K; A.n_poses = h->n; A.Lcap = s.Lcap;
     A.odom = h->cl_odom ? h->cl_odom : (d2 ? h->d_odom9 : h->d_odom49);
     A.odom_commit = d2 ? h->d_odom9 : h->d_odom49;
-    A.pose = h->d_pose; A.loops = h->cl_loops; A.ev = ClEvents{h->cl_ev_ptr, h->cl_ev_idx};
-    A.B[0] = h->clB[0]; A.B[1] = h->clB[1]; A.G = h->cl_G; A.H = h->cl_H; A.lg = h->cl_lg;
-    A.n_pad = (DQ * K + CH_NB - 1) / CH_NB * CH_NB; A.ld = A.n_pad + CH_NB; A.S = h->cl_S; A.z = h->cl_z;
-    A.res = h->cl_res; A.stage3 = h->cl_stage; A.bar = h->cl_bar; A.ctl = reinterpret_cast<int*>(h->cl_bar + 1);
+    A.pose = h->d_pose; A.loops = s.loops; A.ev = ClEvents{s.ev_ptr, s.ev_idx};
+    A.B[0] = s.B[0]; A.B[1] = s.B[1]; A.G = s.G; A.H = s.H; A.lg = s.lg;
+    A.n_pad = (DQ * K + CH_NB - 1) / CH_NB * CH_NB; A.ld = A.n_pad + CH_NB; A.S = s.S; A.z = s.z;
+    A.res = h->cl_res + CL_NRES * si; A.stage3 = h->cl_stage; A.bar = h->cl_bar + 4 * si; A.ctl = reinterpret_cast<int*>(h->cl_bar + 4 * si + 1);
     A.th = th; A.max_iter = iter_base;
     if (!exact_iters && L + K > 100) A.max_iter *= 5;          // src/consensus_utils.cpp:12-13
-    A.max_tries = h->max_tries; A.noise_eps = h->noise_eps; A.commit = commit; A.out = h->cl_out; A.prof = h->cl_prof;
-    CUDA_TRY(cudaMemcpyAsync(h->cl_args, &A, sizeof(A), cudaMemcpyHostToDevice, st));
-    const StreamArgs* d_args = h->cl_args; int group_size = h->cl_grid;
-    void* args[] = {&d_args, &group_size};
-    const size_t smem = stream_smem_bytes(A.n_pad);
-    const void* fn = d2 ? (const void*)stream_check_kernel<2> : (const void*)stream_check_kernel<3>;
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(h->cl_grid), dim3(CL_NT), args, smem, st));
-    CUDA_TRY(cudaMemcpyAsync(h->cl_hout, h->cl_out, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const double* o = h->cl_hout;
-    *ok_out = o[0] != 0.0;
-    h->cl_n_fact += (long long)o[6]; h->cl_n_trial += (long long)o[7]; ++h->cl_n_checks;
-    if (info) { info->max_chi2 = o[1]; info->cand_chi2 = o[2]; info->sum_chi2 = o[3]; info->iterations = (int)o[4]; info->evals = (int)o[5]; info->window_len = L; info->n_loops = K; }
+    A.max_tries = h->max_tries; A.noise_eps = h->noise_eps; A.commit = commit; A.out = h->cl_out + 16 * si;
+    A.prof = si == 0 ? h->cl_prof : nullptr;
     return IPC_OK;
+}
+
+// one cooperative launch: group g of `group_size` CTAs solves args[g]; results of every slot come back through the pinned buffer
+int launch_groups(ipc_handle* h, const std::vector<StreamArgs>& args, int group_size) {
+    cudaStream_t st = h->stream;
+    const int ng = (int)args.size();
+    size_t smem = 0;
+    for (const StreamArgs& a : args) smem = std::max(smem, stream_smem_bytes(a.n_pad));
+    CUDA_TRY(cudaMemsetAsync(h->cl_bar, 0, sizeof(unsigned) * 4 * CL_MAX_SLOTS, st));
+    CUDA_TRY(cudaMemcpyAsync(h->cl_args, args.data(), sizeof(StreamArgs) * ng, cudaMemcpyHostToDevice, st));
+    const StreamArgs* d_args = h->cl_args;
+    void* kargs[] = {&d_args, &group_size};
+    const void* fn = h->dim == 2 ? (const void*)stream_check_kernel<2> : (const void*)stream_check_kernel<3>;
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(ng * group_size), dim3(CL_NT), kargs, smem, st));
+    CUDA_TRY(cudaMemcpyAsync(h->cl_hout, h->cl_out, sizeof(double) * 16 * ng, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->staging.clear();
+    for (int g = 0; g < ng; ++g) { const double* o = h->cl_hout + 16 * g; h->cl_n_fact += (long long)o[6]; h->cl_n_trial += (long long)o[7]; ++h->cl_n_checks; }
+    return IPC_OK;
+}
+
+void info_from(const double* o, int L, int K, ipc_check_info* info) {
+    if (!info) return;
+    info->max_chi2 = o[1]; info->cand_chi2 = o[2]; info->sum_chi2 = o[3]; info->iterations = (int)o[4]; info->evals = (int)o[5]; info->window_len = L; info->n_loops = K;
+}
+
+// computeIndependentSubgraph (src/consensus.cpp:123-171) on the host mirror + the loop list of the sub-problem, candidate last
+void cluster_of(ipc_handle* h, int from, int to, const double* meas, const double* info, int& lo, int& hi, std::vector<LoopRef>& loops) {
+    std::vector<int> members;
+    auto ext = h->hs.independent_subgraph(from, to, members);
+    lo = ext.first; hi = ext.second;
+    loops.clear();
+    for (int m : members) { const HostEdge& e = h->hs.cns[m]; loops.push_back(LoopRef{e.from, e.to, e.meas.data(), e.info.data()}); }
+    loops.push_back(LoopRef{from, to, meas, info});
 }
 
 }  // namespace
@@ -522,56 +583,81 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
     if (!h || !meas || !info || !accepted) return fail(IPC_ERR_ARG, "null argument");
     if (from < 0 || to < 0 || from >= h->n || to >= h->n || from == to) return fail(IPC_ERR_ARG, "invalid vertex ids");
     CUDA_TRY(cudaSetDevice(h->device));
-    // computeIndependentSubgraph, src/consensus.cpp:123-171 (integer logic on the host mirror)
-    std::vector<int> members;
-    auto ext = h->hs.independent_subgraph(from, to, members);
-    const int lo = ext.first, hi = ext.second, K = (int)members.size() + 1;
-    const bool slow = !members.empty();
+    int lo, hi; std::vector<LoopRef> loops;
+    cluster_of(h, from, to, meas, info, lo, hi, loops);
+    const bool slow = loops.size() > 1;
     const double th = slow ? h->cfg.slow_reject_th : h->cfg.fast_reject_th;          // src/consensus.cpp:50-52
     const int ib = slow ? h->cfg.slow_reject_iter_base : h->cfg.fast_reject_iter_base;
-    int rc = cl_ensure(h, hi - lo, K);
-    if (rc != IPC_OK) return rc;
-    std::vector<ClLoop> loops;
-    std::vector<ClLoop3> loops3v;
-    if (h->dim == 2) {
-        loops.resize(K);
-        auto fill = [&](ClLoop& o, int f, int t, const double* m, const double* w) {
-            o.jf = f - lo; o.jt = t - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
-            HostState::se2_edge_record(m, w, 1.0, o.meas, o.D);
-            HostState::inv_sym3_host(o.D, o.V);
-        };
-        for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; fill(loops[i], e.from, e.to, e.meas.data(), e.info.data()); }
-        fill(loops[K - 1], from, to, meas, info);
-        CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice, h->stream));
-    } else {
-        loops3v.resize(K);
-        auto fill = [&](ClLoop3& o, int f, int t, const double* m, const double* w) {
-            o.jf = f - lo; o.jt = t - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
-            double r[49];
-            if (!HostState::se3_edge_record(m, w, 1.0, r)) return false;
-            for (int q = 0; q < 7; ++q) o.zinv[q] = r[q];
-            for (int q = 0; q < 21; ++q) { o.Om[q] = r[7 + q]; o.V[q] = r[28 + q]; }
-            return true;
-        };
-        bool okf = true;
-        for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; okf = okf && fill(loops3v[i], e.from, e.to, e.meas.data(), e.info.data()); }
-        okf = okf && fill(loops3v[K - 1], from, to, meas, info);
-        if (!okf) return fail(IPC_ERR_ARG, "loop edge with a zero quaternion or a singular information matrix");
-        CUDA_TRY(cudaMemcpyAsync(h->cl_loops, loops3v.data(), sizeof(ClLoop3) * K, cudaMemcpyHostToDevice, h->stream));
-    }
-    std::vector<std::pair<int, int>> ab(K);
-    for (int i = 0; i + 1 < K; ++i) { const HostEdge& e = h->hs.cns[members[i]]; ab[i] = {std::min(e.from, e.to) - lo, std::max(e.from, e.to) - lo}; }
-    ab[K - 1] = {std::min(from, to) - lo, std::max(from, to) - lo};
-    bool ok = false;
+    std::vector<StreamArgs> args(1);
     // accept = discard + push_back + propagateCurrentGuess (src/consensus.cpp:69-71), done by the kernel; a rejection leaves d_pose
     // untouched (restore): the solve works on a copy of the window
-    rc = cl_window_check(h, lo, hi, K, ab, th, ib, &ok, out_info, /*commit=*/1);
+    int rc = slot_prepare(h, 0, lo, hi, loops, th, ib, /*commit=*/1, false, args[0]);
+    if (rc != IPC_OK) { h->staging.clear(); return rc; }
+    rc = launch_groups(h, args, h->cl_grid);
     if (rc != IPC_OK) return rc;
+    const bool ok = h->cl_hout[0] != 0.0;
+    info_from(h->cl_hout, hi - lo, (int)loops.size(), out_info);
     *accepted = ok ? 1 : 0;
     if (ok) {
         HostEdge e; e.from = from; e.to = to; e.meas.assign(meas, meas + h->mw); e.info.assign(info, info + h->d * h->d);
         h->hs.cns.push_back(std::move(e));
     }
+    return IPC_OK;
+}
+
+// The candidate loop of simulating_incremental_data (src/simulation.cpp:34-47) for n candidates in the given order, with exactly
+// the sequential semantics of n ipc_agreement_check calls. Most candidates are rejected and a rejection leaves the IPC object
+// untouched, so the next `stream_depth` candidates are solved SPECULATIVELY side by side (one group of SMs each) against the
+// current state; results are consumed in order up to and including the first accept, which is committed (window stored,
+// propagateCurrentGuess, consensus set grown) and invalidates the later ones of the round: they are simply solved again.
+int ipc_agreement_check_stream(ipc_handle* h, int n, const int* from, const int* to, const double* meas, const double* info, int* accepted,
+                               ipc_check_info* out_info) {
+    if (!h || n < 0 || (n && (!from || !to || !meas || !info || !accepted))) return fail(IPC_ERR_ARG, "bad arguments");
+    for (int i = 0; i < n; ++i)
+        if (from[i] < 0 || to[i] < 0 || from[i] >= h->n || to[i] >= h->n || from[i] == to[i]) return fail(IPC_ERR_ARG, "candidate " + std::to_string(i) + " has invalid vertex ids");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int depth = std::max(1, std::min(h->stream_depth, CL_MAX_SLOTS));
+    const int mw = h->mw, dd = h->d * h->d;
+    int i = 0;
+    while (i < n) {
+        const int m = std::min(depth, n - i);
+        const int group_size = std::max(1, h->cl_grid / (m == 1 ? 1 : depth));
+        std::vector<StreamArgs> args(m);
+        std::vector<std::pair<int, int>> LK(m);
+        for (int s = 0; s < m; ++s) {
+            int lo, hi; std::vector<LoopRef> loops;
+            cluster_of(h, from[i + s], to[i + s], meas + (size_t)mw * (i + s), info + (size_t)dd * (i + s), lo, hi, loops);
+            const bool slow = loops.size() > 1;
+            int rc = slot_prepare(h, s, lo, hi, loops, slow ? h->cfg.slow_reject_th : h->cfg.fast_reject_th,
+                                  slow ? h->cfg.slow_reject_iter_base : h->cfg.fast_reject_iter_base, /*commit=*/0, false, args[s]);
+            if (rc != IPC_OK) { h->staging.clear(); return rc; }
+            LK[s] = {hi - lo, (int)loops.size()};
+        }
+        int rc = launch_groups(h, args, group_size);
+        if (rc != IPC_OK) return rc;
+        int used = 0;
+        for (int s = 0; s < m; ++s) {
+            const double* o = h->cl_hout + 16 * s;
+            const bool ok = o[0] != 0.0;
+            accepted[i + s] = ok ? 1 : 0;
+            if (out_info) info_from(o, LK[s].first, LK[s].second, out_info + i + s);
+            ++used;
+            if (ok) {     // commit slot s: store its window, propagateCurrentGuess, push_back (src/consensus.cpp:69-71)
+                const StreamArgs& A = args[s];
+                const int cur = (int)o[8];
+                if (h->dim == 2) stream_commit_kernel<2><<<1, CL_NT, 0, h->stream>>>(A.B[cur].W, h->d_pose, A.lo, A.L, h->d_odom9, h->n, h->cl_stage);
+                else stream_commit_kernel<3><<<1, CL_NT, 0, h->stream>>>(A.B[cur].W, h->d_pose, A.lo, A.L, h->d_odom49, h->n, h->cl_stage);
+                CUDA_TRY(cudaGetLastError());
+                HostEdge e; e.from = from[i + s]; e.to = to[i + s];
+                e.meas.assign(meas + (size_t)mw * (i + s), meas + (size_t)mw * (i + s + 1)); e.info.assign(info + (size_t)dd * (i + s), info + (size_t)dd * (i + s + 1));
+                h->hs.cns.push_back(std::move(e));
+                h->cl_n_wasted += m - 1 - s;
+                break;
+            }
+        }
+        i += used;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return IPC_OK;
 }
 
@@ -605,38 +691,17 @@ int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* ite
     if (iterations) *iterations = 0;
     if (K == 0) { CUDA_TRY(cudaStreamSynchronize(h->stream)); return IPC_OK; }
     const int lo = 0, hi = h->n - 1;
-    int rc = cl_ensure(h, hi - lo, K);
-    if (rc != IPC_OK) return rc;
-    if (d2) {
-        std::vector<ClLoop> loops(K);
-        for (int i = 0; i < K; ++i) {
-            const HostEdge& e = h->hs.cns[i];
-            ClLoop& o = loops[i];
-            o.jf = e.from - lo; o.jt = e.to - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
-            HostState::se2_edge_record(e.meas.data(), e.info.data(), 1.0, o.meas, o.D);
-            HostState::inv_sym3_host(o.D, o.V);
-        }
-        CUDA_TRY(cudaMemcpy(h->cl_loops, loops.data(), sizeof(ClLoop) * K, cudaMemcpyHostToDevice));
-    } else {
-        std::vector<ClLoop3> loops(K);
-        for (int i = 0; i < K; ++i) {
-            const HostEdge& e = h->hs.cns[i];
-            ClLoop3& o = loops[i];
-            o.jf = e.from - lo; o.jt = e.to - lo; o.a = std::min(o.jf, o.jt); o.b = std::max(o.jf, o.jt);
-            double r[49];
-            if (!HostState::se3_edge_record(e.meas.data(), e.info.data(), 1.0, r)) return fail(IPC_ERR_ARG, "bad loop edge");
-            for (int q = 0; q < 7; ++q) o.zinv[q] = r[q];
-            for (int q = 0; q < 21; ++q) { o.Om[q] = r[7 + q]; o.V[q] = r[28 + q]; }
-        }
-        CUDA_TRY(cudaMemcpy(h->cl_loops, loops.data(), sizeof(ClLoop3) * K, cudaMemcpyHostToDevice));
-    }
-    std::vector<std::pair<int, int>> ab(K);
-    for (int i = 0; i < K; ++i) { const HostEdge& e = h->hs.cns[i]; ab[i] = {std::min(e.from, e.to) - lo, std::max(e.from, e.to) - lo}; }
-    bool ok = false; ipc_check_info ci{};
+    std::vector<LoopRef> loops;
+    for (const HostEdge& e : h->hs.cns) loops.push_back(LoopRef{e.from, e.to, e.meas.data(), e.info.data()});
+    std::vector<StreamArgs> args(1);
     h->cl_odom = d2 ? h->d_odom9_raw : h->d_odom49_raw;        // odometry information / s_factor (src/simulation.cpp:55-56)
-    rc = cl_window_check(h, lo, hi, K, ab, 0.0, max_iterations, &ok, &ci, /*commit=*/2, /*exact_iters=*/true);
+    int rc = slot_prepare(h, 0, lo, hi, loops, 0.0, max_iterations, /*commit=*/2, /*exact_iters=*/true, args[0]);
     h->cl_odom = nullptr;
+    if (rc != IPC_OK) { h->staging.clear(); return rc; }
+    rc = launch_groups(h, args, h->cl_grid);
     if (rc != IPC_OK) return rc;
+    ipc_check_info ci{};
+    info_from(h->cl_hout, hi - lo, K, &ci);
     if (chi2) *chi2 = ci.sum_chi2;
     if (iterations) *iterations = ci.iterations;
     return IPC_OK;
@@ -652,7 +717,7 @@ int ipc_stream_profile(ipc_handle* h, double* out16, int reset) {
     for (int i = 0; i < 8; ++i) out16[i] = (double)c[i] / ((double)khz * 1e3);      // seconds at the nominal SM clock
     out16[8] = (double)h->cl_n_checks; out16[9] = (double)h->cl_n_fact; out16[10] = (double)h->cl_n_trial;
     for (int i = 11; i < 16; ++i) out16[i] = (double)c[i - 3] / ((double)khz * 1e3);    // factorisation sub-phases: diagonal block, panel solve, barrier, update, barrier
-    if (reset) { CUDA_TRY(cudaMemset(h->cl_prof, 0, sizeof(c))); h->cl_n_checks = h->cl_n_fact = h->cl_n_trial = 0; }
+    if (reset) { CUDA_TRY(cudaMemset(h->cl_prof, 0, sizeof(c))); h->cl_n_checks = h->cl_n_fact = h->cl_n_trial = h->cl_n_wasted = 0; }
     return IPC_OK;
 }
 

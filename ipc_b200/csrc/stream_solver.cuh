@@ -445,6 +445,15 @@ __global__ void __launch_bounds__(CL_NT, 1) stream_check_kernel(const StreamArgs
     }
 }
 
+// commit of a speculative slot: store its window, re-dead-reckon everything after it (src/consensus.cpp:69-71)
+template <int DIM>
+__global__ void __launch_bounds__(CL_NT) stream_commit_kernel(const double* W, double* pose, int lo, int L, const double* odom, int n_poses, double* stage3) {
+    __shared__ double red[32 * 2];
+    cl_copy_cta(W, pose + (size_t)ClDim<DIM>::PW * lo, (long long)ClDim<DIM>::PW * (L + 1));
+    if (DIM == 2) cl_dead_reckon_cta(odom, lo + L, n_poses, pose, red);
+    else cl3_dead_reckon_cta(odom, lo + L, n_poses, pose, stage3);
+}
+
 inline size_t stream_smem_bytes(int n_pad) { return sizeof(CholSmem) + sizeof(double) * 32 * 27 + ((sizeof(DlState) + 15) & ~15) + sizeof(double) * 2 * (size_t)n_pad + 64; }
 
 }  // namespace ipcb

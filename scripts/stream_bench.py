@@ -18,14 +18,23 @@ ipc = api.IPC.from_graph(g, cfg, candidates=False)
 create_s = time.perf_counter() - t
 acc = np.zeros(len(order), dtype=bool); mx = np.zeros(len(order)); K = np.zeros(len(order), dtype=int); L = np.zeros(len(order), dtype=int)
 ev = np.zeros(len(order), dtype=int)
+depth = 0
+for a in sys.argv:
+    if a.startswith("--depth="):
+        depth = int(a.split("=")[1])
 t = time.perf_counter()
-for k, l in enumerate(order):
-    ok, ci = ipc.agreementCheck((g.loop_from[l], g.loop_to[l], g.loop_meas[l], g.loop_info[l]))
-    acc[k] = ok; mx[k] = ci.max_chi2; K[k] = ci.n_loops; L[k] = ci.window_len; ev[k] = ci.evals
+if depth:            # the whole candidate loop in one call (speculative side-by-side solves, sequential semantics)
+    ipc.set_option("stream_depth", depth)
+    acc, inf = ipc.agreementCheckStream(g.loop_from[order], g.loop_to[order], g.loop_meas[order], g.loop_info[order])
+    mx, K, L, ev = inf["max_chi2"], inf["n_loops"], inf["window_len"], inf["evals"]
+else:
+    for k, l in enumerate(order):
+        ok, ci = ipc.agreementCheck((g.loop_from[l], g.loop_to[l], g.loop_meas[l], g.loop_info[l]))
+        acc[k] = ok; mx[k] = ci.max_chi2; K[k] = ci.n_loops; L[k] = ci.window_len; ev[k] = ci.evals
 dt = time.perf_counter() - t
 truth = order < g.n_true
 tp = int((acc & truth).sum()); fp = int((acc & ~truth).sum()); fn = int((~acc & truth).sum())
-out = {"config": name, "scale": scale, "create_s": create_s, "n_poses": g.n_poses, "candidates": len(order), "gpu_stream_s": dt, "gpu_checks_per_s": len(order) / dt,
+out = {"stream_depth": depth, "config": name, "scale": scale, "create_s": create_s, "n_poses": g.n_poses, "candidates": len(order), "gpu_stream_s": dt, "gpu_checks_per_s": len(order) / dt,
        "accepted": int(acc.sum()), "precision": tp / max(1, tp + fp), "recall": tp / max(1, tp + fn), "K_median": float(np.median(K)), "K_max": int(K.max()),
        "L_median": float(np.median(L)), "evals_mean": float(ev.mean())}
 out["profile"] = ipc.stream_profile()
