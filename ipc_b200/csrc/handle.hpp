@@ -18,6 +18,8 @@ struct ClSlot {                    // work buffers of one concurrent check of th
     double *G = nullptr, *H = nullptr, *S = nullptr, *z = nullptr, *lg = nullptr;
     int *ev_ptr = nullptr, *ev_idx = nullptr;
     void* loops = nullptr;         // ClLoop (SE2) or ClLoop3 (SE3) records of the cluster
+    unsigned char* hblob = nullptr; size_t hblob_cap = 0;   // pinned host staging of the slot's uploads
+    StreamArgs args_host{};        // arguments of the slot's last launch
 };
 
 struct ipc_handle {
@@ -58,9 +60,13 @@ struct ipc_handle {
     int cl_grid = 0;                                          // cooperative grid of the persistent solver: one CTA per SM
     int stream_depth = CL_MAX_SLOTS;                          // candidates solved side by side by ipc_agreement_check_stream (option stream_depth)
     std::vector<ClSlot> slots;                                // work buffers of the concurrent checks (slot 0: single checks, final optimisation)
-    std::vector<std::vector<unsigned char>> staging;         // host blobs of uploads in flight (freed after the round's synchronisation)
+    cudaStream_t slot_stream[CL_MAX_SLOTS] = {};              // one stream per slot: the speculative solves of the stream run side by side
+    cudaEvent_t slot_ev[CL_MAX_SLOTS] = {};
+    cudaEvent_t commit_ev = nullptr;
+    int* h_abort = nullptr;                                   // host-mapped abort words, one per slot
     double* cl_res = nullptr;                                 // CL_NRES scalars per slot
     unsigned* cl_bar = nullptr;                               // per slot: group barrier counter + control words
+    StreamArgs* cl_hargs = nullptr;                           // pinned copy of the kernel arguments
     StreamArgs* cl_args = nullptr;                            // kernel arguments, one record per group
     unsigned long long* cl_prof = nullptr;                    // phase cycle counters of slot 0's window CTA (ipc_stream_profile)
     long long cl_n_checks = 0, cl_n_fact = 0, cl_n_trial = 0, cl_n_wasted = 0;

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <chrono>
+#include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "handle.hpp"
@@ -268,7 +271,11 @@ void ipc_destroy(ipc_handle* h) {
     cudaFree(h->cl_bar); cudaFree(h->cl_args); cudaFree(h->cl_prof); cudaFree(h->cl_out); cudaFree(h->cl_stage); cudaFree(h->d_odom49_raw);
     for (ClSlot& sl : h->slots) slot_free(sl);
     delete h->comm;
+    for (int s = 0; s < CL_MAX_SLOTS; ++s) { if (h->slot_stream[s]) cudaStreamDestroy(h->slot_stream[s]); if (h->slot_ev[s]) cudaEventDestroy(h->slot_ev[s]); }
+    if (h->commit_ev) cudaEventDestroy(h->commit_ev);
+    if (h->h_abort) cudaFreeHost(h->h_abort);
     if (h->cl_hout) cudaFreeHost(h->cl_hout);
+    if (h->cl_hargs) cudaFreeHost(h->cl_hargs);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->ev_k0) cudaEventDestroy(h->ev_k0);
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
@@ -429,6 +436,7 @@ int stream_solver_setup(ipc_handle* h) {
     CUDA_TRY(cudaMalloc(&h->cl_out, sizeof(double) * 16 * CL_MAX_SLOTS));
     CUDA_TRY(cudaMallocHost(&h->cl_hout, sizeof(double) * 16 * CL_MAX_SLOTS));
     CUDA_TRY(cudaMalloc(&h->cl_args, sizeof(StreamArgs) * CL_MAX_SLOTS));
+    CUDA_TRY(cudaMallocHost(&h->cl_hargs, sizeof(StreamArgs) * CL_MAX_SLOTS));
     CUDA_TRY(cudaMalloc(&h->cl_res, sizeof(double) * CL_NRES * CL_MAX_SLOTS));
     return IPC_OK;
 }
@@ -436,13 +444,16 @@ int stream_solver_setup(ipc_handle* h) {
 void slot_free(ClSlot& s) {
     for (int q = 0; q < 2; ++q) { cudaFree(s.B[q].W); cudaFree(s.B[q].T); cudaFree(s.B[q].P); cudaFree(s.B[q].chi_e); cudaFree(s.B[q].lt); s.B[q] = ClBuffers{}; }
     cudaFree(s.G); cudaFree(s.H); cudaFree(s.S); cudaFree(s.z); cudaFree(s.lg); cudaFree(s.ev_ptr); cudaFree(s.ev_idx); cudaFree(s.loops);
+    if (s.hblob) cudaFreeHost(s.hblob);
     s = ClSlot{};
 }
 
 int slot_ensure(ipc_handle* h, ClSlot& s, int L, int K) {
     const int PW = h->dim == 2 ? 5 : 7, NPQ = h->dim == 2 ? NPRE : se3::NP3, DQ = h->dim == 2 ? 3 : 6, LTW = h->dim == 2 ? 12 : CL3_LT;
     if (L > s.Lcap) {
-        int cap = std::max(L, 256);
+        // the window buffers are O(n_poses): size them for the whole graph at once — cudaFree / cudaMalloc synchronise the device, and
+        // a reallocation per growing window would serialise the side-by-side solves of the stream
+        int cap = std::max(L, h->n);
         for (int q = 0; q < 2; ++q) { cudaFree(s.B[q].W); cudaFree(s.B[q].T); cudaFree(s.B[q].P); cudaFree(s.B[q].chi_e); s.B[q].W = s.B[q].T = s.B[q].P = s.B[q].chi_e = nullptr; }
         cudaFree(s.G); cudaFree(s.H); cudaFree(s.ev_ptr); s.G = s.H = nullptr; s.ev_ptr = nullptr; s.Lcap = 0;
         for (int q = 0; q < 2; ++q) {
@@ -457,7 +468,7 @@ int slot_ensure(ipc_handle* h, ClSlot& s, int L, int K) {
         s.Lcap = cap;
     }
     if (K > s.Kcap) {
-        int cap = std::max(K + K / 2, 64);
+        int cap = std::max(2 * K, 64);
         auto pad_of = [&](int k) { return ((size_t)DQ * k + CH_NB - 1) / CH_NB * CH_NB; };
         if (stream_smem_bytes((int)pad_of(cap)) > 226 * 1024) {
             cap = K;
@@ -484,18 +495,24 @@ struct LoopRef { int from, to; const double* meas; const double* info; };
 // Upload the sub-problem of one check into slot `si` (loop records, end-point events) and fill its kernel arguments.
 // loops: the K loop edges, the candidate last. commit: see StreamArgs::commit.
 int slot_prepare(ipc_handle* h, int si, int lo, int hi, const std::vector<LoopRef>& loops, double th, int iter_base, int commit, bool exact_iters,
-                 StreamArgs& A) {
+                 StreamArgs& A, cudaStream_t st) {
     ClSlot& s = h->slots[si];
     const bool d2 = h->dim == 2;
     const int L = hi - lo, K = (int)loops.size(), DQ = d2 ? 3 : 6;
     int rc = slot_ensure(h, s, L, K);
     if (rc != IPC_OK) return rc;
-    cudaStream_t st = h->stream;
-    // pinned-free staging: the vectors live until the synchronisation at the end of the round (h->staging keeps them)
-    h->staging.emplace_back();
-    std::vector<unsigned char>& blob = h->staging.back();
+    // PINNED host staging of this slot's uploads: copies from pageable memory block the calling thread, which would serialise
+    // the side-by-side solves of the stream
     const size_t rec = d2 ? sizeof(ClLoop) : sizeof(ClLoop3);
-    blob.resize(rec * K + sizeof(int) * ((size_t)L + 3 + 2 * (size_t)K));
+    const size_t need = rec * K + sizeof(int) * ((size_t)L + 3 + 2 * (size_t)K);
+    if (need > s.hblob_cap) {
+        if (s.hblob) cudaFreeHost(s.hblob);
+        s.hblob = nullptr; s.hblob_cap = 0;
+        const size_t cap = need + need / 2 + 4096;
+        CUDA_TRY(cudaMallocHost(&s.hblob, cap));
+        s.hblob_cap = cap;
+    }
+    struct { unsigned char* p; unsigned char* data() { return p; } } blob{s.hblob};
     int* ptr = reinterpret_cast<int*>(blob.data() + rec * K);
     int* idx = ptr + (L + 3);
     std::fill(ptr, ptr + L + 3, 0);
@@ -540,6 +557,26 @@ int slot_prepare(ipc_handle* h, int si, int lo, int hi, const std::vector<LoopRe
     if (!exact_iters && L + K > 100) A.max_iter *= 5;          // src/consensus_utils.cpp:12-13
     A.max_tries = h->max_tries; A.noise_eps = h->noise_eps; A.commit = commit; A.out = h->cl_out + 16 * si;
     A.prof = si == 0 ? h->cl_prof : nullptr;
+    A.abort = nullptr;
+    return IPC_OK;
+}
+
+// enqueue ONE check (slot si, a group of `group_size` CTAs) on `st`: barrier reset, arguments, cooperative launch, results to the
+// pinned buffer. Several such launches on different streams run side by side (18 CTAs each on a 148-SM part).
+int slot_launch(ipc_handle* h, int si, const StreamArgs& A, int group_size, cudaStream_t st, bool cooperative) {
+    CUDA_TRY(cudaMemsetAsync(h->cl_bar + 4 * si, 0, sizeof(unsigned) * 4, st));
+    h->slots[si].args_host = A;
+    h->cl_hargs[si] = A;                                   // pinned
+    CUDA_TRY(cudaMemcpyAsync(h->cl_args + si, h->cl_hargs + si, sizeof(StreamArgs), cudaMemcpyHostToDevice, st));
+    const StreamArgs* d_args = h->cl_args + si;
+    void* kargs[] = {&d_args, &group_size};
+    const void* fn = h->dim == 2 ? (const void*)stream_check_kernel<2> : (const void*)stream_check_kernel<3>;
+    // Cooperative launches do not overlap with one another; the side-by-side solves are plain launches instead. Their barriers need
+    // every CTA of the group resident, which holds because the slots together never ask for more CTAs than the device has SMs
+    // (stream_depth x group_size <= cl_grid, one CTA per SM) and a slot is only refilled after its previous kernel has finished.
+    if (cooperative) CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(group_size), dim3(CL_NT), kargs, stream_smem_bytes(A.n_pad), st));
+    else CUDA_TRY(cudaLaunchKernel(fn, dim3(group_size), dim3(CL_NT), kargs, stream_smem_bytes(A.n_pad), st));
+    CUDA_TRY(cudaMemcpyAsync(h->cl_hout + 16 * si, h->cl_out + 16 * si, sizeof(double) * 16, cudaMemcpyDeviceToHost, st));
     return IPC_OK;
 }
 
@@ -550,14 +587,14 @@ int launch_groups(ipc_handle* h, const std::vector<StreamArgs>& args, int group_
     size_t smem = 0;
     for (const StreamArgs& a : args) smem = std::max(smem, stream_smem_bytes(a.n_pad));
     CUDA_TRY(cudaMemsetAsync(h->cl_bar, 0, sizeof(unsigned) * 4 * CL_MAX_SLOTS, st));
-    CUDA_TRY(cudaMemcpyAsync(h->cl_args, args.data(), sizeof(StreamArgs) * ng, cudaMemcpyHostToDevice, st));
+    for (int g = 0; g < ng; ++g) h->cl_hargs[g] = args[g];
+    CUDA_TRY(cudaMemcpyAsync(h->cl_args, h->cl_hargs, sizeof(StreamArgs) * ng, cudaMemcpyHostToDevice, st));
     const StreamArgs* d_args = h->cl_args;
     void* kargs[] = {&d_args, &group_size};
     const void* fn = h->dim == 2 ? (const void*)stream_check_kernel<2> : (const void*)stream_check_kernel<3>;
     CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(ng * group_size), dim3(CL_NT), kargs, smem, st));
     CUDA_TRY(cudaMemcpyAsync(h->cl_hout, h->cl_out, sizeof(double) * 16 * ng, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    h->staging.clear();
     for (int g = 0; g < ng; ++g) { const double* o = h->cl_hout + 16 * g; h->cl_n_fact += (long long)o[6]; h->cl_n_trial += (long long)o[7]; ++h->cl_n_checks; }
     return IPC_OK;
 }
@@ -591,8 +628,8 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
     std::vector<StreamArgs> args(1);
     // accept = discard + push_back + propagateCurrentGuess (src/consensus.cpp:69-71), done by the kernel; a rejection leaves d_pose
     // untouched (restore): the solve works on a copy of the window
-    int rc = slot_prepare(h, 0, lo, hi, loops, th, ib, /*commit=*/1, false, args[0]);
-    if (rc != IPC_OK) { h->staging.clear(); return rc; }
+    int rc = slot_prepare(h, 0, lo, hi, loops, th, ib, /*commit=*/1, false, args[0], h->stream);
+    if (rc != IPC_OK) return rc;
     rc = launch_groups(h, args, h->cl_grid);
     if (rc != IPC_OK) return rc;
     const bool ok = h->cl_hout[0] != 0.0;
@@ -607,9 +644,10 @@ int ipc_agreement_check(ipc_handle* h, int from, int to, const double* meas, con
 
 // The candidate loop of simulating_incremental_data (src/simulation.cpp:34-47) for n candidates in the given order, with exactly
 // the sequential semantics of n ipc_agreement_check calls. Most candidates are rejected and a rejection leaves the IPC object
-// untouched, so the next `stream_depth` candidates are solved SPECULATIVELY side by side (one group of SMs each) against the
-// current state; results are consumed in order up to and including the first accept, which is committed (window stored,
-// propagateCurrentGuess, consensus set grown) and invalidates the later ones of the round: they are simply solved again.
+// untouched, so up to `stream_depth` candidates are in flight at once, each solved SPECULATIVELY against the current state by its
+// own group of SMs (one cooperative launch per candidate, one CUDA stream per slot). Results are consumed strictly in order; a slot
+// that finishes is refilled with the next candidate at once. An accept is committed (window stored, propagateCurrentGuess, consensus
+// set grown); it invalidates every later solve in flight: those are told to give up (abort word) and are started again.
 int ipc_agreement_check_stream(ipc_handle* h, int n, const int* from, const int* to, const double* meas, const double* info, int* accepted,
                                ipc_check_info* out_info) {
     if (!h || n < 0 || (n && (!from || !to || !meas || !info || !accepted))) return fail(IPC_ERR_ARG, "bad arguments");
@@ -617,45 +655,87 @@ int ipc_agreement_check_stream(ipc_handle* h, int n, const int* from, const int*
         if (from[i] < 0 || to[i] < 0 || from[i] >= h->n || to[i] >= h->n || from[i] == to[i]) return fail(IPC_ERR_ARG, "candidate " + std::to_string(i) + " has invalid vertex ids");
     CUDA_TRY(cudaSetDevice(h->device));
     const int depth = std::max(1, std::min(h->stream_depth, CL_MAX_SLOTS));
+    const int group_size = depth == 1 ? h->cl_grid : std::max(1, h->cl_grid / depth);
     const int mw = h->mw, dd = h->d * h->d;
-    int i = 0;
-    while (i < n) {
-        const int m = std::min(depth, n - i);
-        const int group_size = std::max(1, h->cl_grid / (m == 1 ? 1 : depth));
-        std::vector<StreamArgs> args(m);
-        std::vector<std::pair<int, int>> LK(m);
-        for (int s = 0; s < m; ++s) {
-            int lo, hi; std::vector<LoopRef> loops;
-            cluster_of(h, from[i + s], to[i + s], meas + (size_t)mw * (i + s), info + (size_t)dd * (i + s), lo, hi, loops);
-            const bool slow = loops.size() > 1;
-            int rc = slot_prepare(h, s, lo, hi, loops, slow ? h->cfg.slow_reject_th : h->cfg.fast_reject_th,
-                                  slow ? h->cfg.slow_reject_iter_base : h->cfg.fast_reject_iter_base, /*commit=*/0, false, args[s]);
-            if (rc != IPC_OK) { h->staging.clear(); return rc; }
-            LK[s] = {hi - lo, (int)loops.size()};
+    if (!h->slot_stream[0]) {
+        for (int s = 0; s < CL_MAX_SLOTS; ++s) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&h->slot_stream[s], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->slot_ev[s], cudaEventDisableTiming));
         }
-        int rc = launch_groups(h, args, group_size);
-        if (rc != IPC_OK) return rc;
-        int used = 0;
-        for (int s = 0; s < m; ++s) {
+        CUDA_TRY(cudaEventCreateWithFlags(&h->commit_ev, cudaEventDisableTiming));
+        CUDA_TRY(cudaHostAlloc(&h->h_abort, sizeof(int) * CL_MAX_SLOTS, cudaHostAllocMapped));
+        std::fill(h->h_abort, h->h_abort + CL_MAX_SLOTS, 0);
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    struct Fl { int cand = -1; bool busy = false, done = false; int L = 0, K = 0; double t_launch = 0; };
+    const bool trace = getenv("IPC_STREAM_TRACE") != nullptr;
+    const auto t_origin = std::chrono::steady_clock::now();
+    auto now_ms = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_origin).count(); };
+    Fl fl[CL_MAX_SLOTS];
+    int next_launch = 0, next_final = 0;
+    auto fail_out = [&](int rc) { for (int s = 0; s < depth; ++s) cudaStreamSynchronize(h->slot_stream[s]); return rc; };
+    while (next_final < n) {
+        bool progressed = false;
+        // refill free slots with the next candidates, solved against the CURRENT state
+        for (int s = 0; s < depth && next_launch < n; ++s) {
+            if (fl[s].busy || fl[s].done) continue;
+            const int c = next_launch++;
+            int lo, hi; std::vector<LoopRef> loops;
+            cluster_of(h, from[c], to[c], meas + (size_t)mw * c, info + (size_t)dd * c, lo, hi, loops);
+            const bool slow = loops.size() > 1;
+            StreamArgs A;
+            int rc = slot_prepare(h, s, lo, hi, loops, slow ? h->cfg.slow_reject_th : h->cfg.fast_reject_th,
+                                  slow ? h->cfg.slow_reject_iter_base : h->cfg.fast_reject_iter_base, /*commit=*/0, false, A, h->slot_stream[s]);
+            if (rc != IPC_OK) return fail_out(rc);
+            A.abort = h->h_abort + s;
+            rc = slot_launch(h, s, A, group_size, h->slot_stream[s], /*cooperative=*/depth == 1);
+            if (rc != IPC_OK) return fail_out(rc);
+            CUDA_TRY(cudaEventRecord(h->slot_ev[s], h->slot_stream[s]));
+            fl[s].cand = c; fl[s].busy = true; fl[s].done = false; fl[s].L = hi - lo; fl[s].K = (int)loops.size(); fl[s].t_launch = now_ms();
+            progressed = true;
+        }
+        for (int s = 0; s < depth; ++s) {
+            if (!fl[s].busy) continue;
+            const cudaError_t q = cudaEventQuery(h->slot_ev[s]);
+            if (q == cudaSuccess) {
+                fl[s].busy = false; fl[s].done = true; progressed = true;
+                if (trace) std::fprintf(stderr, "slot %d cand %d K %d launched %.3f done %.3f ms\n", s, fl[s].cand, fl[s].K, fl[s].t_launch, now_ms());
+            }
+            else if (q != cudaErrorNotReady) return fail_out(fail(IPC_ERR_CUDA, std::string("stream slot: ") + cudaGetErrorString(q)));
+        }
+        // consume finished solves in candidate order
+        for (;;) {
+            int s = -1;
+            for (int t = 0; t < depth; ++t) if (fl[t].done && fl[t].cand == next_final) s = t;
+            if (s < 0) break;
             const double* o = h->cl_hout + 16 * s;
             const bool ok = o[0] != 0.0;
-            accepted[i + s] = ok ? 1 : 0;
-            if (out_info) info_from(o, LK[s].first, LK[s].second, out_info + i + s);
-            ++used;
-            if (ok) {     // commit slot s: store its window, propagateCurrentGuess, push_back (src/consensus.cpp:69-71)
-                const StreamArgs& A = args[s];
-                const int cur = (int)o[8];
-                if (h->dim == 2) stream_commit_kernel<2><<<1, CL_NT, 0, h->stream>>>(A.B[cur].W, h->d_pose, A.lo, A.L, h->d_odom9, h->n, h->cl_stage);
-                else stream_commit_kernel<3><<<1, CL_NT, 0, h->stream>>>(A.B[cur].W, h->d_pose, A.lo, A.L, h->d_odom49, h->n, h->cl_stage);
-                CUDA_TRY(cudaGetLastError());
-                HostEdge e; e.from = from[i + s]; e.to = to[i + s];
-                e.meas.assign(meas + (size_t)mw * (i + s), meas + (size_t)mw * (i + s + 1)); e.info.assign(info + (size_t)dd * (i + s), info + (size_t)dd * (i + s + 1));
-                h->hs.cns.push_back(std::move(e));
-                h->cl_n_wasted += m - 1 - s;
-                break;
-            }
+            accepted[next_final] = ok ? 1 : 0;
+            if (out_info) info_from(o, fl[s].L, fl[s].K, out_info + next_final);
+            h->cl_n_fact += (long long)o[6]; h->cl_n_trial += (long long)o[7]; ++h->cl_n_checks;
+            fl[s].done = false; fl[s].cand = -1;
+            const int c = next_final++;
+            progressed = true;
+            if (!ok) continue;
+            // accept: every later solve in flight started from a state that no longer exists
+            for (int t = 0; t < depth; ++t) if (fl[t].busy) h->h_abort[t] = 1;
+            for (int t = 0; t < depth; ++t) if (fl[t].busy || fl[t].done) { CUDA_TRY(cudaStreamSynchronize(h->slot_stream[t])); ++h->cl_n_wasted; }
+            for (int t = 0; t < depth; ++t) { h->h_abort[t] = 0; fl[t] = Fl{}; }
+            next_launch = next_final;
+            // commit slot s: store its window, propagateCurrentGuess, push_back (src/consensus.cpp:69-71)
+            const StreamArgs& A = h->slots[s].args_host;
+            const int cur = (int)o[8];
+            if (h->dim == 2) stream_commit_kernel<2><<<1, CL_NT, 0, h->stream>>>(A.B[cur].W, h->d_pose, A.lo, A.L, h->d_odom9, h->n, h->cl_stage);
+            else stream_commit_kernel<3><<<1, CL_NT, 0, h->stream>>>(A.B[cur].W, h->d_pose, A.lo, A.L, h->d_odom49, h->n, h->cl_stage);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(h->commit_ev, h->stream));
+            for (int t = 0; t < depth; ++t) CUDA_TRY(cudaStreamWaitEvent(h->slot_stream[t], h->commit_ev, 0));
+            HostEdge e; e.from = from[c]; e.to = to[c];
+            e.meas.assign(meas + (size_t)mw * c, meas + (size_t)mw * (c + 1)); e.info.assign(info + (size_t)dd * c, info + (size_t)dd * (c + 1));
+            h->hs.cns.push_back(std::move(e));
+            break;
         }
-        i += used;
+        if (!progressed) std::this_thread::yield();
     }
     CUDA_TRY(cudaStreamSynchronize(h->stream));
     return IPC_OK;
@@ -695,9 +775,9 @@ int ipc_final_optimize(ipc_handle* h, int max_iterations, double* chi2, int* ite
     for (const HostEdge& e : h->hs.cns) loops.push_back(LoopRef{e.from, e.to, e.meas.data(), e.info.data()});
     std::vector<StreamArgs> args(1);
     h->cl_odom = d2 ? h->d_odom9_raw : h->d_odom49_raw;        // odometry information / s_factor (src/simulation.cpp:55-56)
-    int rc = slot_prepare(h, 0, lo, hi, loops, 0.0, max_iterations, /*commit=*/2, /*exact_iters=*/true, args[0]);
+    int rc = slot_prepare(h, 0, lo, hi, loops, 0.0, max_iterations, /*commit=*/2, /*exact_iters=*/true, args[0], h->stream);
     h->cl_odom = nullptr;
-    if (rc != IPC_OK) { h->staging.clear(); return rc; }
+    if (rc != IPC_OK) return rc;
     rc = launch_groups(h, args, h->cl_grid);
     if (rc != IPC_OK) return rc;
     ipc_check_info ci{};

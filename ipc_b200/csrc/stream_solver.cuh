@@ -45,6 +45,8 @@ struct StreamArgs {
     double th; int max_iter; int max_tries; double noise_eps;
     int commit;                    // 1: agreementCheck semantics (store the window on accept + propagateCurrentGuess); 2: final optimisation
                                    // (always store); 0: leave the global estimates alone (speculative slot: the host commits in order)
+    const int* abort;              // host-mapped word (may be null): non-zero = give up at the next iteration (a speculative solve that
+                                   // an earlier accept has invalidated)
     double* out;                   // results: [0] accepted, [1] max chi2, [2] cand chi2, [3] sum chi2, [4] iterations, [5] evals,
                                    // [6] factorisations, [7] trial states evaluated, [8] index of the final state buffer
     unsigned long long* prof;      // window CTA / thread 0 cycle counters per phase (ipc_stream_profile): 0 setup, 1 assemble, 2 factor,
@@ -99,100 +101,161 @@ __device__ __noinline__ void chol32_warp(CholSmem& sm, int lane) {
 }
 
 #define CH_PROF(i) do { if (prof && g.rank == 0 && threadIdx.x == 0) { const long long now_ = clock64(); prof[i] += (unsigned long long)(now_ - cpt_); cpt_ = now_; } } while (0)
-// dinv (shared memory of the window CTA, may be null elsewhere): 1 / L_cc of every column, for the back-substitution
-__device__ __forceinline__ void chol_factor(double* S, int ld, int n_pad, CholSmem& sm, Group& g, double* dinv, unsigned long long* prof = nullptr) {
+
+// rank 0: load the diagonal block at (j0, j0), factor it (warp 0, registers), write L_pp back and publish 1 / L_cc (global dinv_g for
+// the panel solves of every CTA; shared dinv of the window CTA for the back-substitution). `pre` = the block is already in sm.Dg.
+__device__ __forceinline__ void chol_diag_rank0(double* S, int ld, int j0, CholSmem& sm, double* dinv, double* dinv_g, bool pre) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = CL_NT / 32;
+    if (!pre) {
+        for (int c = warp; c < CH_NB; c += NW) sm.Dg[lane][c] = S[(size_t)(j0 + c) * ld + j0 + lane];
+    }
+    __syncthreads();
+    if (warp == 0) chol32_warp(sm, lane);
+    __syncthreads();
+    for (int c = warp; c < CH_NB; c += NW) if (lane >= c) S[(size_t)(j0 + c) * ld + j0 + lane] = sm.Dg[lane][c];
+    if (warp == 0) { dinv[j0 + lane] = sm.inv[lane]; dinv_g[j0 + lane] = sm.inv[lane]; }
+}
+
+// X L_pp^T = A_ip for NS row blocks (rb0, rb0 + stride, ...) of one CTA: warp w solves rows w and w + 16 of every block (2 NS
+// independent substitution chains), lane c holds a[r][c]. sm.Dg = L_pp, sm.inv = 1 / L_cc.
+template <int NS> __device__ __forceinline__ void chol_panel_pass(double* S, int ld, int j0, int rb0, int stride, CholSmem& sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = CL_NT / 32;
+    __syncthreads();
+#pragma unroll
+    for (int s4 = 0; s4 < NS; ++s4) {
+        const int rb = rb0 + s4 * stride;
+        for (int c = warp; c < CH_NB; c += NW) sm.Xa[s4][c][lane] = S[(size_t)(j0 + c) * ld + rb * CH_NB + lane];      // Xa[s][c][r]
+    }
+    __syncthreads();
+    double a[2 * NS];
+#pragma unroll
+    for (int s4 = 0; s4 < NS; ++s4) { a[2 * s4] = sm.Xa[s4][lane][warp]; a[2 * s4 + 1] = sm.Xa[s4][lane][warp + NW]; }
+#pragma unroll 4
+    for (int c = 0; c < CH_NB; ++c) {
+        const double ic = sm.inv[c], lc = sm.Dg[lane][c];
+#pragma unroll
+        for (int e = 0; e < 2 * NS; ++e) {
+            const double x = __shfl_sync(0xffffffffu, a[e], c) * ic;
+            a[e] = lane == c ? x : (lane > c ? fma(-x, lc, a[e]) : a[e]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s4 = 0; s4 < NS; ++s4) { sm.Xa[s4][lane][warp] = a[2 * s4]; sm.Xa[s4][lane][warp + NW] = a[2 * s4 + 1]; }
+    __syncthreads();
+#pragma unroll
+    for (int s4 = 0; s4 < NS; ++s4) {
+        const int rb = rb0 + s4 * stride;
+        for (int c = warp; c < CH_NB; c += NW) S[(size_t)(j0 + c) * ld + rb * CH_NB + lane] = sm.Xa[s4][c][lane];
+    }
+}
+
+// dinv: shared memory of the window CTA (null elsewhere); dinv_g: global, n_pad doubles (reuses the force vector z, which is only
+// written after the factorisation).
+// Schedule per 32-column panel p (look-ahead of one diagonal block):
+//   panel  : every CTA that owns row blocks of the panel loads the FACTORED L_pp and solves its rows (up to four 32-row blocks per
+//            pass, eight independent substitution chains per warp)                                         -> group barrier
+//   update : rank 0 updates the next diagonal block and factors it at once (one warp, registers) while ranks 1.. update the rest of
+//            the trailing matrix, one 32 x 32 tile per four warps (rows on lanes, 8 columns per warp as shared-memory broadcasts:
+//            bound by the fp64 pipe, not by shared-memory bandwidth); C is fetched together with the X panels  -> group barrier
+__device__ __forceinline__ void chol_factor(double* S, int ld, int n_pad, CholSmem& sm, Group& g, double* dinv, double* dinv_g, unsigned long long* prof = nullptr) {
     long long cpt_ = clock64();
     const int nbk = n_pad / CH_NB;             // column blocks
     const int nrb = nbk + 1;                   // row blocks (the last one holds the right-hand side row)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = CL_NT / 32;
+    const int slot = warp >> 2, q = warp & 3, st = threadIdx.x & 127;
+    if (g.rank == 0) chol_diag_rank0(S, ld, 0, sm, dinv, dinv_g, false);
+    group_barrier(g);
+    CH_PROF(8);
     for (int p = 0; p < nbk; ++p) {
         const int j0 = p * CH_NB;
-        // ---- panel: row blocks p+1 .. nrb-1 are dealt round robin; every owner factors the diagonal block itself
+        // ---- panel solve: row blocks p+1 .. nrb-1 dealt round robin over the group
         const int first_rb = p + 1 + g.rank;
         if (first_rb < nrb) {
-            // diagonal block and this CTA's first row block -> shared memory (column c by warp: coalesced)
-            for (int c = warp; c < CH_NB; c += NW) {
-                sm.Dg[lane][c] = S[(size_t)(j0 + c) * ld + j0 + lane];
-                sm.Xa[0][c][lane] = S[(size_t)(j0 + c) * ld + first_rb * CH_NB + lane];      // [c][r]
+            for (int c = warp; c < CH_NB; c += NW) sm.Dg[lane][c] = S[(size_t)(j0 + c) * ld + j0 + lane];
+            if (warp == 0) sm.inv[lane] = dinv_g[j0 + lane];
+            for (int rb0 = first_rb; rb0 < nrb; rb0 += g.size * CH_SLOTS) {
+                const int ns = min(CH_SLOTS, (nrb - rb0 + g.size - 1) / g.size);     // row blocks of this CTA in this pass
+                if (ns == 1) chol_panel_pass<1>(S, ld, j0, rb0, g.size, sm);
+                else if (ns == 2) chol_panel_pass<2>(S, ld, j0, rb0, g.size, sm);
+                else if (ns == 3) chol_panel_pass<3>(S, ld, j0, rb0, g.size, sm);
+                else chol_panel_pass<4>(S, ld, j0, rb0, g.size, sm);
             }
-            __syncthreads();
-            if (warp == 0) chol32_warp(sm, lane);
-            __syncthreads();
-            if (g.rank == 0) {                  // the window CTA always owns a row block: it writes L_pp back and keeps 1 / L_cc
-                for (int c = warp; c < CH_NB; c += NW) if (lane >= c) S[(size_t)(j0 + c) * ld + j0 + lane] = sm.Dg[lane][c];
-                if (dinv && warp == 0) dinv[j0 + lane] = sm.inv[lane];
-            }
-            CH_PROF(8);
-            for (int rb = first_rb; rb < nrb; rb += g.size) {
-                const int i0 = rb * CH_NB;
-                if (rb != first_rb) {
-                    __syncthreads();
-                    for (int c = warp; c < CH_NB; c += NW) sm.Xa[0][c][lane] = S[(size_t)(j0 + c) * ld + i0 + lane];
-                    __syncthreads();
-                }
-                // X L_pp^T = A_ip: warp w solves rows w and w + NW (two independent chains), lane c holds a[r][c]
-                double a0 = sm.Xa[0][lane][warp], a1 = sm.Xa[0][lane][warp + NW];
-#pragma unroll 4
-                for (int c = 0; c < CH_NB; ++c) {
-                    const double ic = sm.inv[c], lc = sm.Dg[lane][c];
-                    const double x0 = __shfl_sync(0xffffffffu, a0, c) * ic, x1 = __shfl_sync(0xffffffffu, a1, c) * ic;
-                    if (lane == c) { a0 = x0; a1 = x1; }
-                    else if (lane > c) { a0 = fma(-x0, lc, a0); a1 = fma(-x1, lc, a1); }
-                }
-                __syncthreads();
-                sm.Xa[0][lane][warp] = a0; sm.Xa[0][lane][warp + NW] = a1;
-                __syncthreads();
-                for (int c = warp; c < CH_NB; c += NW) S[(size_t)(j0 + c) * ld + i0 + lane] = sm.Xa[0][c][lane];
-            }
-            CH_PROF(9);
         }
+        CH_PROF(9);
         group_barrier(g);
         CH_PROF(10);
-        // ---- trailing update: C_ij -= X_i X_j^T for block rows i >= j > p. One 32 x 32 tile per slot of four warps (warp q of the
-        // slot owns columns 8q .. 8q+7 of the tile: rows come from distinct lanes, columns are shared-memory broadcasts, so the loop
-        // is bound by the fp64 pipe, not by shared-memory bandwidth). Tiles are dealt to CTAs first, then to slots.
+        // ---- trailing update: C_ij -= X_i X_j^T for block rows i >= j > p
         const int base = p + 1;
         const int m = nbk - base;                                 // remaining column blocks; row blocks: m + 1
         if (m > 0) {
             const int T = (m + 1) * (m + 2) / 2 - 1;              // lower triangle of (m+1) x (m+1) blocks without the last diagonal block
-            const int slot = warp >> 2, q = warp & 3, st = threadIdx.x & 127;
-            for (int t0 = g.rank; t0 < T; t0 += g.size * CH_SLOTS) {
-                const int t = t0 + slot * g.size;
-                const bool on = t < T;
-                int ib = 0, jb = 0;
-                if (on) {
-                    int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-                    while (I * (I + 1) / 2 > t) --I;
-                    while ((I + 1) * (I + 2) / 2 <= t) ++I;
-                    ib = base + I; jb = base + (t - I * (I + 1) / 2);
+            // tile 0 is the next diagonal block: rank 0 updates it and factors it right away (look-ahead); the other tiles go to
+            // ranks 1 .. size-1 (or to everyone but tile 0 when the group is a single CTA)
+            const bool solo = g.size == 1;
+            const int workers = solo ? 1 : g.size - 1, wrank = solo ? 0 : g.rank - 1;
+            if (g.rank == 0) {
+                // diagonal tile (base, base): X_i = X_j
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = warp + NW * e;
+                    sm.Xa[0][k][lane] = S[(size_t)(j0 + k) * ld + base * CH_NB + lane];
+                    sm.Dg[lane][k] = S[(size_t)(base * CH_NB + k) * ld + base * CH_NB + lane];
                 }
                 __syncthreads();
-                if (on) {
-                    // slot-local load: 128 threads, X_i and X_j (32 x 32 each): thread st loads rows (st & 31), columns (st >> 5) + 4 e
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int k = (st >> 5) + 4 * e, r = st & 31;
-                        sm.Xa[slot][k][r] = S[(size_t)(j0 + k) * ld + ib * CH_NB + r];
-                        sm.Xb[slot][k][r] = S[(size_t)(j0 + k) * ld + jb * CH_NB + r];
-                    }
-                }
-                __syncthreads();
-                if (on) {
-                    double acc[8];
-#pragma unroll
-                    for (int b = 0; b < 8; ++b) acc[b] = 0;
+                {   // thread (row = lane, cols = warp, warp + NW)
+                    double acc0 = 0, acc1 = 0;
 #pragma unroll 8
-                    for (int k = 0; k < CH_NB; ++k) {
-                        const double xa = sm.Xa[slot][k][lane];
-                        const double4 b0 = *reinterpret_cast<const double4*>(&sm.Xb[slot][k][8 * q]);
-                        const double4 b1 = *reinterpret_cast<const double4*>(&sm.Xb[slot][k][8 * q + 4]);
-                        acc[0] = fma(xa, b0.x, acc[0]); acc[1] = fma(xa, b0.y, acc[1]); acc[2] = fma(xa, b0.z, acc[2]); acc[3] = fma(xa, b0.w, acc[3]);
-                        acc[4] = fma(xa, b1.x, acc[4]); acc[5] = fma(xa, b1.y, acc[5]); acc[6] = fma(xa, b1.z, acc[6]); acc[7] = fma(xa, b1.w, acc[7]);
+                    for (int k = 0; k < CH_NB; ++k) { const double xa = sm.Xa[0][k][lane]; acc0 = fma(xa, sm.Xa[0][k][warp], acc0); acc1 = fma(xa, sm.Xa[0][k][warp + NW], acc1); }
+                    sm.Dg[lane][warp] -= acc0; sm.Dg[lane][warp + NW] -= acc1;
+                }
+                chol_diag_rank0(S, ld, base * CH_NB, sm, dinv, dinv_g, true);
+            }
+            if (g.rank > 0 || solo) {
+                for (int t0 = 1 + wrank; t0 < T; t0 += workers * CH_SLOTS) {
+                    const int t = t0 + slot * workers;
+                    const bool on = t < T;
+                    int ib = 0, jb = 0;
+                    if (on) {
+                        int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+                        while (I * (I + 1) / 2 > t) --I;
+                        while ((I + 1) * (I + 2) / 2 <= t) ++I;
+                        ib = base + I; jb = base + (t - I * (I + 1) / 2);
                     }
-                    double* c = S + (size_t)(jb * CH_NB + 8 * q) * ld + ib * CH_NB + lane;
+                    __syncthreads();
+                    double cold[8];
+                    double* cptr = S + (size_t)(jb * CH_NB + 8 * q) * ld + ib * CH_NB + lane;
+                    if (on) {
+                        // slot-local load: 128 threads, X_i and X_j (32 x 32 each); the C values of this thread ride along
 #pragma unroll
-                    for (int b = 0; b < 8; ++b) c[(size_t)b * ld] -= acc[b];
+                        for (int e = 0; e < 8; ++e) {
+                            const int k = (st >> 5) + 4 * e, r = st & 31;
+                            sm.Xa[slot][k][r] = S[(size_t)(j0 + k) * ld + ib * CH_NB + r];
+                            sm.Xb[slot][k][r] = S[(size_t)(j0 + k) * ld + jb * CH_NB + r];
+                        }
+#pragma unroll
+                        for (int b8 = 0; b8 < 8; ++b8) cold[b8] = cptr[(size_t)b8 * ld];
+                    }
+                    __syncthreads();
+                    if (on) {
+                        double acc[8];
+#pragma unroll
+                        for (int b8 = 0; b8 < 8; ++b8) acc[b8] = 0;
+#pragma unroll 8
+                        for (int k = 0; k < CH_NB; ++k) {
+                            const double xa = sm.Xa[slot][k][lane];
+                            const double4 b0 = *reinterpret_cast<const double4*>(&sm.Xb[slot][k][8 * q]);
+                            const double4 b1 = *reinterpret_cast<const double4*>(&sm.Xb[slot][k][8 * q + 4]);
+                            acc[0] = fma(xa, b0.x, acc[0]); acc[1] = fma(xa, b0.y, acc[1]); acc[2] = fma(xa, b0.z, acc[2]); acc[3] = fma(xa, b0.w, acc[3]);
+                            acc[4] = fma(xa, b1.x, acc[4]); acc[5] = fma(xa, b1.y, acc[5]); acc[6] = fma(xa, b1.z, acc[6]); acc[7] = fma(xa, b1.w, acc[7]);
+                        }
+#pragma unroll
+                        for (int b8 = 0; b8 < 8; ++b8) cptr[(size_t)b8 * ld] = cold[b8] - acc[b8];
+                    }
                 }
             }
         }
@@ -202,28 +265,32 @@ __device__ __forceinline__ void chol_factor(double* S, int ld, int n_pad, CholSm
     }
 }
 
-// Window CTA: L^T z = y with y in matrix row n_pad. zs, dinv: shared memory, n_pad doubles each. One warp per column of a block.
+// Window CTA: L^T z = y with y in matrix row n_pad. zs, dinv: shared memory, n_pad doubles each. Warp w owns columns w and w + 16 of
+// a block: both dot products run together, eight loads in flight per lane.
 __device__ __forceinline__ void chol_back_substitute(const double* S, int ld, int n_pad, double* zs, const double* dinv, CholSmem& sm, double* z_out) {
     const int nbk = n_pad / CH_NB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = CL_NT / 32;
+    static_assert(NW * 2 == CH_NB, "two columns per warp");
     for (int b = nbk - 1; b >= 0; --b) {
-        for (int w = warp; w < CH_NB; w += NW) {
-            const int i = b * CH_NB + w;                          // this warp's column
-            const double* col = S + (size_t)i * ld;
-            double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-            int j = (b + 1) * CH_NB + lane;
-            for (; j + 96 < n_pad; j += 128) {                    // four loads in flight per lane
-                const double c0 = col[j], c1 = col[j + 32], c2 = col[j + 64], c3 = col[j + 96];
-                p0 = fma(c0, zs[j], p0); p1 = fma(c1, zs[j + 32], p1); p2 = fma(c2, zs[j + 64], p2); p3 = fma(c3, zs[j + 96], p3);
-            }
-            for (; j < n_pad; j += 32) p0 = fma(col[j], zs[j], p0);
-            double part = (p0 + p1) + (p2 + p3);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            sm.Dg[lane][w] = col[b * CH_NB + lane];               // diagonal block, Dg[row][col]
-            if (lane == 0) sm.inv[w] = col[n_pad] - part;         // y_i - sum_{j beyond the block} L_ji z_j
+        const double* c0 = S + (size_t)(b * CH_NB + warp) * ld;
+        const double* c1 = S + (size_t)(b * CH_NB + warp + NW) * ld;
+        double p0 = 0, p1 = 0, p2 = 0, p3 = 0, r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        int j = (b + 1) * CH_NB + lane;
+        for (; j + 96 < n_pad; j += 128) {
+            const double a0 = c0[j], a1 = c0[j + 32], a2 = c0[j + 64], a3 = c0[j + 96];
+            const double b0 = c1[j], b1 = c1[j + 32], b2 = c1[j + 64], b3 = c1[j + 96];
+            const double z0 = zs[j], z1 = zs[j + 32], z2 = zs[j + 64], z3 = zs[j + 96];
+            p0 = fma(a0, z0, p0); p1 = fma(a1, z1, p1); p2 = fma(a2, z2, p2); p3 = fma(a3, z3, p3);
+            r0 = fma(b0, z0, r0); r1 = fma(b1, z1, r1); r2 = fma(b2, z2, r2); r3 = fma(b3, z3, r3);
         }
+        for (; j < n_pad; j += 32) { const double zz = zs[j]; p0 = fma(c0[j], zz, p0); r0 = fma(c1[j], zz, r0); }
+        double part0 = (p0 + p1) + (p2 + p3), part1 = (r0 + r1) + (r2 + r3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { part0 += __shfl_xor_sync(0xffffffffu, part0, o); part1 += __shfl_xor_sync(0xffffffffu, part1, o); }
+        sm.Dg[lane][warp] = c0[b * CH_NB + lane];                 // diagonal block, Dg[row][col]
+        sm.Dg[lane][warp + NW] = c1[b * CH_NB + lane];
+        if (lane == 0) { sm.inv[warp] = c0[n_pad] - part0; sm.inv[warp + NW] = c1[n_pad] - part1; }   // y_i - sum_{j beyond the block} L_ji z_j
         __syncthreads();
         if (warp == 0) {
             double r = sm.inv[lane];
@@ -341,7 +408,7 @@ __global__ void __launch_bounds__(CL_NT, 1) stream_check_kernel(const StreamArgs
         T::assemble(A, cur, g);
         group_barrier(g);
         ST_PROF(1);
-        chol_factor(A.S, A.ld, A.n_pad, cs, g, cta0 ? dinv : nullptr, A.prof);
+        chol_factor(A.S, A.ld, A.n_pad, cs, g, dinv, A.z, A.prof);
         ST_PROF(2);
         ++n_fact;
         if (cta0) {
@@ -423,7 +490,8 @@ __global__ void __launch_bounds__(CL_NT, 1) stream_check_kernel(const StreamArgs
             ST_PROF(6);
             if (threadIdx.x == 0) {
                 A.ctl[1] = dl.cur;
-                A.ctl[0] = (dl.ok && it + 1 < A.max_iter) ? 1 : 0;
+                const bool aborted = A.abort && *reinterpret_cast<const volatile int*>(A.abort) != 0;
+                A.ctl[0] = (dl.ok && it + 1 < A.max_iter && !aborted) ? 1 : 0;
                 __threadfence();
             }
             __syncthreads();

@@ -120,6 +120,12 @@ void orc_get_consensus(void* hv, int* from_to) {   // 2 ints per edge
     if (hb->dim == 2) { auto& c = static_cast<Handle<G2>*>(hb)->ipc.cns; for (size_t i = 0; i < c.size(); ++i) { from_to[2 * i] = c[i].from; from_to[2 * i + 1] = c[i].to; } }
     else { auto& c = static_cast<Handle<G3>*>(hb)->ipc.cns; for (size_t i = 0; i < c.size(); ++i) { from_to[2 * i] = c[i].from; from_to[2 * i + 1] = c[i].to; } }
 }
+// the final full-graph optimisation (src/simulation.cpp:50-65); returns chi2, *iterations = Dogleg iterations executed
+double orc_final_optimize(void* hv, int max_iterations, int* iterations) {
+    auto* hb = static_cast<HandleBase*>(hv);
+    if (hb->dim == 2) return static_cast<Handle<G2>*>(hb)->ipc.finalOptimize(max_iterations, iterations);
+    return static_cast<Handle<G3>*>(hb)->ipc.finalOptimize(max_iterations, iterations);
+}
 void orc_get_poses(void* hv, double* out) {        // 3 (x y th) or 7 (x y z qx qy qz qw) per pose
     auto* hb = static_cast<HandleBase*>(hv);
     if (hb->dim == 2) { auto& e = static_cast<Handle<G2>*>(hb)->ipc.est; for (size_t i = 0; i < e.size(); ++i) G2::to_flat(e[i], out + 3 * i); }

@@ -51,6 +51,8 @@ def lib():
         _LIB.orc_consensus_size.argtypes = [C.c_void_p]
         _LIB.orc_get_consensus.argtypes = [C.c_void_p, C.c_void_p]
         _LIB.orc_get_poses.argtypes = [C.c_void_p, C.c_void_p]
+        _LIB.orc_final_optimize.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        _LIB.orc_final_optimize.restype = C.c_double
         _LIB.orc_check_batch.argtypes = [C.c_void_p] + [C.c_void_p] * 4 + [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _LIB.orc_edge_eval.argtypes = [C.c_int] + [C.c_void_p] * 6
         _LIB.orc_oplus.argtypes = [C.c_int] + [C.c_void_p] * 3
@@ -110,6 +112,12 @@ class OracleIPC:
         out = np.zeros((self.g.n_poses, self.meas_w), dtype=np.float64)
         lib().orc_get_poses(self._h, _p(out))
         return out
+
+    def final_optimize(self, max_iterations: int = 1000):
+        """Final full-graph optimisation of simulating_incremental_data (src/simulation.cpp:50-65). Returns (chi2, iterations)."""
+        it = C.c_int(0)
+        chi2 = lib().orc_final_optimize(self._h, int(max_iterations), C.byref(it))
+        return float(chi2), it.value
 
     def check_batch(self, check_ptr, check_idx, n_threads: int = 1):
         """Independent checks from the dead-reckoned state; see orc_check_batch."""

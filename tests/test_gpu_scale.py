@@ -1,0 +1,99 @@
+"""Parity at BASELINE sizes and for the rows next to the hot path, on the GPU box (pytest -m gpu), through the C ABI:
+  * final full-graph optimisation (src/simulation.cpp:50-65) against the oracle: poses <= 1e-6, chi2 <= 1e-4 relative;
+  * the full-size M3500-shaped stream prefix reaching clusters of K >= 250 loops against the committed oracle fixture;
+  * windows longer than shared memory holds (L > 5400, global-state kernel) from the 50 k-pose and City10000-shaped configs;
+  * a full-size Sphere2500 SE(3) sample of >= 5000 checks."""
+import os
+
+import numpy as np
+import pytest
+
+from ipc_b200 import api, sharding, synth
+from tests.golden_util import GOLDEN, rel_err
+
+pytestmark = pytest.mark.gpu
+CHI2_RTOL = 1e-4
+
+
+def _angle_diff(a, b):
+    d = a - b
+    return np.abs((d + np.pi) % (2 * np.pi) - np.pi)
+
+
+def _pose_err(dim, p, q):
+    if dim == 2:
+        return max(np.abs(p[:, :2] - q[:, :2]).max(), _angle_diff(p[:, 2], q[:, 2]).max())
+    sgn = np.sign((p[:, 3:] * q[:, 3:]).sum(axis=1, keepdims=True))          # q and -q are the same rotation
+    return max(np.abs(p[:, :3] - q[:, :3]).max(), np.abs(p[:, 3:] - sgn * q[:, 3:]).max())
+
+
+@pytest.mark.parametrize("name,scale", [("intel", 0.5), ("sphere", 0.05)])
+def test_final_optimisation_matches_oracle(gpu_lib, oracle_lib, name, scale):
+    """N1: propagateGuess, odometry information / s_factor, Dogleg optimize(1000) on odometry + consensus set."""
+    g, cfg = synth.make_config(name, scale=scale)
+    o = g.time_order()
+    orc = oracle_lib.OracleIPC(g, cfg, noise_exit=True)
+    oacc, _ = orc.run_stream(o)
+    ochi, oit = orc.final_optimize(1000)
+    ipc = gpu_lib.IPC.from_graph(g, cfg, candidates=False)
+    acc, _ = ipc.agreementCheckStream(g.loop_from[o], g.loop_to[o], g.loop_meas[o], g.loop_info[o])
+    assert np.array_equal(acc, oacc) and acc.sum() >= 5
+    chi, it = ipc.final_optimize(1000)
+    assert it >= 2 and abs(chi - ochi) <= CHI2_RTOL * ochi
+    assert _pose_err(g.dim, ipc.poses(), orc.poses()) < 1e-6
+    ipc.close()
+
+
+def test_m3500_stream_prefix_matches_oracle_fixture(gpu_lib):
+    """Full-size M3500-shaped stream, first 1700 time-ordered candidates: clusters grow past K = 250 loops (the regime the
+    reference's own tester spends its time in). Inlier set bit-identical, chi2 within 1e-4, estimates and
+    the final optimisation of the resulting consensus set equal the oracle's (tests/golden/make_golden_large.py)."""
+    z = np.load(os.path.join(GOLDEN, "stream_se2_m3500_prefix.npz"))
+    g, cfg = synth.make_config("m3500")
+    o = z["order"]
+    assert np.array_equal(o, g.time_order()[: len(o)])
+    ipc = gpu_lib.IPC.from_graph(g, cfg, candidates=False)
+    acc, info = ipc.agreementCheckStream(g.loop_from[o], g.loop_to[o], g.loop_meas[o], g.loop_info[o])
+    assert np.array_equal(acc, z["accept"])
+    assert np.array_equal(info["n_loops"], z["n_cluster"] + 1) and info["n_loops"].max() >= 250
+    assert rel_err(info["max_chi2"], z["max_chi2"]).max() < CHI2_RTOL
+    assert np.array_equal(ipc.getMaxConsensusSet(), z["consensus"])
+    assert _pose_err(2, ipc.poses(), z["poses_stream"]) < 1e-6
+    chi, it = ipc.final_optimize(1000)
+    assert abs(chi - float(z["final_chi2"])) <= CHI2_RTOL * float(z["final_chi2"])
+    assert _pose_err(2, ipc.poses(), z["poses_final"]) < 1e-6
+    ipc.close()
+
+
+@pytest.mark.parametrize("name,n_checks", [("synth50k", 160), ("city10k", 120)])
+def test_long_windows_match_oracle(gpu_lib, oracle_lib, name, n_checks):
+    """Windows longer than the shared-memory state holds (L > 5400 edges) at real size: the global-state kernel (MODE 1)."""
+    g, cfg = synth.make_config(name)
+    mem, cnd = api.pair_checks(g)
+    L = sharding.window_lengths(g, mem, cnd)
+    long_ = np.nonzero(L > 5400)[0]
+    assert len(long_) > n_checks
+    sel = np.sort(np.random.default_rng(4).choice(long_, n_checks, replace=False))
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem[sel], cnd[sel])
+    assert info["window_len"].min() > 5400
+    ptr, idx = api.checks_to_csr(mem[sel], cnd[sel])
+    oacc, orep = oracle_lib.OracleIPC(g, cfg, noise_exit=True).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
+    ipc.close()
+
+
+def test_sphere2500_full_size_sample_matches_oracle(gpu_lib, oracle_lib):
+    """BASELINE.json configs[2]: Sphere2500 SE(3) + 2000 outliers at full size, seeded sample of 5000 of the matrix checks."""
+    g, cfg = synth.make_config("sphere")
+    mem, cnd = api.pair_checks(g)
+    sel = np.sort(np.random.default_rng(12).choice(len(cnd), 5000, replace=False))
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem[sel], cnd[sel])
+    ptr, idx = api.checks_to_csr(mem[sel], cnd[sel])
+    oacc, orep = oracle_lib.OracleIPC(g, cfg, noise_exit=True).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
+    assert 0 < acc.sum() < len(acc)
+    ipc.close()
