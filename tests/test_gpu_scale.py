@@ -21,10 +21,14 @@ def _angle_diff(a, b):
 
 
 def _pose_err(dim, p, q):
+    """Largest pose difference: translations RELATIVE to the extent of the trajectory (a 1e-8 rad heading difference moves a pose
+    50 m down the chain by 5e-7 m), headings / quaternion components absolute."""
+    nt = 2 if dim == 2 else 3
+    extent = max(1.0, float(np.abs(q[:, :nt]).max()))
     if dim == 2:
-        return max(np.abs(p[:, :2] - q[:, :2]).max(), _angle_diff(p[:, 2], q[:, 2]).max())
+        return max(np.abs(p[:, :2] - q[:, :2]).max() / extent, _angle_diff(p[:, 2], q[:, 2]).max())
     sgn = np.sign((p[:, 3:] * q[:, 3:]).sum(axis=1, keepdims=True))          # q and -q are the same rotation
-    return max(np.abs(p[:, :3] - q[:, :3]).max(), np.abs(p[:, 3:] - sgn * q[:, 3:]).max())
+    return max(np.abs(p[:, :3] - q[:, :3]).max() / extent, np.abs(p[:, 3:] - sgn * q[:, 3:]).max())
 
 
 @pytest.mark.parametrize("name,scale", [("intel", 0.5), ("sphere", 0.05)])
@@ -53,6 +57,7 @@ def test_m3500_stream_prefix_matches_oracle_fixture(gpu_lib):
     o = z["order"]
     assert np.array_equal(o, g.time_order()[: len(o)])
     ipc = gpu_lib.IPC.from_graph(g, cfg, candidates=False)
+    ipc.set_option("noise_exit", 0)                  # g2o's verbatim retry rule on both sides (the fixture's oracle ran it)
     acc, info = ipc.agreementCheckStream(g.loop_from[o], g.loop_to[o], g.loop_meas[o], g.loop_info[o])
     assert np.array_equal(acc, z["accept"])
     assert np.array_equal(info["n_loops"], z["n_cluster"] + 1) and info["n_loops"].max() >= 250
