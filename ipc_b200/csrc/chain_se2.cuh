@@ -381,6 +381,7 @@ template <int NT> IPC_HD int vslot(int j, int S) { return j == 0 ? 0 : ((j - 1) 
 template <int NT> IPC_HD constexpr int scratch_slots(int capv) { return capv + 2 * NT + 2; }
 constexpr int RED_DOUBLES = 16 * (NPRE + 4);     // NW <= 16 warps (NT <= 512) x (NPRE + NS + 1), NS = 3
 constexpr int CHAIN_SMALL_DOUBLES = 2 * RED_DOUBLES + RED2_DOUBLES_ + 2 * NSPEC * SPECW + UNI_DOUBLES + (UNI_DOUBLES & 1);
+IPC_HD constexpr int stage_doubles(int capv) { return (3 * (capv + 2) + 1) & ~1; }   // MODE 2: staged odometry records (UNI, 3 doubles / edge), even
 constexpr int CHAIN_STATE_ARRAYS = 5;            // per-vertex doubles in shared memory (MODE 0)
 constexpr int CHAIN_SCRATCH_ARRAYS = 18;         // per-slot doubles in the global scratch (backup 3, b + h_gn 6, odometry record <= 9)
 
@@ -391,6 +392,8 @@ struct OdomView {            // odometry records of the window in HBM/L2, AoS: (
     const double* Vu;        //      ... and its inverse
     double* zs;              // the window's records again, in the per-CTA scratch in SLOT order (edge k0 + i of thread t at i * NT + t):
                              // written once per check by the dead-reckoning pass, read by every later pass as contiguous warp accesses
+    const double* sm;        // STG kernels: the window's records in SHARED memory, natural order (record of local edge k at sm + 3 k),
+                             // landed there by ONE bulk asynchronous copy (cp.async.bulk + mbarrier) per check
 };
 template <bool UNI> IPC_HD const double* odom_rec(const OdomView& O, int k) { return O.rec + (UNI ? 3 : 9) * (size_t)k; }
 IPC_HD double ldg_d(const double* p) {
@@ -454,8 +457,8 @@ IPC_HD void edge_prefix_terms_iso(const Lin2& e, double va, double vc, double xb
 }
 // z[0..2] (and D for the general case) of one odometry edge, loaded ahead of use
 template <bool UNI> struct OdomRec { double z[UNI ? 3 : 9]; };
-template <bool UNI> IPC_HD void odom_load(const OdomView& O, int es /* edge slot */, OdomRec<UNI>& r) {
-    const double* p = O.zs + (UNI ? 3 : 9) * (size_t)es;
+template <bool UNI, bool STG = false> IPC_HD void odom_load(const OdomView& O, int es /* edge slot */, int k /* local edge */, OdomRec<UNI>& r) {
+    const double* p = STG ? O.sm + 3 * (size_t)k : O.zs + (UNI ? 3 : 9) * (size_t)es;
 #pragma unroll
     for (int q = 0; q < (UNI ? 3 : 9); ++q) r.z[q] = p[q];     // plain loads: this kernel wrote them
 }
@@ -477,7 +480,7 @@ struct SweepOut { double chi, mx, hh, gain; };   // odometry chi2 sum / max at t
 // sums of the new linearisation at the special vertices. The GN step at vertex j needs the prefix of the OLD linearisation at
 // j: it is rebuilt on the fly from the old poses (no sincos: cos / sin are stored). Writes the pose backup when a step is
 // applied. Two block barriers.
-template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
+template <int NT, bool UNI, bool STG = false> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
                                               SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
     const int k0 = ts.k0, k1 = ts.k1;
     const StepSpec* sp = &M.U()->sol;
@@ -511,7 +514,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
     double gn6[6] = {0, 0, 0, 0, 0, 0};      // blend steps: (b, h_gn) of the next vertex, from the global scratch
     int sl = ts.tid + 1;                     // scratch slot of vertex k0 + 1; + NT per vertex
     if (k0 < k1) {
-        odom_load<UNI>(O, sl - 1, rn);       // edge slot = slot of the edge's head vertex - 1
+        odom_load<UNI, STG>(O, sl - 1, k0, rn);       // edge slot = slot of the edge's head vertex - 1
         if (mode == STEP_BLEND) { const double* gq = M.G(sl);
 #pragma unroll
             for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
@@ -523,7 +526,7 @@ template <int NT, bool UNI> IPC_HD void sweep(const ChainMem& M, const OdomView&
 #pragma unroll
         for (int q = 0; q < 6; ++q) g6[q] = gn6[q];
         if (j < k1) {
-            odom_load<UNI>(O, sl + NT - 1, rn);
+            odom_load<UNI, STG>(O, sl + NT - 1, j, rn);
             if (mode == STEP_BLEND) { const double* gq = M.G(sl + NT);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
@@ -919,7 +922,7 @@ template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, int buf, double 
 }
 
 // |h_gn|^2 of the current linearisation without applying it
-template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
+template <int NT, bool UNI, bool STG = false> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
     double v[1] = {0};
     const StepSpec* sp = &M.U()->sol;
     double pre[NPRE];
@@ -928,13 +931,13 @@ template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const Od
     P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
     OdomRec<UNI> rn;
     int es = ts.tid;
-    if (ts.k0 < ts.k1) odom_load<UNI>(O, es, rn);
+    if (ts.k0 < ts.k1) odom_load<UNI, STG>(O, es, ts.k0, rn);
     for (int k = ts.k0; k < ts.k1; ++k, es += NT) {
         const int j = k + 1;
         const double* pq = M.P(j);
         const P2 pb{pq[0], pq[1], pq[2]};
         const OdomRec<UNI> r = rn;
-        if (j < ts.k1) odom_load<UNI>(O, es + NT, rn);
+        if (j < ts.k1) odom_load<UNI, STG>(O, es + NT, j, rn);
         Lin2 e; double t[NPRE], h[3];
         odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
 #pragma unroll
@@ -953,7 +956,7 @@ template <int NT, bool UNI> IPC_HD double gn_norm_sq(const ChainMem& M, const Od
 // k0+1..k1 and the Hessian terms of the edges k0+1..k1 (thread 0 also edge 0); the one term that needs the next thread's first
 // gradient is completed after the block barrier from the scratch. Stands in for gn_norm_sq + a separate gradient pass when the
 // iteration is expected to be trust-region bound (gn_norm_sq alone is the cheaper pass when the GN step is expected to fit).
-template <int NT, bool UNI> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
+template <int NT, bool UNI, bool STG = false> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
                                                  double& bh, double& hh, double& bHb) {
     const CheckGeom& g = M.U()->g;
     const int k0 = ts.k0, k1 = ts.k1, L = g.L;
@@ -1005,13 +1008,13 @@ template <int NT, bool UNI> IPC_HD void sd_fused(const ChainMem& M, const OdomVi
         double gprev[3] = {0, 0, 0};
         int sl = ts.tid + 1;
         int es = ts.tid;
-        OdomRec<UNI> rn; odom_load<UNI>(O, es, rn);
+        OdomRec<UNI> rn; odom_load<UNI, STG>(O, es, k0, rn);
         for (int k = k0; k <= k1 && k < L; ++k, es += NT) {
             const double* pq = M.P(k + 1);
             P2 pb{pq[0], pq[1], pq[2]};
             Lin2 e; double t[NPRE];
             const OdomRec<UNI> r = rn;
-            if (k + 1 <= k1 && k + 1 < L) odom_load<UNI>(O, k + 1 < k1 ? es + NT : ts.tid + 1, rn);   // edge k1: first of thread tid + 1
+            if (k + 1 <= k1 && k + 1 < L) odom_load<UNI, STG>(O, k + 1 < k1 ? es + NT : ts.tid + 1, k + 1, rn);   // edge k1: first of thread tid + 1
             odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
             double gi[3], gj[3]; grad2(e, gi, gj);
             if (k > k0) {
@@ -1085,8 +1088,11 @@ struct CheckResult {
 // around ONE sweep call site, so the sweep is inlined exactly once and nothing lives in local memory.
 enum { P_INIT = 0, P_TRIAL_SPEC, P_TRIAL_GN, P_TRIAL_BLEND, P_RELIN_SPECFAIL, P_RELIN_REJECT };
 
-template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
-                                                  const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res) {
+// STG (device, UNI only): `stage` = shared-memory buffer for the window's odometry records + an mbarrier behind it (StageMem).
+struct StageMem { double* buf; unsigned long long* mbar; unsigned phase; };
+template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
+                                                  const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res,
+                                                  StageMem* stage = nullptr) {
     const int tid = hd_tid();
 #if defined(IPC_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     const long long ph_start = clock64();
@@ -1126,7 +1132,28 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     const double th = (K == 2) ? prm.slow_th : prm.fast_th;
     int max_iter = (K == 2) ? prm.slow_iter : prm.fast_iter;
     if (L + K > 100) max_iter *= 5;                        // src/consensus_utils.cpp:12-13
-    OdomView O{odom + (UNI ? 3 : 9) * (size_t)M.U()->g.lo, Du, Vu, M.Z()};
+    OdomView O{odom + (UNI ? 3 : 9) * (size_t)M.U()->g.lo, Du, Vu, M.Z(), nullptr};
+#ifdef __CUDA_ARCH__
+    if (STG) {
+        // ONE bulk asynchronous copy (TMA engine, 1-D) of the window's records into shared memory. Source and size must be multiples
+        // of 16 B: records are 24 B, so the copy starts at the even record at or below lo and is rounded up (the array is padded).
+        const int lo = M.U()->g.lo, off = lo & 1;
+        const unsigned bytes = (unsigned)((24u * (unsigned)(L + off) + 15u) & ~15u);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage->buf), bar = (unsigned)__cvta_generic_to_shared(stage->mbar);
+        if (tid == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(odom + 3 * (size_t)(lo - off)), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+        asm volatile(
+            "{\n .reg .pred p;\n IPC_STG_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra IPC_STG_DONE;\n bra IPC_STG_WAIT;\n IPC_STG_DONE:\n }" ::"r"(bar),
+            "r"(stage->phase)
+            : "memory");
+        stage->phase ^= 1u;
+        O.sm = stage->buf + 3 * off;
+    }
+#endif
 
     ThreadState ts;
     int S = (L + NT - 1) / NT; if (S < 1) S = 1; S |= 1;   // odd segment length: conflict-free strided shared-memory access
@@ -1139,7 +1166,8 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         double v[1] = {0};
         {   // the only strided read of the odometry: the records go to the scratch in slot order
             int es = tid;
-            for (int k = k0; k < k1; ++k, es += NT) {
+            if (STG) { for (int k = k0; k < k1; ++k) v[0] += O.sm[3 * k + 2]; }
+            else for (int k = k0; k < k1; ++k, es += NT) {
                 const double* zr = odom_rec<UNI>(O, k);
                 double* zo = O.zs + (UNI ? 3 : 9) * (size_t)es;
 #pragma unroll
@@ -1155,7 +1183,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         ts.pa.t = th0; ts.ca = c; ts.sa = s;
         int es = tid;
         for (int k = k0; k < k1; ++k, es += NT) {
-            const double* zr = O.zs + (UNI ? 3 : 9) * (size_t)es;
+            const double* zr = STG ? O.sm + 3 * k : O.zs + (UNI ? 3 : 9) * (size_t)es;
             const double zx = zr[0], zy = zr[1], zt = zr[2];
             p[0] += c * zx - s * zy; p[1] += s * zx + c * zy;
             acc += zt;
@@ -1171,7 +1199,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
         c = ts.ca; s = ts.sa;
         es = tid;
         for (int k = k0; k < k1; ++k, es += NT) {
-            const double* zr = O.zs + (UNI ? 3 : 9) * (size_t)es;
+            const double* zr = STG ? O.sm + 3 * k : O.zs + (UNI ? 3 : 9) * (size_t)es;
             const double zx = zr[0], zy = zr[1];
             ax += c * zx - s * zy; ay += s * zx + c * zy;
             double* pq = M.P(k + 1);
@@ -1205,7 +1233,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
     for (;;) {
         if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
         IPC_PH(7);
-        sweep<NT, UNI>(M, O, mode, c1, c2, ts, so, buf, spec_v IPC_PH_PASS); ++n_sweeps;
+        sweep<NT, UNI, STG>(M, O, mode, c1, c2, ts, so, buf, spec_v IPC_PH_PASS); ++n_sweeps;
         IPC_PH_COUNT(mode == STEP_GN ? 8 : (mode == STEP_BLEND ? 9 : 10), 1);
         if (mode == STEP_NONE && purpose != P_INIT) ++n_relin;
         if (mode == STEP_BLEND) ++n_blend;
@@ -1283,12 +1311,12 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
                 if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
                 IPC_PH(7);
                 if (prm.sd_fuse == 1 || (prm.sd_fuse == 2 && last_bound)) {
-                    sd_fused<NT, UNI>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps; ++n_sd;
+                    sd_fused<NT, UNI, STG>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps; ++n_sd;
                     IPC_PH(5); IPC_PH_COUNT(12, 1);
                     hgnNorm = sqrt(hh);
                     alpha = bb / bHb; hsdNorm = alpha * sqrt(bb); have_sd = true;
                 } else {
-                    hgnNorm = sqrt(gn_norm_sq<NT, UNI>(M, O, ts)); ++n_norm; ++n_sweeps;
+                    hgnNorm = sqrt(gn_norm_sq<NT, UNI, STG>(M, O, ts)); ++n_norm; ++n_sweeps;
                     IPC_PH(4); IPC_PH_COUNT(11, 1);
                 }
                 have_norm = true;
@@ -1301,7 +1329,7 @@ template <int NT, bool UNI> IPC_HD void run_check(const ChainMem& M, const doubl
             if (!have_sd) {
                 if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
                 IPC_PH(7);
-                sd_fused<NT, UNI>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps;
+                sd_fused<NT, UNI, STG>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps;
                 IPC_PH(5); IPC_PH_COUNT(12, 1);
                 ++n_sd;
                 alpha = bb / bHb;

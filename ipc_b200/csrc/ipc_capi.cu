@@ -84,6 +84,10 @@ namespace {
 // vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
 const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3}, {2600, 128, 0, 2}, {5400, 256, 0, 1}, {1 << 30, 256, 1, 1}};
 
+// MODE 2 (option stage_odom = 1, uniform-information graphs): + 24 B / vertex for the odometry window staged by cp.async.bulk: the
+// same CTAs per SM hold shorter windows (measured A/B in profiles/)
+const Bucket kBuckets2S[NB] = {{96, 32, 2, 16}, {320, 64, 2, 8}, {1100, 128, 2, 3}, {1700, 128, 2, 2}, {3500, 256, 2, 1}, {1 << 30, 256, 1, 1}};
+
 // SE(3): 7 doubles of state per vertex, 256 resident threads per SM (the 27 running prefix values need the registers)
 const Bucket kBuckets3[NB] = {{96, 32, 0, 8}, {320, 64, 0, 4}, {800, 128, 0, 2}, {3700, 256, 0, 1}, {3701, 256, 0, 1}, {1 << 30, 256, 1, 1}};
 const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
@@ -293,6 +297,12 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
         else if (!strcmp(name + 8, "minb")) h->buckets[b].minb = (int)value;
         else return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
         for (int q = 1; q < NB - 1; ++q) if (h->buckets[q].cap < h->buckets[q - 1].cap) return fail(IPC_ERR_ARG, "bucket caps must be non-decreasing");
+        CUDA_TRY(cudaSetDevice(h->device));
+        return size_scratch(h);
+    }
+    if (!strcmp(name, "stage_odom")) {     // 1: odometry window staged in shared memory by one bulk copy per check (MODE 2 kernels)
+        if (value != 0 && !(h->dim == 2 && h->hs.uniform_iso && h->d_odom3)) return fail(IPC_ERR_UNSUPPORTED, "stage_odom needs an SE(2) graph with uniform isotropic odometry information");
+        for (int b = 0; b < NB; ++b) h->buckets[b] = (value != 0 ? kBuckets2S : kBuckets2)[b];
         CUDA_TRY(cudaSetDevice(h->device));
         return size_scratch(h);
     }

@@ -23,7 +23,7 @@ struct Bucket { int cap; int nt; int mode; int minb; };   // minb: CTAs per SM t
 
 inline size_t smem_bytes(int mode, int cap, int dim = 2, int nt = 0) {
     size_t capv = std::max(cap + 2, nt);
-    size_t n = dim == 2 ? CHAIN_SMALL_DOUBLES + (mode == 0 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0)
+    size_t n = dim == 2 ? CHAIN_SMALL_DOUBLES + (mode != 1 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0) + (mode == 2 ? (size_t)stage_doubles((int)capv) + 2 : 0)
                         : se3::CHAIN3_SMALL_DOUBLES + (mode == 0 ? (size_t)se3::CHAIN3_STATE * capv : 0);
     return n * sizeof(double);
 }

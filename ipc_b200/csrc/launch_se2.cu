@@ -7,7 +7,7 @@
 namespace ipcb {
 
 template <int NT, int MODE, bool UNI, int MINB> int launch_se2u(const BatchArgs& a, int grid, cudaStream_t st) {
-    size_t sm = smem_bytes(MODE, a.Lcap);
+    size_t sm = smem_bytes(MODE, a.Lcap, 2, NT);
     // the opt-in is per device (a process may hold handles on several GPUs): one flag per ordinal, set under the launch that needs it
     static std::atomic<bool> attr_done[64];
     int dev = 0;
@@ -26,6 +26,13 @@ template <int NT, int MODE, int MINB> int launch_se2(const BatchArgs& a, int gri
 // the instantiated (threads, CTAs per SM) variants
 int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
     if (mode == 1) return nt == 256 ? launch_se2<256, 1, 1>(a, grid, st, uni) : launch_se2<512, 1, 1>(a, grid, st, uni);
+    if (mode == 2) {      // staged odometry (cp.async.bulk): uniform-information kernels only
+        if (!uni) return fail(IPC_ERR_ARG, "staged-odometry kernels need a uniform-information graph");
+#define VS(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2u<NT_, 2, true, MB_>(a, grid, st);
+        VS(32, 16) VS(64, 8) VS(128, 3) VS(128, 2) VS(256, 1)
+#undef VS
+        return fail(IPC_ERR_ARG, "no staged kernel variant for " + std::to_string(nt) + " threads x " + std::to_string(minb) + " CTAs per SM");
+    }
 #define V(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2<NT_, 0, MB_>(a, grid, st, uni);
     V(32, 16) V(32, 8) V(64, 8) V(64, 4) V(64, 2) V(128, 4) V(128, 3) V(128, 2) V(128, 1) V(192, 2) V(256, 2) V(256, 1) V(384, 1) V(512, 1)
 #undef V
