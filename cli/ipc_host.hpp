@@ -8,17 +8,21 @@
 //   splitProblemConstraints               src/utils.cpp:172-189       (|id1 - id0| == 1 -> odometry, else loop; FILE order)
 //   simulating_incremental_data           src/simulation.cpp:8-108
 //   writeVertex / readSolutionFile        src/utils.cpp:239-282
+//   graph_fixer                           examples/graph_fixer.cpp:36-54
 #pragma once
 #include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <map>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../include/ipc_b200.h"
@@ -86,33 +90,149 @@ struct Graph {
     std::vector<int> fixed;
 };
 
-inline Graph loadG2O(const std::string& path, int dim) {
-    std::ifstream f(path);
-    if (!f) throw std::runtime_error("cannot open dataset " + path);
-    Graph g; g.dim = dim;
-    const std::string vtag = dim == 2 ? "VERTEX_SE2" : "VERTEX_SE3:QUAT", etag = dim == 2 ? "EDGE_SE2" : "EDGE_SE3:QUAT";
+// optimizer.load (src/utils.cpp:114, g2o core/optimizable_graph.cpp::load) on a fast path: the file is read in one piece, cut
+// into chunks at line boundaries, and the chunks are tokenised by worker threads with strtod / strtol straight from the buffer
+// (no per-line stream objects); the pieces are concatenated in FILE order, so candidate order and labels do not depend on the
+// thread count. Unknown tags are skipped, like g2o's loader (it prints a warning); FIX lines are recorded.
+namespace detail {
+struct Piece { std::vector<int> vertex_ids; std::vector<std::vector<double>> vertex_est; std::vector<EdgeRec> edges; std::vector<int> fixed; std::string err; };
+inline const char* skip_ws(const char* p, const char* e) { while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p; return p; }
+inline bool rd_int(const char*& p, const char* e, int& v) {
+    p = skip_ws(p, e); if (p >= e) return false;
+    char* q = nullptr; const long x = std::strtol(p, &q, 10);
+    if (q == p) return false;
+    v = (int)x; p = q; return true;
+}
+inline bool rd_dbl(const char*& p, const char* e, double& v) {
+    p = skip_ws(p, e); if (p >= e) return false;
+    char* q = nullptr; const double x = std::strtod(p, &q);
+    if (q == p) return false;
+    v = x; p = q; return true;
+}
+inline void parse_chunk(const char* b, const char* e, int dim, Piece& out) {
+    const char* vtag = dim == 2 ? "VERTEX_SE2" : "VERTEX_SE3:QUAT"; const char* etag = dim == 2 ? "EDGE_SE2" : "EDGE_SE3:QUAT";
+    const size_t vl = std::strlen(vtag), el = std::strlen(etag);
     const int mw = dim == 2 ? 3 : 7, d = dim == 2 ? 3 : 6;
-    std::string line;
-    while (std::getline(f, line)) {
-        std::istringstream is(line);
-        std::string tag;
-        if (!(is >> tag) || tag[0] == '#') continue;
-        if (tag == vtag) {
-            int id; is >> id; std::vector<double> e(mw); for (auto& x : e) is >> x;
-            if (!is) throw std::runtime_error("malformed vertex line: " + line);
-            g.vertex_ids.push_back(id); g.vertex_est.push_back(e);
-        } else if (tag == etag) {
-            EdgeRec e; is >> e.from >> e.to; e.meas.resize(mw); for (auto& x : e.meas) is >> x;
-            std::vector<double> up(d * (d + 1) / 2); for (auto& x : up) is >> x;      // upper triangle, row-major
-            if (!is) throw std::runtime_error("malformed edge line: " + line);
-            e.info.assign(d * d, 0.0);
-            int q = 0;
-            for (int r = 0; r < d; ++r) for (int c = r; c < d; ++c) { e.info[r * d + c] = up[q]; e.info[c * d + r] = up[q]; ++q; }
-            g.edges.push_back(std::move(e));
-        } else if (tag == "FIX") { int id; while (is >> id) g.fixed.push_back(id); }
-        // unknown tags are skipped, like g2o's loader (it prints a warning)
+    std::vector<double> up((size_t)d * (d + 1) / 2);
+    while (b < e) {
+        const char* nl = (const char*)std::memchr(b, '\n', (size_t)(e - b));
+        const char* le = nl ? nl : e;                       // the buffer is NUL-terminated past e, so strtod cannot run away
+        const char* p = skip_ws(b, le);
+        const char* t = p; while (t < le && *t != ' ' && *t != '\t' && *t != '\r') ++t;
+        const size_t tl = (size_t)(t - p);
+        bool bad = false;
+        if (tl == vl && std::memcmp(p, vtag, vl) == 0) {
+            int id; const char* q = t; std::vector<double> est(mw);
+            bad = !rd_int(q, le, id); for (int c = 0; c < mw && !bad; ++c) bad = !rd_dbl(q, le, est[c]);
+            if (!bad) { out.vertex_ids.push_back(id); out.vertex_est.push_back(std::move(est)); }
+        } else if (tl == el && std::memcmp(p, etag, el) == 0) {
+            EdgeRec r; const char* q = t; r.meas.resize(mw);
+            bad = !rd_int(q, le, r.from) || !rd_int(q, le, r.to);
+            for (int c = 0; c < mw && !bad; ++c) bad = !rd_dbl(q, le, r.meas[c]);
+            for (size_t c = 0; c < up.size() && !bad; ++c) bad = !rd_dbl(q, le, up[c]);       // upper triangle, row-major
+            if (!bad) {
+                r.info.assign((size_t)d * d, 0.0);
+                int k = 0;
+                for (int i = 0; i < d; ++i) for (int j = i; j < d; ++j) { r.info[i * d + j] = up[k]; r.info[j * d + i] = up[k]; ++k; }
+                out.edges.push_back(std::move(r));
+            }
+        } else if (tl == 3 && std::memcmp(p, "FIX", 3) == 0) { const char* q = t; int id; while (rd_int(q, le, id)) out.fixed.push_back(id); }
+        if (bad && out.err.empty()) out.err = std::string("malformed line: ") + std::string(b, le);
+        b = nl ? nl + 1 : e;
+    }
+}
+}  // namespace detail
+
+inline Graph loadG2O(const std::string& path, int dim, int n_threads = 0) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open dataset " + path);
+    f.seekg(0, std::ios::end);
+    const std::streamoff len = f.tellg();
+    f.seekg(0);
+    std::string buf((size_t)len, '\0');                    // std::string keeps a NUL behind the last byte
+    if (len > 0) f.read(&buf[0], len);
+    if (n_threads <= 0) { n_threads = (int)std::thread::hardware_concurrency(); if (n_threads <= 0) n_threads = 1; if (n_threads > 16) n_threads = 16; }
+    const size_t min_chunk = 1 << 16;
+    int nt = (int)std::min<size_t>((size_t)n_threads, buf.size() / min_chunk + 1);
+    std::vector<size_t> cut(nt + 1, buf.size());
+    cut[0] = 0;
+    for (int i = 1; i < nt; ++i) {                          // chunk i starts behind the first newline at or after its even split
+        size_t p = buf.size() / nt * i;
+        if (p < cut[i - 1]) p = cut[i - 1];
+        const size_t q = buf.find('\n', p);
+        cut[i] = q == std::string::npos ? buf.size() : q + 1;
+    }
+    std::vector<detail::Piece> pieces(nt);
+    std::vector<std::thread> th;
+    for (int i = 1; i < nt; ++i) th.emplace_back([&, i] { detail::parse_chunk(buf.data() + cut[i], buf.data() + cut[i + 1], dim, pieces[i]); });
+    detail::parse_chunk(buf.data() + cut[0], buf.data() + cut[1], dim, pieces[0]);
+    for (auto& t : th) t.join();
+    Graph g; g.dim = dim;
+    for (auto& p : pieces) {
+        if (!p.err.empty()) throw std::runtime_error(p.err);
+        g.vertex_ids.insert(g.vertex_ids.end(), p.vertex_ids.begin(), p.vertex_ids.end());
+        for (auto& v : p.vertex_est) g.vertex_est.push_back(std::move(v));
+        for (auto& e : p.edges) g.edges.push_back(std::move(e));
+        g.fixed.insert(g.fixed.end(), p.fixed.begin(), p.fixed.end());
     }
     return g;
+}
+
+// optimizer.save (examples/graph_fixer.cpp:54): vertices in id order, FIX lines, then the edges (FILE order here; g2o walks a
+// pointer-ordered set), information as the row-major upper triangle, 17 significant digits so a reload is bit exact.
+inline void saveG2O(const Graph& g, const std::string& path) {
+    std::FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) throw std::runtime_error("cannot write " + path);
+    const char* vtag = g.dim == 2 ? "VERTEX_SE2" : "VERTEX_SE3:QUAT"; const char* etag = g.dim == 2 ? "EDGE_SE2" : "EDGE_SE3:QUAT";
+    const int d = g.dim == 2 ? 3 : 6;
+    std::vector<size_t> vo(g.vertex_ids.size());
+    for (size_t i = 0; i < vo.size(); ++i) vo[i] = i;
+    std::stable_sort(vo.begin(), vo.end(), [&](size_t a, size_t b) { return g.vertex_ids[a] < g.vertex_ids[b]; });
+    for (size_t i : vo) {
+        std::fprintf(f, "%s %d", vtag, g.vertex_ids[i]);
+        for (double x : g.vertex_est[i]) std::fprintf(f, " %.17g", x);
+        std::fputc('\n', f);
+    }
+    for (int id : g.fixed) std::fprintf(f, "FIX %d\n", id);
+    for (const auto& e : g.edges) {
+        std::fprintf(f, "%s %d %d", etag, e.from, e.to);
+        for (double x : e.meas) std::fprintf(f, " %.17g", x);
+        for (int r = 0; r < d; ++r) for (int c = r; c < d; ++c) std::fprintf(f, " %.17g", e.info[(size_t)r * d + c]);
+        std::fputc('\n', f);
+    }
+    std::fclose(f);
+}
+
+// measurement().inverse() of a relative pose: SE(2) (x y theta) / SE(3) (t, unit quaternion qx qy qz qw)
+inline std::vector<double> inverseMeasurement(const std::vector<double>& m) {
+    if (m.size() == 3) {
+        const double c = std::cos(m[2]), s = std::sin(m[2]);
+        double th = -m[2];
+        th -= 6.283185307179586476925 * std::floor((th + 3.14159265358979323846) / 6.283185307179586476925);   // normalize_theta: [-pi, pi)
+        return {-(c * m[0] + s * m[1]), -(-s * m[0] + c * m[1]), th};
+    }
+    double qx = m[3], qy = m[4], qz = m[5], qw = m[6];
+    const double n = std::sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+    qx /= n; qy /= n; qz /= n; qw /= n;
+    // R^T t with R from the unit quaternion; t' = -R^T t, q' = conjugate
+    const double R[9] = {1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw), 2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz),
+                         2 * (qy * qz - qx * qw), 2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)};
+    const double tx = -(R[0] * m[0] + R[3] * m[1] + R[6] * m[2]), ty = -(R[1] * m[0] + R[4] * m[1] + R[7] * m[2]), tz = -(R[2] * m[0] + R[5] * m[1] + R[8] * m[2]);
+    return {tx, ty, tz, -qx, -qy, -qz, qw};
+}
+
+// examples/graph_fixer.cpp:36-52: every loop edge (|from - to| != 1) stored as to < from is re-oriented: vertices swapped,
+// measurement inverted, information copied UNCHANGED (the reference does not transport it to the other frame; kept as is).
+// Returns the number of edges that were flipped.
+inline int fixGraph(Graph& g) {
+    int flipped = 0;
+    for (auto& e : g.edges) {
+        if (std::abs(e.to - e.from) == 1 || e.from < e.to) continue;
+        std::swap(e.from, e.to);
+        e.meas = inverseMeasurement(e.meas);
+        ++flipped;
+    }
+    return flipped;
 }
 
 // splitProblemConstraints (src/utils.cpp:172-189) + getProblemOdom ordering (src/consensus.cpp:15): odometry j -> j+1
@@ -260,6 +380,32 @@ inline int tester_main(int argc, char** argv, int dim) {
         std::cout << "TP " << r.tp << " FP " << r.fp << " TN " << r.tn << " FN " << r.fn << "\n";
         std::cout << "Precision = " << r.precision << "  Recall = " << r.recall << "\n";
         std::cout << "Total time = " << r.total_s << " s  Avg Time x test = " << (r.n_candidates ? r.total_s / r.n_candidates : 0.0) << " s\n";
+        return 0;
+    } catch (const std::exception& e) {
+        std::cerr << "error: " << e.what() << "\n";
+        return 1;
+    }
+}
+
+// examples/graph_fixer.cpp: `graph_fixer -c cfg.yaml` loads cfg.dataset (SE(3) in the reference; --dim 2 for SE(2) files),
+// re-orients the loop edges and writes ./graph.g2o (or -o <path>).
+inline int graph_fixer_main(int argc, char** argv) {
+    std::string cfg_path, out = "graph.g2o"; int dim = 3;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "-c" && i + 1 < argc) cfg_path = argv[++i];
+        else if (a == "-o" && i + 1 < argc) out = argv[++i];
+        else if (a == "--dim" && i + 1 < argc) dim = std::stoi(argv[++i]);
+        else { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [-o graph.g2o] [--dim 2|3]\n"; return 2; }
+    }
+    if (cfg_path.empty() || (dim != 2 && dim != 3)) { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [-o graph.g2o] [--dim 2|3]\n"; return 2; }
+    try {
+        Config cfg = readConfig(cfg_path);
+        Graph g = loadG2O(cfg.dataset, dim);
+        std::cout << "Tot Edges = " << g.edges.size() << "\n" << "Tot Vertices = " << g.vertex_ids.size() << "\n";   // examples/graph_fixer.cpp:30-31
+        const int n = fixGraph(g);
+        saveG2O(g, out);
+        std::cout << "Re-oriented " << n << " loop edges -> " << out << "\n";
         return 0;
     } catch (const std::exception& e) {
         std::cerr << "error: " << e.what() << "\n";
