@@ -24,7 +24,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-__all__ = ["Graph", "manhattan", "sphere", "add_outliers", "CONFIGS", "make_config"]
+__all__ = ["Graph", "manhattan", "sphere", "add_outliers", "CONFIGS", "make_config", "make_clean"]
 
 
 @dataclass
@@ -279,15 +279,13 @@ CONFIGS = {
 }
 
 
-def make_config(name: str, scale: float = 1.0, noise_scale: float | None = None):
-    """Build (graph, ipc_cfg) for a named config. ``scale`` < 1 shrinks poses / loops / outliers
-    proportionally (parity-test sizes); 1.0 is the BASELINE.json size."""
+def make_clean(name: str, scale: float = 1.0, noise_scale: float | None = None) -> Graph:
+    """The named shape WITHOUT outliers (true loops only): what the Monte-Carlo protocol spoils (scripts/montecarlo.py)."""
     c = CONFIGS[name]
     if noise_scale is None:
         # sphere: the file's information (sigma 0.01) is 4x more conservative than the noise actually drawn, as in
         # public datasets; with noise at the stated sigma and s_factor = 50 the reference rejects every loop
         noise_scale = c.get("noise_scale", 1.0)
-    n_out = max(1, int(round(c["outliers"] * scale)))
     if c["kind"] == "manhattan":
         n = max(32, int(round(c["n_poses"] * scale)))
         m = max(4, int(round(c["n_loops"] * scale)))
@@ -296,6 +294,15 @@ def make_config(name: str, scale: float = 1.0, noise_scale: float | None = None)
         rings = max(3, int(round(c["rings"] * math.sqrt(scale))))
         per = max(4, int(round(c["per_ring"] * math.sqrt(scale))))
         g = sphere(rings, per, c["seed"], noise_scale=noise_scale)
-    g = add_outliers(g, n_out, c["seed"] + 1000)
+    g.meta["config"] = name
+    return g
+
+
+def make_config(name: str, scale: float = 1.0, noise_scale: float | None = None):
+    """Build (graph, ipc_cfg) for a named config. ``scale`` < 1 shrinks poses / loops / outliers
+    proportionally (parity-test sizes); 1.0 is the BASELINE.json size."""
+    c = CONFIGS[name]
+    n_out = max(1, int(round(c["outliers"] * scale)))
+    g = add_outliers(make_clean(name, scale, noise_scale), n_out, c["seed"] + 1000)
     g.meta["config"] = name
     return g, dict(c["cfg"])
