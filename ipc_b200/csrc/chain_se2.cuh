@@ -364,7 +364,7 @@ struct ChainMem {            // three base pointers + a capacity: cheap to keep 
                              // slot = step * NT + thread makes every scratch access of a warp one contiguous run of records
     double* small;           // shared memory: collective staging (2 buffers), special-vertex table (2 buffers), UniBlock
     int capv, capg;          // capacity of the state arrays (vertices) and of the scratch arrays (slots)
-    IPC_HD double* P(int j) const { return st + 5 * j; }                          // x y theta cos sin of vertex j
+    IPC_HD double* P(int j) const { return st + 5 * j; }                          // x y theta cos sin of vertex j (state in shared memory)
     IPC_HD double* B(int sl) const { return scr + 3 * sl; }                       // pose backup: state before the last trial sweep
     IPC_HD double* G(int sl) const { return scr + 3 * (size_t)capg + 6 * sl; }    // gradient b_j (3) and h_gn,j (3), g2o vertex coordinates
     IPC_HD double* Z() const { return scr + 9 * (size_t)capg; }                  // odometry records of the window, slot order (3 or 9 / edge)
@@ -375,6 +375,24 @@ struct ChainMem {            // three base pointers + a capacity: cheap to keep 
     IPC_HD double* spec() const { return small + 2 * RED_DOUBLES_ + RED2_DOUBLES_; }
     IPC_HD UniBlock* U() const { return reinterpret_cast<UniBlock*>(small + 2 * RED_DOUBLES_ + RED2_DOUBLES_ + 2 * NSPEC * SPECW); }
 };
+// State record of a vertex (x y theta cos sin). Shared-memory state (GST = false): AoS by VERTEX, components 1 double apart (odd segment
+// lengths keep the strided accesses of a warp conflict free). Global-memory state (GST = true: windows that do not fit shared memory,
+// and the one-warp-per-check kernels): tiles of 5 x NT doubles by STEP — the vertex thread t reaches at step i of its segment walk
+// (vertex k0(t) + 1 + i) is element t of tile i + 1, components NT doubles apart — so every access of a warp is one contiguous
+// 256-byte run (coalesced in L2 / HBM). Tile 0 holds the fixed origin (vertex 0) in element 0.
+template <int NT, bool GST> struct StateAt {
+    static constexpr int CS = GST ? NT : 1;                                       // distance between the components of one record
+    IPC_HD static double* step(const ChainMem& M, int j, int i, int t) {         // vertex j = k0(t) + 1 + i of thread t
+        return GST ? M.st + ((size_t)(i + 1) * 5) * NT + t : M.st + 5 * j;
+    }
+    IPC_HD static double* vertex(const ChainMem& M, int j, int S) {              // any vertex (rare accesses: loop end points)
+        if (!GST) return M.st + 5 * j;
+        if (j == 0) return M.st;
+        const int t = (j - 1) / S, i = (j - 1) - t * S;
+        return M.st + ((size_t)(i + 1) * 5) * NT + t;
+    }
+};
+IPC_HD constexpr int global_state_doubles(int capv, int nt) { return 5 * (capv + 4 * nt); }   // tiles: (S + 1) * 5 * NT <= 5 (L + 3 NT)
 // scratch slot of vertex j for segments of S vertices per thread: vertex 0 -> 0; vertex k0 + 1 + i of thread t -> i * NT + t + 1.
 // Slots reach S * NT <= L + 2 NT, hence capg = capv + 2 NT + 2.
 template <int NT> IPC_HD int vslot(int j, int S) { return j == 0 ? 0 : ((j - 1) % S) * NT + (j - 1) / S + 1; }
@@ -480,19 +498,57 @@ struct SweepOut { double chi, mx, hh, gain; };   // odometry chi2 sum / max at t
 // sums of the new linearisation at the special vertices. The GN step at vertex j needs the prefix of the OLD linearisation at
 // j: it is rebuilt on the fly from the old poses (no sincos: cos / sin are stored). Writes the pose backup when a step is
 // applied. Two block barriers.
-template <int NT, bool UNI, bool STG = false> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
-                                              SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
+//
+// One edge of the sweep is two dependent halves: A(k) = old linearisation of edge k + step of vertex k + 1 (-> its new pose),
+// B(k) = sincos of the new heading + new linearisation of edge k + the accumulations. B(k) and A(k + 1) do not depend on each
+// other (A only reads OLD poses and the running old prefix), so the loop is software pipelined by hand: iteration k holds
+// B(k) and A(k + 1) in ONE basic block (one loop per step kind, no branches in the body, loads first, stores last), which lets the
+// scheduler interleave the two dependent chains — the edge loop is bound by dependent-issue latency, not by the fp64 pipe.
+// Every accumulation keeps its order (k ascending), so the results are bit-identical to the unpipelined loop.
+template <bool UNI> IPC_HD void sweep_gn_step(const OdomView& O, const OdomRec<UNI>& r, const double* zr, const double* Cr, const P2& oa, double oca, double osa,
+                                              const P2& ob, double* pre, double& gain, double* h) {
+    Lin2 eo; double to[NPRE];
+    odom_terms<UNI>(O, r, oca, osa, oa, ob, eo, to);
+    const double z0 = zr[0], z1 = zr[1], z2 = zr[2];
+    {   // predicted gain h_gn^T H h_gn, accumulated edge by edge from non-negative terms |J h_gn|^2_Omega (chi2 - model
+        // cancels catastrophically near convergence and for gross outliers): the residual change of edge k under the
+        // force z of its region is -(d + V Q^T z)
+        const double y0 = eo.c * z0 + eo.s * z1, y1 = -eo.s * z0 + eo.c * z1, y2 = ob.y * z0 - ob.x * z1 + z2;
+        if (UNI) {
+            const double w0 = fma(O.Vu[0], y0, eo.d0), w1 = fma(O.Vu[0], y1, eo.d1), w2 = fma(O.Vu[5], y2, eo.d2);
+            gain += O.Du[0] * (w0 * w0 + w1 * w1) + O.Du[5] * w2 * w2;
+        } else {
+            double V6[6]; inv_sym3(r.z + (UNI ? 0 : 3), V6);
+            const double w0 = eo.d0 + V6[0] * y0 + V6[1] * y1 + V6[2] * y2;
+            const double w1 = eo.d1 + V6[1] * y0 + V6[3] * y1 + V6[4] * y2;
+            const double w2 = eo.d2 + V6[2] * y0 + V6[4] * y1 + V6[5] * y2;
+            gain += quad3(r.z + (UNI ? 0 : 3), w0, w1, w2);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
+    // twist Xi = Pm - PM z - C of the vertex's region, u = T Xi (gn_step_at with the region's z, C already in registers)
+    const double X0 = pre[6] - (pre[0] * z0 + pre[1] * z1 + pre[2] * z2) - Cr[0];
+    const double X1 = pre[7] - (pre[1] * z0 + pre[3] * z1 + pre[4] * z2) - Cr[1];
+    const double X2 = pre[8] - (pre[2] * z0 + pre[4] * z1 + pre[5] * z2) - Cr[2];
+    h[0] = X0 - ob.y * X2; h[1] = X1 + ob.x * X2; h[2] = X2;
+}
+
+template <int NT, bool UNI, bool STG, int STEP, bool GST = false> IPC_HD void sweep_mode(const ChainMem& M, const OdomView& O, double c1, double c2, ThreadState& ts,
+                                                                       SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
     const int k0 = ts.k0, k1 = ts.k1;
     const StepSpec* sp = &M.U()->sol;
     double* spec = M.spec() + (size_t)buf * NSPEC * SPECW;
     double pre[NPRE];        // running prefix of the OLD linearisation (GN mode)
 #pragma unroll
     for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
-    P2 oa = ts.pa; double oca = ts.ca, osa = ts.sa;      // old from-vertex
-    P2 na = oa; double nca = oca, nsa = osa;             // new from-vertex
-    if (mode != STEP_NONE && k0 > 0 && k0 < k1) {        // boundary vertex k0: same arithmetic as its owner => identical bits
+    P2 oa = ts.pa; double oca = ts.ca, osa = ts.sa;      // old from-vertex of the next A
+    P2 na = oa; double nca = oca, nsa = osa;             // new from-vertex of the next B
+    if (STEP != STEP_NONE && k0 > 0 && k0 < k1) {        // boundary vertex k0: same arithmetic as its owner => identical bits
         double h[3];
-        if (mode == STEP_GN) gn_step_at(sp, k0, pre, oa.x, oa.y, h);
+        if (STEP == STEP_GN) gn_step_at(sp, k0, pre, oa.x, oa.y, h);
         else {
             const double* gq = M.G((ts.S - 1) * NT + ts.tid);      // vertex k0 = the last vertex of thread tid - 1
 #pragma unroll
@@ -509,89 +565,143 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void sweep(const ChainMem& 
     bool has_spec = false;
 #pragma unroll
     for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
-    // the odometry record of the next edge is fetched one iteration ahead (L2 latency); state comes from shared memory
-    OdomRec<UNI> rn;
-    double gn6[6] = {0, 0, 0, 0, 0, 0};      // blend steps: (b, h_gn) of the next vertex, from the global scratch
-    int sl = ts.tid + 1;                     // scratch slot of vertex k0 + 1; + NT per vertex
+    const int v_rs = spec_v[1], v_re = spec_v[2];        // region boundaries (sp->rs, sp->re)
     if (k0 < k1) {
-        odom_load<UNI, STG>(O, sl - 1, k0, rn);       // edge slot = slot of the edge's head vertex - 1
-        if (mode == STEP_BLEND) { const double* gq = M.G(sl);
+        int sl = ts.tid + 1;                     // scratch slot of vertex k + 1 (the vertex B(k) finishes); + NT per vertex
+        // odometry records: rB of edge k (for B), rA of edge k + 1 (for A), loaded one more iteration ahead (L2 latency)
+        OdomRec<UNI> rB, rA;
+        double gA[6] = {0, 0, 0, 0, 0, 0};       // blend steps: (b, h_gn) of the vertex the next A moves, from the global scratch
+        odom_load<UNI, STG>(O, sl - 1, k0, rB);                    // edge slot = slot of the edge's head vertex - 1
+        {
+            const bool more = k0 + 1 < k1;
+            odom_load<UNI, STG>(O, more ? sl + NT - 1 : sl - 1, more ? k0 + 1 : k0, rA);
+            if (STEP == STEP_BLEND) { const double* gq = M.G(more ? sl + NT : sl);
 #pragma unroll
-            for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
-    }
-    for (int k = k0; k < k1; ++k, sl += NT) {
-        const int j = k + 1;
-        const OdomRec<UNI> r = rn;
-        double g6[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) g6[q] = gn6[q];
-        if (j < k1) {
-            odom_load<UNI, STG>(O, sl + NT - 1, j, rn);
-            if (mode == STEP_BLEND) { const double* gq = M.G(sl + NT);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) gn6[q] = gq[q]; }
+                for (int q = 0; q < 6; ++q) gA[q] = gq[q]; }
         }
-        const double* pq0 = M.P(j);
-        const P2 ob{pq0[0], pq0[1], pq0[2]};
-        const double ocb = pq0[3], osb = pq0[4];
-        P2 nb = ob;
-        double ncb = ocb, nsb = osb;
-        if (mode != STEP_NONE) {
-            double h[3];
-            if (mode == STEP_GN) {
-                Lin2 eo; double to[NPRE];
-                odom_terms<UNI>(O, r, oca, osa, oa, ob, eo, to);
-                {   // predicted gain h_gn^T H h_gn, accumulated edge by edge from non-negative terms |J h_gn|^2_Omega (chi2 - model
-                    // cancels catastrophically near convergence and for gross outliers): the residual change of edge k under the
-                    // force z of its region is -(d + V Q^T z)
-                    const int rg = (k < sp->rs) ? 0 : (k < sp->re ? 1 : 2);
-                    const double* zr = sp->z[rg];
-                    const double z0 = zr[0], z1 = zr[1], z2 = zr[2];
-                    const double y0 = eo.c * z0 + eo.s * z1, y1 = -eo.s * z0 + eo.c * z1, y2 = ob.y * z0 - ob.x * z1 + z2;
-                    if (UNI) {
-                        const double w0 = fma(O.Vu[0], y0, eo.d0), w1 = fma(O.Vu[0], y1, eo.d1), w2 = fma(O.Vu[5], y2, eo.d2);
-                        gain += O.Du[0] * (w0 * w0 + w1 * w1) + O.Du[5] * w2 * w2;
-                    } else {
-                        double V6[6]; inv_sym3(r.z + (UNI ? 0 : 3), V6);
-                        const double w0 = eo.d0 + V6[0] * y0 + V6[1] * y1 + V6[2] * y2;
-                        const double w1 = eo.d1 + V6[1] * y0 + V6[3] * y1 + V6[4] * y2;
-                        const double w2 = eo.d2 + V6[2] * y0 + V6[4] * y1 + V6[5] * y2;
-                        gain += quad3(r.z + (UNI ? 0 : 3), w0, w1, w2);
+        // ---- prologue: A(k0) ----
+        P2 nb; double ncb, nsb;                  // vertex k + 1 at the new state (cos / sin: known only for STEP_NONE before B)
+        {
+            const double* pq0 = SA::step(M, k0 + 1, 0, ts.tid);
+            const P2 ob{pq0[0], pq0[CS], pq0[2 * CS]};
+            const double ocb = pq0[3 * CS], osb = pq0[4 * CS];
+            nb = ob; ncb = ocb; nsb = osb;
+            if (STEP != STEP_NONE) {
+                double h[3];
+                if (STEP == STEP_GN) {
+                    const int rg = (k0 < v_rs) ? 0 : (k0 < v_re ? 1 : 2);
+                    sweep_gn_step<UNI>(O, rB, sp->z[rg], sp->C[rg], oa, oca, osa, ob, pre, gain, h);
+                } else {
+                    const double* gq = M.G(sl);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) h[q] = c1 * gq[q] + c2 * gq[3 + q];
+                }
+                double* bq = M.B(sl);
+                bq[0] = ob.x; bq[1] = ob.y; bq[2] = ob.t;
+                nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
+                hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+            }
+            oa = ob; oca = ocb; osa = osb;
+        }
+        // ---- steady state: B(k) next to A(k + 1) ----
+        int k = k0;
+        // GST (state in the global scratch): the old pose of vertex k + 2 is fetched one iteration ahead as well (L2 / HBM latency)
+        double pn[5] = {0, 0, 0, 0, 0};
+        if (GST) { const int jn = k0 + 2 <= k1 ? k0 + 2 : k1; const double* pq = SA::step(M, jn, jn - k0 - 1, ts.tid);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) pn[q] = pq[q * CS]; }
+        for (; k + 1 < k1; ++k, sl += NT) {
+            // loads first (shared memory: old pose of vertex k + 2, the region's force; global: records / gradients two edges ahead)
+            const int jn = GST ? (k + 3 <= k1 ? k + 3 : k1) : k + 2;
+            const double* pq2 = SA::step(M, jn, jn - k0 - 1, ts.tid);
+            double pc5[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { pc5[q] = GST ? pn[q] : pq2[q * CS]; if (GST) pn[q] = pq2[q * CS]; }
+            const P2 ob2{pc5[0], pc5[1], pc5[2]};
+            const double ocb2 = pc5[3], osb2 = pc5[4];
+            double zr[3] = {0, 0, 0}, Cr[3] = {0, 0, 0};
+            if (STEP == STEP_GN) {
+                const int rg = (k + 1 < v_rs) ? 0 : (k + 1 < v_re ? 1 : 2);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { zr[q] = sp->z[rg][q]; Cr[q] = sp->C[rg][q]; }
+            }
+            const bool more = k + 2 < k1;
+            OdomRec<UNI> rP;
+            odom_load<UNI, STG>(O, more ? sl + 2 * NT - 1 : sl + NT - 1, more ? k + 2 : k + 1, rP);
+            double gP[6] = {0, 0, 0, 0, 0, 0};
+            if (STEP == STEP_BLEND) { const double* gq = M.G(more ? sl + 2 * NT : sl + NT);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) gP[q] = gq[q]; }
+            // B(k): vertex j = k + 1 gets its cos / sin, edge k its new linearisation
+            const int j = k + 1;
+            if (STEP != STEP_NONE) ipc_sincos(nb.t, &nsb, &ncb);
+            Lin2 e; double t[NPRE];
+            odom_terms<UNI>(O, rB, nca, nsa, na, nb, e, t);
+            chi += e.chi; mx = fmax(mx, e.chi);
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) run[m] += t[m];
+            // A(k + 1): step of vertex k + 2 from the old linearisation of edge k + 1
+            P2 nb2 = ob2;
+            if (STEP != STEP_NONE) {
+                double h[3];
+                if (STEP == STEP_GN) sweep_gn_step<UNI>(O, rA, zr, Cr, oa, oca, osa, ob2, pre, gain, h);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) h[q] = c1 * gA[q] + c2 * gA[3 + q];
+                }
+                nb2.x += h[0]; nb2.y += h[1]; nb2.t = wrap_pi_hd(nb2.t + h[2]);
+                hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+            }
+            // stores last
+            if (STEP != STEP_NONE) {
+                double* pq = SA::step(M, j, k - k0, ts.tid);
+                pq[0] = nb.x; pq[CS] = nb.y; pq[2 * CS] = nb.t; pq[3 * CS] = ncb; pq[4 * CS] = nsb;
+                double* bq = M.B(sl + NT);
+                bq[0] = ob2.x; bq[1] = ob2.y; bq[2] = ob2.t;
+            }
+            if (has_spec) {
+#pragma unroll
+                for (int q = 1; q < NSPEC; ++q) {
+                    if (j == spec_v[q]) {        // local part now, the thread base is added after the scan
+                        double* o = spec + q * SPECW;
+#pragma unroll
+                        for (int m = 0; m < NPRE; ++m) o[m] = run[m];
+                        o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
                     }
                 }
-#pragma unroll
-                for (int m = 0; m < NPRE; ++m) pre[m] += to[m];
-                gn_step_at(sp, j, pre, ob.x, ob.y, h);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 3; ++q) h[q] = c1 * g6[q] + c2 * g6[3 + q];
             }
-            double* bq = M.B(sl);
-            bq[0] = ob.x; bq[1] = ob.y; bq[2] = ob.t;
-            nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
-            hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
-            ipc_sincos(nb.t, &nsb, &ncb);
-            double* pq = M.P(j);
-            pq[0] = nb.x; pq[1] = nb.y; pq[2] = nb.t; pq[3] = ncb; pq[4] = nsb;
+            na = nb; nca = ncb; nsa = nsb;
+            nb = nb2; ncb = ocb2; nsb = osb2;
+            oa = ob2; oca = ocb2; osa = osb2;
+            rB = rA; rA = rP;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) gA[q] = gP[q];
         }
-        Lin2 e; double t[NPRE];
-        odom_terms<UNI>(O, r, nca, nsa, na, nb, e, t);
-        chi += e.chi; mx = fmax(mx, e.chi);
+        // ---- epilogue: B(k1 - 1) ----
+        {
+            const int j = k + 1;
+            if (STEP != STEP_NONE) {
+                ipc_sincos(nb.t, &nsb, &ncb);
+                double* pq = SA::step(M, j, k - k0, ts.tid);
+                pq[0] = nb.x; pq[CS] = nb.y; pq[2 * CS] = nb.t; pq[3 * CS] = ncb; pq[4 * CS] = nsb;
+            }
+            Lin2 e; double t[NPRE];
+            odom_terms<UNI>(O, rB, nca, nsa, na, nb, e, t);
+            chi += e.chi; mx = fmax(mx, e.chi);
 #pragma unroll
-        for (int m = 0; m < NPRE; ++m) run[m] += t[m];
-        if (has_spec) {
+            for (int m = 0; m < NPRE; ++m) run[m] += t[m];
+            if (has_spec) {
 #pragma unroll
-            for (int q = 1; q < NSPEC; ++q) {
-                if (j == spec_v[q]) {        // local part now, the thread base is added after the scan
-                    double* o = spec + q * SPECW;
+                for (int q = 1; q < NSPEC; ++q) {
+                    if (j == spec_v[q]) {
+                        double* o = spec + q * SPECW;
 #pragma unroll
-                    for (int m = 0; m < NPRE; ++m) o[m] = run[m];
-                    o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+                        for (int m = 0; m < NPRE; ++m) o[m] = run[m];
+                        o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+                    }
                 }
             }
         }
-        oa = ob; oca = ocb; osa = osb;
-        na = nb; nca = ncb; nsa = nsb;
     }
     double s[3] = {chi, hh, gain};
     IPC_PH(1);
@@ -614,23 +724,31 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void sweep(const ChainMem& 
     buf ^= 1;
     IPC_PH(2);
 }
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
+                                              SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
+    if (mode == STEP_GN) sweep_mode<NT, UNI, STG, STEP_GN, GST>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
+    else if (mode == STEP_BLEND) sweep_mode<NT, UNI, STG, STEP_BLEND, GST>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
+    else sweep_mode<NT, UNI, STG, STEP_NONE, GST>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
+}
 
 // undo the last applied sweep: poses from the backup, cos / sin recomputed, boundary registers re-read. Thread bases are NOT
 // restored: every caller re-linearises (GN rejection) or only runs blend sweeps (which do not read them) until a step is kept.
-template <int NT> IPC_HD void rollback(const ChainMem& M, ThreadState& ts) {
+template <int NT, bool GST = false> IPC_HD void rollback(const ChainMem& M, ThreadState& ts) {
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
     int sl = ts.tid + 1;
     for (int k = ts.k0; k < ts.k1; ++k, sl += NT) {
         const int j = k + 1;
         const double* bq = M.B(sl);
         const double t = bq[2];
         double s, c; ipc_sincos(t, &s, &c);
-        double* pq = M.P(j);
-        pq[0] = bq[0]; pq[1] = bq[1]; pq[2] = t; pq[3] = c; pq[4] = s;
+        double* pq = SA::step(M, j, k - ts.k0, ts.tid);
+        pq[0] = bq[0]; pq[CS] = bq[1]; pq[2 * CS] = t; pq[3 * CS] = c; pq[4 * CS] = s;
     }
     bsync<NT>();
     if (ts.k0 < ts.k1 && ts.k0 > 0) {
-        const double* pq = M.P(ts.k0);
-        ts.pa.x = pq[0]; ts.pa.y = pq[1]; ts.pa.t = pq[2]; ts.ca = pq[3]; ts.sa = pq[4];
+        const double* pq = SA::step(M, ts.k0, ts.S - 1, ts.tid - 1);         // vertex k0 = the last vertex of thread tid - 1
+        ts.pa.x = pq[0]; ts.pa.y = pq[CS]; ts.pa.t = pq[2 * CS]; ts.ca = pq[3 * CS]; ts.sa = pq[4 * CS];
     }
     bsync<NT>();
 }
@@ -922,7 +1040,9 @@ template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, int buf, double 
 }
 
 // |h_gn|^2 of the current linearisation without applying it
-template <int NT, bool UNI, bool STG = false> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
     double v[1] = {0};
     const StepSpec* sp = &M.U()->sol;
     double pre[NPRE];
@@ -934,8 +1054,9 @@ template <int NT, bool UNI, bool STG = false> IPC_HD double gn_norm_sq(const Cha
     if (ts.k0 < ts.k1) odom_load<UNI, STG>(O, es, ts.k0, rn);
     for (int k = ts.k0; k < ts.k1; ++k, es += NT) {
         const int j = k + 1;
-        const double* pq = M.P(j);
-        const P2 pb{pq[0], pq[1], pq[2]};
+        const double* pq = SA::step(M, j, k - ts.k0, ts.tid);
+        const P2 pb{pq[0], pq[CS], pq[2 * CS]};
+        const double cb = pq[3 * CS], sb = pq[4 * CS];
         const OdomRec<UNI> r = rn;
         if (j < ts.k1) odom_load<UNI, STG>(O, es + NT, j, rn);
         Lin2 e; double t[NPRE], h[3];
@@ -944,7 +1065,7 @@ template <int NT, bool UNI, bool STG = false> IPC_HD double gn_norm_sq(const Cha
         for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
         gn_step_at(sp, j, pre, pb.x, pb.y, h);
         v[0] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
-        pa = pb; ca = pq[3]; sa = pq[4];
+        pa = pb; ca = cb; sa = sb;
     }
     hd_block_sum<NT, 1>(v, M.red2());
     return v[0];
@@ -956,25 +1077,27 @@ template <int NT, bool UNI, bool STG = false> IPC_HD double gn_norm_sq(const Cha
 // k0+1..k1 and the Hessian terms of the edges k0+1..k1 (thread 0 also edge 0); the one term that needs the next thread's first
 // gradient is completed after the block barrier from the scratch. Stands in for gn_norm_sq + a separate gradient pass when the
 // iteration is expected to be trust-region bound (gn_norm_sq alone is the cheaper pass when the GN step is expected to fit).
-template <int NT, bool UNI, bool STG = false> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
                                                  double& bh, double& hh, double& bHb) {
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
     const CheckGeom& g = M.U()->g;
     const int k0 = ts.k0, k1 = ts.k1, L = g.L;
     const StepSpec* sp = &M.U()->sol;
     const LoopRec2& Lc = M.U()->Lc; const LoopRec2& Lm = M.U()->Lm;
     Lin2 ec, em; const int cjf = Lc.from - g.lo, cjt = Lc.to - g.lo; int mjf = -1, mjt = -1;
     {
-        const double* qf = M.P(cjf); const double* qt = M.P(cjt);
-        P2 pf{qf[0], qf[1], qf[2]}, pt{qt[0], qt[1], qt[2]};
-        lin2cs(qf[3], qf[4], pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
+        const double* qf = SA::vertex(M, cjf, ts.S); const double* qt = SA::vertex(M, cjt, ts.S);
+        P2 pf{qf[0], qf[CS], qf[2 * CS]}, pt{qt[0], qt[CS], qt[2 * CS]};
+        lin2cs(qf[3 * CS], qf[4 * CS], pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
     }
     double gci[3], gcj[3], gmi[3] = {0, 0, 0}, gmj[3] = {0, 0, 0};
     grad2(ec, gci, gcj);
     if (g.K == 2) {
         mjf = Lm.from - g.lo; mjt = Lm.to - g.lo;
-        const double* qf = M.P(mjf); const double* qt = M.P(mjt);
-        P2 pf{qf[0], qf[1], qf[2]}, pt{qt[0], qt[1], qt[2]};
-        lin2cs(qf[3], qf[4], pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
+        const double* qf = SA::vertex(M, mjf, ts.S); const double* qt = SA::vertex(M, mjt, ts.S);
+        P2 pf{qf[0], qf[CS], qf[2 * CS]}, pt{qt[0], qt[CS], qt[2 * CS]};
+        lin2cs(qf[3 * CS], qf[4 * CS], pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
         grad2(em, gmi, gmj);
     }
     double v[4] = {0, 0, 0, 0};
@@ -1010,8 +1133,9 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void sd_fused(const ChainMe
         int es = ts.tid;
         OdomRec<UNI> rn; odom_load<UNI, STG>(O, es, k0, rn);
         for (int k = k0; k <= k1 && k < L; ++k, es += NT) {
-            const double* pq = M.P(k + 1);
-            P2 pb{pq[0], pq[1], pq[2]};
+            const double* pq = k < k1 ? SA::step(M, k + 1, k - k0, ts.tid) : SA::step(M, k + 1, 0, ts.tid + 1);   // vertex k1 + 1: first of thread tid + 1
+            P2 pb{pq[0], pq[CS], pq[2 * CS]};
+            const double cbn = pq[3 * CS], sbn = pq[4 * CS];
             Lin2 e; double t[NPRE];
             const OdomRec<UNI> r = rn;
             if (k + 1 <= k1 && k + 1 < L) odom_load<UNI, STG>(O, k + 1 < k1 ? es + NT : ts.tid + 1, k + 1, rn);   // edge k1: first of thread tid + 1
@@ -1033,7 +1157,7 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void sd_fused(const ChainMe
 #pragma unroll
                 for (int c = 0; c < 6; ++c) pD[c] = r.z[UNI ? 0 : 3 + c];
             }
-            pa = pb; ca = pq[3]; sa = pq[4];
+            pa = pb; ca = cbn; sa = sbn;
         }
         if (k1 == L) {
             double b[3];
@@ -1090,9 +1214,11 @@ enum { P_INIT = 0, P_TRIAL_SPEC, P_TRIAL_GN, P_TRIAL_BLEND, P_RELIN_SPECFAIL, P_
 
 // STG (device, UNI only): `stage` = shared-memory buffer for the window's odometry records + an mbarrier behind it (StageMem).
 struct StageMem { double* buf; unsigned long long* mbar; unsigned phase; };
-template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
                                                   const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res,
                                                   StageMem* stage = nullptr) {
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
     const int tid = hd_tid();
 #if defined(IPC_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     const long long ph_start = clock64();
@@ -1177,7 +1303,7 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainM
         hd_block_excl_scan<NT, 1>(v, M.red2());
         double acc = v[0];
         const double th0 = wrap_pi_hd(acc);                 // heading of vertex k0
-        if (tid == 0) { double* p0 = M.P(0); p0[0] = 0; p0[1] = 0; p0[2] = 0; p0[3] = 1; p0[4] = 0; }
+        if (tid == 0) { double* p0 = SA::vertex(M, 0, 1); p0[0] = 0; p0[CS] = 0; p0[2 * CS] = 0; p0[3 * CS] = 1; p0[4 * CS] = 0; }
         double p[2] = {0, 0};
         double s, c; ipc_sincos(th0, &s, &c);
         ts.pa.t = th0; ts.ca = c; ts.sa = s;
@@ -1189,8 +1315,8 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainM
             acc += zt;
             const double thk = wrap_pi_hd(acc);
             ipc_sincos(thk, &s, &c);
-            double* pq = M.P(k + 1);
-            pq[2] = thk; pq[3] = c; pq[4] = s;
+            double* pq = SA::step(M, k + 1, k - k0, tid);
+            pq[2 * CS] = thk; pq[3 * CS] = c; pq[4 * CS] = s;
         }
         bsync<NT>();
         hd_block_excl_scan<NT, 2>(p, M.red2());
@@ -1202,8 +1328,8 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainM
             const double* zr = STG ? O.sm + 3 * k : O.zs + (UNI ? 3 : 9) * (size_t)es;
             const double zx = zr[0], zy = zr[1];
             ax += c * zx - s * zy; ay += s * zx + c * zy;
-            double* pq = M.P(k + 1);
-            pq[0] = ax; pq[1] = ay; c = pq[3]; s = pq[4];
+            double* pq = SA::step(M, k + 1, k - k0, tid);
+            pq[0] = ax; pq[CS] = ay; c = pq[3 * CS]; s = pq[4 * CS];
         }
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) ts.base[m] = 0;
@@ -1231,9 +1357,9 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainM
     int purpose = P_INIT, mode = STEP_NONE;
     double c1 = 0, c2 = 0;
     for (;;) {
-        if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
+        if (need_rollback) { rollback<NT, GST>(M, ts); need_rollback = false; IPC_PH(6); }
         IPC_PH(7);
-        sweep<NT, UNI, STG>(M, O, mode, c1, c2, ts, so, buf, spec_v IPC_PH_PASS); ++n_sweeps;
+        sweep<NT, UNI, STG, GST>(M, O, mode, c1, c2, ts, so, buf, spec_v IPC_PH_PASS); ++n_sweeps;
         IPC_PH_COUNT(mode == STEP_GN ? 8 : (mode == STEP_BLEND ? 9 : 10), 1);
         if (mode == STEP_NONE && purpose != P_INIT) ++n_relin;
         if (mode == STEP_BLEND) ++n_blend;
@@ -1308,15 +1434,15 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainM
                     mode = STEP_GN; purpose = P_TRIAL_SPEC; c1 = 0; c2 = 1;
                     continue;
                 }
-                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
+                if (need_rollback) { rollback<NT, GST>(M, ts); need_rollback = false; IPC_PH(6); }
                 IPC_PH(7);
                 if (prm.sd_fuse == 1 || (prm.sd_fuse == 2 && last_bound)) {
-                    sd_fused<NT, UNI, STG>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps; ++n_sd;
+                    sd_fused<NT, UNI, STG, GST>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps; ++n_sd;
                     IPC_PH(5); IPC_PH_COUNT(12, 1);
                     hgnNorm = sqrt(hh);
                     alpha = bb / bHb; hsdNorm = alpha * sqrt(bb); have_sd = true;
                 } else {
-                    hgnNorm = sqrt(gn_norm_sq<NT, UNI, STG>(M, O, ts)); ++n_norm; ++n_sweeps;
+                    hgnNorm = sqrt(gn_norm_sq<NT, UNI, STG, GST>(M, O, ts)); ++n_norm; ++n_sweeps;
                     IPC_PH(4); IPC_PH_COUNT(11, 1);
                 }
                 have_norm = true;
@@ -1327,9 +1453,9 @@ template <int NT, bool UNI, bool STG = false> IPC_HD void run_check(const ChainM
             }
             last_bound = true;
             if (!have_sd) {
-                if (need_rollback) { rollback<NT>(M, ts); need_rollback = false; IPC_PH(6); }
+                if (need_rollback) { rollback<NT, GST>(M, ts); need_rollback = false; IPC_PH(6); }
                 IPC_PH(7);
-                sd_fused<NT, UNI, STG>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps;
+                sd_fused<NT, UNI, STG, GST>(M, O, ts, bb, bh, hh, bHb); ++n_sweeps;
                 IPC_PH(5); IPC_PH_COUNT(12, 1);
                 ++n_sd;
                 alpha = bb / bHb;

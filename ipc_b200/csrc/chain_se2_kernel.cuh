@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(NT, MINB) chain_check_se2(BatchArgs A) {
         const int chk = A.work[wi];
         const int midx = A.member[chk];
         CheckResult r;
-        run_check<NT, UNI, MODE == 2>(M, A.odom, A.Du, A.Vu, loops + A.cand[chk], midx >= 0 ? loops + midx : nullptr, prm, A.info != nullptr, r, &stg);
+        run_check<NT, UNI, MODE == 2, MODE == 1>(M, A.odom, A.Du, A.Vu, loops + A.cand[chk], midx >= 0 ? loops + midx : nullptr, prm, A.info != nullptr, r, &stg);
         if (threadIdx.x == 0) {
             A.verdict[chk] = (unsigned char)r.verdict;
             if (A.info) {

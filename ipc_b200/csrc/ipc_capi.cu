@@ -295,6 +295,7 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
         if (!strcmp(name + 8, "cap")) h->buckets[b].cap = (int)value;
         else if (!strcmp(name + 8, "nt")) h->buckets[b].nt = (int)value;        // (nt, minb) must name an instantiated variant: checked at launch
         else if (!strcmp(name + 8, "minb")) h->buckets[b].minb = (int)value;
+        else if (!strcmp(name + 8, "mode")) h->buckets[b].mode = (int)value;      // 0 state in shared memory, 1 in the global scratch, 2 staged odometry
         else return fail(IPC_ERR_ARG, std::string("unknown option ") + name);
         for (int q = 1; q < NB - 1; ++q) if (h->buckets[q].cap < h->buckets[q - 1].cap) return fail(IPC_ERR_ARG, "bucket caps must be non-decreasing");
         CUDA_TRY(cudaSetDevice(h->device));

@@ -30,9 +30,9 @@ inline size_t smem_bytes(int mode, int cap, int dim = 2, int nt = 0) {
 inline size_t scratch_doubles_per_cta(int mode, int cap, int dim = 2, int nt = 0) {
     size_t capv = std::max(cap + 2, nt);
     // SE(2): the scratch is indexed by slot (vslot, chain_se2.cuh): up to capv + 2 nt + 2 records; nt = 0 sizes for the widest CTA
-    if (mode == 1) nt = nt == 256 ? 256 : 512;      // the global-state kernel exists for 256 and 512 threads (launch_se2_variant)
+    if (mode == 1) nt = 512;                        // global-state kernels: sized for the widest CTA (32 .. 512 threads, launch_se2_variant)
     const size_t capg = capv + 2 * (size_t)(nt > 0 ? nt : 512) + 2;
-    return dim == 2 ? (size_t)CHAIN_SCRATCH_ARRAYS * capg + (mode == 1 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0)
+    return dim == 2 ? (size_t)CHAIN_SCRATCH_ARRAYS * capg + (mode == 1 ? (size_t)global_state_doubles((int)capv, 512) : 0)
                     : (size_t)(se3::CHAIN3_SCRATCH + (mode == 1 ? se3::CHAIN3_STATE : 0)) * capv;
 }
 // the instantiated (threads, CTAs per SM) variants of the SE(2) kernel, and the SE(3) variants by thread count

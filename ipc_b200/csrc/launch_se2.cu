@@ -25,7 +25,11 @@ template <int NT, int MODE, int MINB> int launch_se2(const BatchArgs& a, int gri
 }
 // the instantiated (threads, CTAs per SM) variants
 int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni) {
-    if (mode == 1) return nt == 256 ? launch_se2<256, 1, 1>(a, grid, st, uni) : launch_se2<512, 1, 1>(a, grid, st, uni);
+    if (mode == 1) {      // state in the global scratch
+        if (nt == 32) return launch_se2<32, 1, 8>(a, grid, st, uni);
+        if (nt == 64) return launch_se2<64, 1, 4>(a, grid, st, uni);
+        return nt == 256 ? launch_se2<256, 1, 1>(a, grid, st, uni) : launch_se2<512, 1, 1>(a, grid, st, uni);
+    }
     if (mode == 2) {      // staged odometry (cp.async.bulk): uniform-information kernels only
         if (!uni) return fail(IPC_ERR_ARG, "staged-odometry kernels need a uniform-information graph");
 #define VS(NT_, MB_) if (nt == NT_ && minb == MB_) return launch_se2u<NT_, 2, true, MB_>(a, grid, st);

@@ -16,6 +16,8 @@ using namespace ipcb;
 static int* g_diag = nullptr;
 static int g_sd_fuse = 2;
 static int g_cta = 1;
+static int g_gst = 0;      // 1: run the checks with the global-memory state layout (tiles by step, StateAt<NT, true>)
+extern "C" void emul_set_global_state(int v) { g_gst = v; }
 extern "C" int emul_set_cta_threads(int nt) { if (nt != 1 && nt != 8 && nt != 16) return -1; g_cta = nt; return 0; }
 
 struct SpinBarrier {
@@ -34,10 +36,12 @@ template <int NT, bool UNI, class Out>
 static void cta_group(int n_poses, const double* odom, const double* Du, const double* Vu, const LoopRec2* recs, int n_checks, const int* member,
                       const int* cand, const CheckParams& prm, bool want_info, std::atomic<int>& next, Out&& out) {
     const int capv = n_poses + 2, capg = scratch_slots<NT>(capv);
-    std::vector<double> buf((size_t)CHAIN_STATE_ARRAYS * capv + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
+    const size_t st_doubles = std::max((size_t)CHAIN_STATE_ARRAYS * capv, (size_t)global_state_doubles(capv, NT));
+    std::vector<double> buf(st_doubles + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
     ChainMem M; double* p = buf.data();
-    M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN_STATE_ARRAYS * capv; M.capv = capv; M.capg = capg;
+    M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + st_doubles; M.capv = capv; M.capg = capg;
     SpinBarrier bar; bar.n = NT;
+    const bool gst = g_gst != 0;
     int cur = 0;
     auto body = [&](int tid) {
         HostCta cta{tid, &SpinBarrier::sync, &bar};
@@ -48,7 +52,8 @@ static void cta_group(int n_poses, const double* odom, const double* Du, const d
             const int c = cur;
             if (c >= n_checks) break;
             CheckResult r;
-            run_check<NT, UNI>(M, odom, Du, Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info, r);
+            if (gst) run_check<NT, UNI, false, true>(M, odom, Du, Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info, r);
+            else run_check<NT, UNI>(M, odom, Du, Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info, r);
             if (tid == 0) out(c, r);
             bar.wait();
         }
@@ -98,14 +103,18 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
     auto work = [&]() {
         const int capv = n_poses + 2;
         const int capg = scratch_slots<1>(capv);
-        std::vector<double> buf((size_t)CHAIN_STATE_ARRAYS * capv + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
+        const size_t st_doubles = std::max((size_t)CHAIN_STATE_ARRAYS * capv, (size_t)global_state_doubles(capv, 1));
+        std::vector<double> buf(st_doubles + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
         ChainMem M; double* p = buf.data();
-        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN_STATE_ARRAYS * capv; M.capv = capv; M.capg = capg;
+        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + st_doubles; M.capv = capv; M.capg = capg;
+        const bool gst = g_gst != 0;
         for (;;) {
             int c = next.fetch_add(1);
             if (c >= n_checks) break;
             CheckResult r;
-            if (uni) run_check<1, true>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+            if (gst) { if (uni) run_check<1, true, false, true>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
+                       else run_check<1, false, false, true>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r); }
+            else if (uni) run_check<1, true>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
             else run_check<1, false>(M, soa.data(), hs.Du, hs.Vu, &recs[cand[c]], member[c] >= 0 ? &recs[member[c]] : nullptr, prm, want_info != 0, r);
             emit(c, r);
         }

@@ -113,3 +113,24 @@ def test_emulated_edge_cases_match_oracle(oracle_lib, nt):
             assert np.array_equal(info["n_loops"], orep["n_cluster"] + 1)
     finally:
         emul.lib().emul_set_cta_threads(1)
+
+
+@pytest.mark.parametrize("nt", [1, 8, 16])
+def test_global_state_tile_layout_matches_shared_state(nt):
+    """State in global memory (tiles by step, StateAt<NT, true>: the one-warp-per-check and long-window kernels) against the
+    shared-memory layout: the arithmetic is the same, so verdicts, iteration counts and chi2 must agree to the last bit."""
+    from tests.host_emul import emul
+    z, g, cfg = load("pairs_se2_m3500.npz")
+    assert emul.lib().emul_set_cta_threads(nt) == 0
+    try:
+        for use_uni in (1, 0):
+            emul.lib().emul_set_global_state(0)
+            a0, i0, s0 = emul.check_batch(g, cfg, z["member"], z["cand"], use_uni=use_uni, n_threads=max(8, 2 * nt))
+            emul.lib().emul_set_global_state(1)
+            a1, i1, s1 = emul.check_batch(g, cfg, z["member"], z["cand"], use_uni=use_uni, n_threads=max(8, 2 * nt))
+            assert np.array_equal(a1, a0) and np.array_equal(a1, z["accept"])
+            assert np.array_equal(i1["iterations"], i0["iterations"]) and np.array_equal(s1, s0)
+            assert np.array_equal(i1["max_chi2"], i0["max_chi2"])
+    finally:
+        emul.lib().emul_set_global_state(0)
+        emul.lib().emul_set_cta_threads(1)
