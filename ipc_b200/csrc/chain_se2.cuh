@@ -359,10 +359,14 @@ constexpr int RED_DOUBLES_ = 16 * (NPRE + 4);
 constexpr int RED2_DOUBLES_ = 16 * 4;            // 16 warps x up to 4 values
 struct ChainMem {            // three base pointers + a capacity: cheap to keep in registers and to pass by value
     double* st;              // per-vertex state, AoS of 5 doubles: x, y, theta, cos, sin. Shared memory (MODE 0) or global scratch (MODE 1)
+    double* stw;             // where a trial sweep writes the new state. Shared-memory state: == st (in place, the old poses go to the backup B).
+                             // Global-memory state: a second buffer — an accepted trial swaps st / stw, a rejected one costs nothing (no backup
+                             // stream, no rollback pass)
     double* scr;             // per-CTA global scratch (L2 resident): pose backup AoS[3] x capg, (b, h_gn) AoS[6] x capg, odometry records, indexed
                              // by SLOT (vslot below), not by vertex: the threads of a warp walk their segments in lock step, so
                              // slot = step * NT + thread makes every scratch access of a warp one contiguous run of records
     double* small;           // shared memory: collective staging (2 buffers), special-vertex table (2 buffers), UniBlock
+    double* ring;            // shared memory, global-state kernels: per-thread prefetch ring (TileFeed), RING_D x RING_W x NT doubles
     int capv, capg;          // capacity of the state arrays (vertices) and of the scratch arrays (slots)
     IPC_HD double* P(int j) const { return st + 5 * j; }                          // x y theta cos sin of vertex j (state in shared memory)
     IPC_HD double* B(int sl) const { return scr + 3 * sl; }                       // pose backup: state before the last trial sweep
@@ -384,6 +388,9 @@ template <int NT, bool GST> struct StateAt {
     static constexpr int CS = GST ? NT : 1;                                       // distance between the components of one record
     IPC_HD static double* step(const ChainMem& M, int j, int i, int t) {         // vertex j = k0(t) + 1 + i of thread t
         return GST ? M.st + ((size_t)(i + 1) * 5) * NT + t : M.st + 5 * j;
+    }
+    IPC_HD static double* stepw(const ChainMem& M, int j, int i, int t) {        // same record in the buffer a trial sweep writes
+        return GST ? M.stw + ((size_t)(i + 1) * 5) * NT + t : M.stw + 5 * j;
     }
     IPC_HD static double* vertex(const ChainMem& M, int j, int S) {              // any vertex (rare accesses: loop end points)
         if (!GST) return M.st + 5 * j;
@@ -534,7 +541,9 @@ template <bool UNI> IPC_HD void sweep_gn_step(const OdomView& O, const OdomRec<U
     h[0] = X0 - ob.y * X2; h[1] = X1 + ob.x * X2; h[2] = X2;
 }
 
-template <int NT, bool UNI, bool STG, int STEP, bool GST = false> IPC_HD void sweep_mode(const ChainMem& M, const OdomView& O, double c1, double c2, ThreadState& ts,
+// Shared-memory state (the CTA-per-check kernels): the state is read in place, odometry records and gradients one step ahead
+// through registers.
+template <int NT, bool UNI, bool STG, int STEP, bool GST = false> IPC_HD void sweep_mode_direct(const ChainMem& M, const OdomView& O, double c1, double c2, ThreadState& ts,
                                                                        SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
     using SA = StateAt<NT, GST>;
     constexpr int CS = SA::CS;
@@ -724,8 +733,282 @@ template <int NT, bool UNI, bool STG, int STEP, bool GST = false> IPC_HD void sw
     buf ^= 1;
     IPC_PH(2);
 }
+
+// ---- the per-step input stream of a pass ---------------------------------------------------------------------------------
+// Step i of a thread's segment walk needs the state of vertex k0 + 1 + i, the odometry record of edge k0 + i (its head is that
+// vertex) and, in blend sweeps, (b, h_gn) of that vertex. TileFeed hands these out in step order:
+//   * state in shared memory (GST = false): the state is read in place, record and gradient one step ahead through registers;
+//   * state in global memory, uniform-information kernels on the device (RING): everything for step i + RING_D is already on its
+//     way into a per-thread ring in shared memory (cp.async, one commit group per step), so the L2 / HBM latency of the streamed
+//     window is covered by RING_D steps of arithmetic without holding registers;
+//   * state in global memory otherwise (general information, host emulation): one step ahead through registers.
+IPC_HD constexpr int ring_depth(int nt) { return nt > 256 ? 2 : 4; }      // steps in flight (the 512-thread ring must still fit shared memory)
+constexpr int RING_W = 14;           // doubles per step and thread: state 5, odometry record 3, (b, h_gn) 6
+IPC_HD constexpr int ring_doubles(int nt) { return ring_depth(nt) * RING_W * nt; }
+#ifndef IPC_RING_ODOM_SHARED
+#define IPC_RING_ODOM_SHARED 1
+#endif
+#ifdef __CUDA_ARCH__
+#define IPC_RING_DEVICE 1
+#else
+#define IPC_RING_DEVICE 0
+#endif
+template <int NT, bool UNI, bool STG, bool GST, bool WITH_G> struct TileFeed {
+    static constexpr bool RING = GST && UNI && !STG && (IPC_RING_DEVICE != 0);
+    static constexpr int RING_D = ring_depth(NT);
+    static constexpr int CS = StateAt<NT, GST>::CS;
+    const ChainMem& M; const OdomView& O;
+    int k0, n, tid;                      // first edge, number of steps, thread
+    double bst[5]; OdomRec<UNI> brec; double bg[6];      // register look-ahead (paths without the ring)
+    IPC_HD TileFeed(const ChainMem& M_, const OdomView& O_, int k0_, int n_, int tid_) : M(M_), O(O_), k0(k0_), n(n_), tid(tid_) {}
+    IPC_HD void load_direct(int i, double* st5, OdomRec<UNI>& rec, double* g6) const {
+        const int ic = i < n ? i : n - 1;                // past the end: a valid address, the values are not used
+        if (GST) { const double* ps = StateAt<NT, GST>::step(M, k0 + 1 + ic, ic, tid);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) st5[q] = ps[q * CS]; }
+        odom_load<UNI, STG>(O, ic * NT + tid, k0 + ic, rec);
+        if (WITH_G) { const double* gq = M.G((ic * NT + tid) + 1);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) g6[q] = gq[q]; }
+    }
+#ifdef __CUDA_ARCH__
+    IPC_HD void ring_issue(int i) const {
+        if (i < n) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(M.ring) + (unsigned)((((i & (RING_D - 1)) * RING_W) * NT + tid) * 8);
+            const double* ps = StateAt<NT, GST>::step(M, 0, i, tid);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + q * NT * 8), "l"(ps + q * CS) : "memory");
+            // odometry record of edge k0 + i: from the graph's own array (84 KB for M3500: L1 / L2 resident, shared by every check) —
+            // 24 scattered bytes per thread, but no per-check copy of the window to stream from HBM
+            const double* po = IPC_RING_ODOM_SHARED ? O.rec + 3 * (size_t)(k0 + i) : O.zs + 3 * (size_t)(i * NT + tid);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (5 + q) * NT * 8), "l"(po + q) : "memory");
+            if (WITH_G) { const double* gq = M.G((i * NT + tid) + 1);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (8 + q) * NT * 8), "l"(gq + q) : "memory"); }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#endif
+    IPC_HD void start() {
+#ifdef __CUDA_ARCH__
+        if (RING) {
+#pragma unroll
+            for (int i = 0; i < RING_D; ++i) ring_issue(i);
+            return;
+        }
+#endif
+        load_direct(0, bst, brec, bg);
+    }
+    // inputs of step i (called for i = 0, 1, 2, ... in order; i may run past the end by one: clamped)
+    IPC_HD void next(int i, double* st5, OdomRec<UNI>& rec, double* g6) {
+#ifdef __CUDA_ARCH__
+        if (RING) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RING_D - 1) : "memory");
+            const double* src = M.ring + (((i & (RING_D - 1)) * RING_W) * NT + tid);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) st5[q] = src[q * NT];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) rec.z[q] = src[(5 + q) * NT];
+            if (WITH_G) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) g6[q] = src[(8 + q) * NT]; }
+            ring_issue(i + RING_D);
+            return;
+        }
+#endif
+        if (GST) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) st5[q] = bst[q]; }
+        else { const int ic = i < n ? i : n - 1; const double* ps = StateAt<NT, GST>::step(M, k0 + 1 + ic, ic, tid);
+#pragma unroll
+            for (int q = 0; q < 5; ++q) st5[q] = ps[q * CS]; }
+        rec = brec;
+        if (WITH_G) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) g6[q] = bg[q]; }
+        load_direct(i + 1, bst, brec, bg);
+    }
+    IPC_HD void finish() const {
+#ifdef __CUDA_ARCH__
+        if (RING) asm volatile("cp.async.wait_group 0;" ::: "memory");     // the ring is reused by the next pass
+#endif
+    }
+};
+
+template <int NT, bool UNI, bool STG, int STEP, bool GST = false> IPC_HD void sweep_mode(const ChainMem& M, const OdomView& O, double c1, double c2, ThreadState& ts,
+                                                                       SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
+    const int k0 = ts.k0, k1 = ts.k1;
+    const StepSpec* sp = &M.U()->sol;
+    double* spec = M.spec() + (size_t)buf * NSPEC * SPECW;
+    double pre[NPRE];        // running prefix of the OLD linearisation (GN mode)
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
+    P2 oa = ts.pa; double oca = ts.ca, osa = ts.sa;      // old from-vertex of the next A
+    P2 na = oa; double nca = oca, nsa = osa;             // new from-vertex of the next B
+    if (STEP != STEP_NONE && k0 > 0 && k0 < k1) {        // boundary vertex k0: same arithmetic as its owner => identical bits
+        double h[3];
+        if (STEP == STEP_GN) gn_step_at(sp, k0, pre, oa.x, oa.y, h);
+        else {
+            const double* gq = M.G((ts.S - 1) * NT + ts.tid);      // vertex k0 = the last vertex of thread tid - 1
+#pragma unroll
+            for (int q = 0; q < 3; ++q) h[q] = c1 * gq[q] + c2 * gq[3 + q];
+        }
+        na.x += h[0]; na.y += h[1]; na.t = wrap_pi_hd(na.t + h[2]);
+        ipc_sincos(na.t, &nsa, &nca);
+    }
+    ts.pa = na; ts.ca = nca; ts.sa = nsa;
+    double run[NPRE];        // local prefix of the NEW linearisation
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) run[m] = 0;
+    double chi = 0, mx = 0, hh = 0, gain = 0;
+    bool has_spec = false;
+#pragma unroll
+    for (int q = 1; q < NSPEC; ++q) has_spec |= (spec_v[q] > k0 && spec_v[q] <= k1);
+    const int v_rs = spec_v[1], v_re = spec_v[2];        // region boundaries (sp->rs, sp->re)
+    if (k0 < k1) {
+        int sl = ts.tid + 1;                     // scratch slot of vertex k + 1 (the vertex B(k) finishes); + NT per vertex
+        TileFeed<NT, UNI, STG, GST, STEP == STEP_BLEND> feed(M, O, k0, k1 - k0, ts.tid);
+        feed.start();
+        OdomRec<UNI> rB;                         // record of edge k (B uses it one step after A did)
+        // ---- prologue: A(k0) ----
+        P2 nb; double ncb, nsb;                  // vertex k + 1 at the new state (cos / sin: known only for STEP_NONE before B)
+        {
+            double p5[5], g6[6];
+            feed.next(0, p5, rB, g6);
+            const P2 ob{p5[0], p5[1], p5[2]};
+            const double ocb = p5[3], osb = p5[4];
+            nb = ob; ncb = ocb; nsb = osb;
+            if (STEP != STEP_NONE) {
+                double h[3];
+                if (STEP == STEP_GN) {
+                    const int rg = (k0 < v_rs) ? 0 : (k0 < v_re ? 1 : 2);
+                    sweep_gn_step<UNI>(O, rB, sp->z[rg], sp->C[rg], oa, oca, osa, ob, pre, gain, h);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) h[q] = c1 * g6[q] + c2 * g6[3 + q];
+                }
+                if (!GST) { double* bq = M.B(sl); bq[0] = ob.x; bq[1] = ob.y; bq[2] = ob.t; }
+                nb.x += h[0]; nb.y += h[1]; nb.t = wrap_pi_hd(nb.t + h[2]);
+                hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+            }
+            oa = ob; oca = ocb; osa = osb;
+        }
+        // ---- steady state: B(k) next to A(k + 1) ----
+        int k = k0;
+        for (; k + 1 < k1; ++k, sl += NT) {
+            // loads first (old pose of vertex k + 2, record of edge k + 1, the region's force)
+            double p5[5], gA[6];
+            OdomRec<UNI> rA;
+            feed.next(k - k0 + 1, p5, rA, gA);
+            const P2 ob2{p5[0], p5[1], p5[2]};
+            const double ocb2 = p5[3], osb2 = p5[4];
+            double zr[3] = {0, 0, 0}, Cr[3] = {0, 0, 0};
+            if (STEP == STEP_GN) {
+                const int rg = (k + 1 < v_rs) ? 0 : (k + 1 < v_re ? 1 : 2);
+#pragma unroll
+                for (int q = 0; q < 3; ++q) { zr[q] = sp->z[rg][q]; Cr[q] = sp->C[rg][q]; }
+            }
+            // B(k): vertex j = k + 1 gets its cos / sin, edge k its new linearisation
+            const int j = k + 1;
+            if (STEP != STEP_NONE) ipc_sincos(nb.t, &nsb, &ncb);
+            Lin2 e; double t[NPRE];
+            odom_terms<UNI>(O, rB, nca, nsa, na, nb, e, t);
+            chi += e.chi; mx = fmax(mx, e.chi);
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) run[m] += t[m];
+            // A(k + 1): step of vertex k + 2 from the old linearisation of edge k + 1
+            P2 nb2 = ob2;
+            if (STEP != STEP_NONE) {
+                double h[3];
+                if (STEP == STEP_GN) sweep_gn_step<UNI>(O, rA, zr, Cr, oa, oca, osa, ob2, pre, gain, h);
+                else {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) h[q] = c1 * gA[q] + c2 * gA[3 + q];
+                }
+                nb2.x += h[0]; nb2.y += h[1]; nb2.t = wrap_pi_hd(nb2.t + h[2]);
+                hh += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+            }
+            // stores last
+            if (STEP != STEP_NONE) {
+                double* pq = SA::stepw(M, j, k - k0, ts.tid);
+                pq[0] = nb.x; pq[CS] = nb.y; pq[2 * CS] = nb.t; pq[3 * CS] = ncb; pq[4 * CS] = nsb;
+                if (!GST) { double* bq = M.B(sl + NT); bq[0] = ob2.x; bq[1] = ob2.y; bq[2] = ob2.t; }
+            }
+            if (has_spec) {
+#pragma unroll
+                for (int q = 1; q < NSPEC; ++q) {
+                    if (j == spec_v[q]) {        // local part now, the thread base is added after the scan
+                        double* o = spec + q * SPECW;
+#pragma unroll
+                        for (int m = 0; m < NPRE; ++m) o[m] = run[m];
+                        o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+                    }
+                }
+            }
+            na = nb; nca = ncb; nsa = nsb;
+            nb = nb2; ncb = ocb2; nsb = osb2;
+            oa = ob2; oca = ocb2; osa = osb2;
+            rB = rA;
+        }
+        feed.finish();
+        // ---- epilogue: B(k1 - 1) ----
+        {
+            const int j = k + 1;
+            if (STEP != STEP_NONE) {
+                ipc_sincos(nb.t, &nsb, &ncb);
+                double* pq = SA::stepw(M, j, k - k0, ts.tid);
+                pq[0] = nb.x; pq[CS] = nb.y; pq[2 * CS] = nb.t; pq[3 * CS] = ncb; pq[4 * CS] = nsb;
+            }
+            Lin2 e; double t[NPRE];
+            odom_terms<UNI>(O, rB, nca, nsa, na, nb, e, t);
+            chi += e.chi; mx = fmax(mx, e.chi);
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) run[m] += t[m];
+            if (has_spec) {
+#pragma unroll
+                for (int q = 1; q < NSPEC; ++q) {
+                    if (j == spec_v[q]) {
+                        double* o = spec + q * SPECW;
+#pragma unroll
+                        for (int m = 0; m < NPRE; ++m) o[m] = run[m];
+                        o[NPRE] = nb.x; o[NPRE + 1] = nb.y; o[NPRE + 2] = nb.t;
+                    }
+                }
+            }
+        }
+    }
+    double s[3] = {chi, hh, gain};
+    IPC_PH(1);
+    ScanSumMax<NT, 3>::run(run, s, mx, M.red() + (size_t)buf * RED_DOUBLES);
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) ts.base[m] = run[m];
+    out.chi = s[0]; out.hh = s[1]; out.gain = s[2]; out.mx = mx;
+    if (has_spec) {
+#pragma unroll
+        for (int q = 1; q < NSPEC; ++q) {
+            const int v = spec_v[q];
+            if (v > k0 && v <= k1) {
+                double* o = spec + q * SPECW;
+#pragma unroll
+                for (int m = 0; m < NPRE; ++m) o[m] += run[m];
+            }
+        }
+    }
+    bsync<NT>();
+    buf ^= 1;
+    IPC_PH(2);
+}
 template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sweep(const ChainMem& M, const OdomView& O, int mode, double c1, double c2, ThreadState& ts,
                                               SweepOut& out, int& buf, const int* spec_v IPC_PH_ARG) {
+    if (!GST) {
+        if (mode == STEP_GN) sweep_mode_direct<NT, UNI, STG, STEP_GN, false>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
+        else if (mode == STEP_BLEND) sweep_mode_direct<NT, UNI, STG, STEP_BLEND, false>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
+        else sweep_mode_direct<NT, UNI, STG, STEP_NONE, false>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
+        return;
+    }
     if (mode == STEP_GN) sweep_mode<NT, UNI, STG, STEP_GN, GST>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
     else if (mode == STEP_BLEND) sweep_mode<NT, UNI, STG, STEP_BLEND, GST>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
     else sweep_mode<NT, UNI, STG, STEP_NONE, GST>(M, O, c1, c2, ts, out, buf, spec_v IPC_PH_PASS);
@@ -737,7 +1020,9 @@ template <int NT, bool GST = false> IPC_HD void rollback(const ChainMem& M, Thre
     using SA = StateAt<NT, GST>;
     constexpr int CS = SA::CS;
     int sl = ts.tid + 1;
-    for (int k = ts.k0; k < ts.k1; ++k, sl += NT) {
+    // global-memory state: the rejected trial went to the other buffer, only the boundary registers are re-read below
+#pragma unroll 4
+    for (int k = ts.k0; k < ts.k1 && !GST; ++k, sl += NT) {
         const int j = k + 1;
         const double* bq = M.B(sl);
         const double t = bq[2];
@@ -1039,8 +1324,8 @@ template <int NT> IPC_HD void eval_and_solve(const ChainMem& M, int buf, double 
     n_c = M.U()->n_c; n_m = M.U()->n_m;
 }
 
-// |h_gn|^2 of the current linearisation without applying it
-template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
+// |h_gn|^2 of the current linearisation without applying it (state in shared memory: read in place)
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD double gn_norm_sq_direct(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
     using SA = StateAt<NT, GST>;
     constexpr int CS = SA::CS;
     double v[1] = {0};
@@ -1071,13 +1356,44 @@ template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD double gn
     return v[0];
 }
 
+// |h_gn|^2 of the current linearisation without applying it
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD double gn_norm_sq(const ChainMem& M, const OdomView& O, const ThreadState& ts) {
+    if (!GST) return gn_norm_sq_direct<NT, UNI, STG, false>(M, O, ts);
+    double v[1] = {0};
+    const StepSpec* sp = &M.U()->sol;
+    double pre[NPRE];
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
+    P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
+    if (ts.k0 < ts.k1) {
+        TileFeed<NT, UNI, STG, GST, false> feed(M, O, ts.k0, ts.k1 - ts.k0, ts.tid);
+        feed.start();
+        for (int k = ts.k0; k < ts.k1; ++k) {
+            const int j = k + 1;
+            double p5[5], g6[6]; OdomRec<UNI> r;
+            feed.next(k - ts.k0, p5, r, g6);
+            const P2 pb{p5[0], p5[1], p5[2]};
+            Lin2 e; double t[NPRE], h[3];
+            odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
+            gn_step_at(sp, j, pre, pb.x, pb.y, h);
+            v[0] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+            pa = pb; ca = p5[3]; sa = p5[4];
+        }
+        feed.finish();
+    }
+    hd_block_sum<NT, 1>(v, M.red2());
+    return v[0];
+}
+
 // Steepest-descent pass at the current state (poses + prefixes valid): gradient b and h_gn per vertex (g2o vertex coordinates)
 // into the scratch, bb = |b|^2, bh = b . h_gn, hh = |h_gn|^2, bHb = b^T H b = sum over edges |J (b_k, b_k+1)|^2_D — in ONE pass:
 // the edge term of b^T H b lags one edge behind the gradient, so both are finished from a single evaluation of every edge. A thread owns the vertices
 // k0+1..k1 and the Hessian terms of the edges k0+1..k1 (thread 0 also edge 0); the one term that needs the next thread's first
 // gradient is completed after the block barrier from the scratch. Stands in for gn_norm_sq + a separate gradient pass when the
 // iteration is expected to be trust-region bound (gn_norm_sq alone is the cheaper pass when the GN step is expected to fit).
-template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sd_fused_direct(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
                                                  double& bh, double& hh, double& bHb) {
     using SA = StateAt<NT, GST>;
     constexpr int CS = SA::CS;
@@ -1189,6 +1505,134 @@ template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sd_f
     bb = v[0]; bh = v[1]; hh = v[2]; bHb = v[3];
 }
 
+// Steepest-descent pass at the current state (poses + prefixes valid): gradient b and h_gn per vertex (g2o vertex coordinates)
+// into the scratch, bb = |b|^2, bh = b . h_gn, hh = |h_gn|^2, bHb = b^T H b = sum over edges |J (b_k, b_k+1)|^2_D — in ONE pass:
+// the edge term of b^T H b lags one edge behind the gradient, so both are finished from a single evaluation of every edge. A thread owns the vertices
+// k0+1..k1 and the Hessian terms of the edges k0+1..k1 (thread 0 also edge 0); the one term that needs the next thread's first
+// gradient is completed after the block barrier from the scratch. Stands in for gn_norm_sq + a separate gradient pass when the
+// iteration is expected to be trust-region bound (gn_norm_sq alone is the cheaper pass when the GN step is expected to fit).
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void sd_fused(const ChainMem& M, const OdomView& O, const ThreadState& ts, double& bb,
+                                                 double& bh, double& hh, double& bHb) {
+    if (!GST) { sd_fused_direct<NT, UNI, STG, false>(M, O, ts, bb, bh, hh, bHb); return; }
+    using SA = StateAt<NT, GST>;
+    constexpr int CS = SA::CS;
+    const CheckGeom& g = M.U()->g;
+    const int k0 = ts.k0, k1 = ts.k1, L = g.L;
+    const StepSpec* sp = &M.U()->sol;
+    const LoopRec2& Lc = M.U()->Lc; const LoopRec2& Lm = M.U()->Lm;
+    Lin2 ec, em; const int cjf = Lc.from - g.lo, cjt = Lc.to - g.lo; int mjf = -1, mjt = -1;
+    {
+        const double* qf = SA::vertex(M, cjf, ts.S); const double* qt = SA::vertex(M, cjt, ts.S);
+        P2 pf{qf[0], qf[CS], qf[2 * CS]}, pt{qt[0], qt[CS], qt[2 * CS]};
+        lin2cs(qf[3 * CS], qf[4 * CS], pf, pt, Lc.meas[0], Lc.meas[1], Lc.meas[2], Lc.D, ec);
+    }
+    double gci[3], gcj[3], gmi[3] = {0, 0, 0}, gmj[3] = {0, 0, 0};
+    grad2(ec, gci, gcj);
+    if (g.K == 2) {
+        mjf = Lm.from - g.lo; mjt = Lm.to - g.lo;
+        const double* qf = SA::vertex(M, mjf, ts.S); const double* qt = SA::vertex(M, mjt, ts.S);
+        P2 pf{qf[0], qf[CS], qf[2 * CS]}, pt{qt[0], qt[CS], qt[2 * CS]};
+        lin2cs(qf[3 * CS], qf[4 * CS], pf, pt, Lm.meas[0], Lm.meas[1], Lm.meas[2], Lm.D, em);
+        grad2(em, gmi, gmj);
+    }
+    double v[4] = {0, 0, 0, 0};
+    double pre[NPRE];
+#pragma unroll
+    for (int m = 0; m < NPRE; ++m) pre[m] = ts.base[m];
+    double bprev[3] = {0, 0, 0};        // gradient at the tail vertex of the lagging edge (vertex 0: fixed, zero)
+    double pc = 1, ps = 0, prx = 0, pry = 0, pD[6] = {0, 0, 0, 0, 0, 0};   // Jacobian pieces (and information) of the lagging edge
+    bool tail_pending = false;          // edge k1 (< L) waits for the next thread's first gradient
+    auto finish_vertex = [&](int j, int sl, const double* gsum, double x, double y, double* b) {
+        b[0] = -gsum[0]; b[1] = -gsum[1]; b[2] = -gsum[2];
+        if (j == cjf) { b[0] -= gci[0]; b[1] -= gci[1]; b[2] -= gci[2]; }
+        if (j == cjt) { b[0] -= gcj[0]; b[1] -= gcj[1]; b[2] -= gcj[2]; }
+        if (j == mjf) { b[0] -= gmi[0]; b[1] -= gmi[1]; b[2] -= gmi[2]; }
+        if (j == mjt) { b[0] -= gmj[0]; b[1] -= gmj[1]; b[2] -= gmj[2]; }
+        double h[3];
+        gn_step_at(sp, j, pre, x, y, h);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { M.G(sl)[q] = b[q]; M.G(sl)[3 + q] = h[q]; }
+        v[0] += b[0] * b[0] + b[1] * b[1] + b[2] * b[2];
+        v[1] += b[0] * h[0] + b[1] * h[1] + b[2] * h[2];
+        v[2] += h[0] * h[0] + h[1] * h[1] + h[2] * h[2];
+    };
+    auto lag_term = [&](const double* ba, const double* bv) {   // |J (ba, bv)|^2_D of the lagging edge
+        const double ux = bv[0] - ba[0], uy = bv[1] - ba[1];
+        const double q0 = pc * ux + ps * uy + pry * ba[2], q1 = -ps * ux + pc * uy - prx * ba[2], q2 = bv[2] - ba[2];
+        v[3] += quad3(UNI ? O.Du : pD, q0, q1, q2);
+    };
+    if (k0 < k1) {
+        P2 pa = ts.pa; double ca = ts.ca, sa = ts.sa;
+        double gprev[3] = {0, 0, 0};
+        int sl = ts.tid + 1;
+        TileFeed<NT, UNI, STG, GST, false> feed(M, O, k0, k1 - k0, ts.tid);
+        feed.start();
+        for (int k = k0; k <= k1 && k < L; ++k) {
+            double p5[5], g6u[6]; OdomRec<UNI> r;
+            if (k < k1) feed.next(k - k0, p5, r, g6u);
+            else {                               // edge k1: the first step of thread tid + 1 (vertex k1 + 1, its record)
+                const double* pq = SA::step(M, k + 1, 0, ts.tid + 1);
+#pragma unroll
+                for (int q = 0; q < 5; ++q) p5[q] = pq[q * CS];
+                if (GST && UNI && !STG && (IPC_RING_DEVICE != 0) && (IPC_RING_ODOM_SHARED != 0)) {      // no per-check copy of the records
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) r.z[q] = ldg_d(odom_rec<UNI>(O, k) + q);
+                } else odom_load<UNI, STG>(O, ts.tid + 1, k, r);
+            }
+            P2 pb{p5[0], p5[1], p5[2]};
+            const double cbn = p5[3], sbn = p5[4];
+            Lin2 e; double t[NPRE];
+            odom_terms<UNI>(O, r, ca, sa, pa, pb, e, t);
+            double gi[3], gj[3]; grad2(e, gi, gj);
+            if (k > k0) {
+                const double gs[3] = {gprev[0] + gi[0], gprev[1] + gi[1], gprev[2] + gi[2]};
+                double b[3];
+                finish_vertex(k, sl, gs, pa.x, pa.y, b);     // vertex k = k0 + 1 + (k - k0 - 1)
+                sl += NT;
+                if (k - 1 > k0 || k0 == 0) lag_term(bprev, b);      // edge k-1: both gradients are this thread's
+                bprev[0] = b[0]; bprev[1] = b[1]; bprev[2] = b[2];
+            }
+#pragma unroll
+            for (int m = 0; m < NPRE; ++m) pre[m] += t[m];
+            gprev[0] = gj[0]; gprev[1] = gj[1]; gprev[2] = gj[2];
+            pc = e.c; ps = e.s; prx = e.rx; pry = e.ry;
+            if (!UNI) {
+#pragma unroll
+                for (int c = 0; c < 6; ++c) pD[c] = r.z[UNI ? 0 : 3 + c];
+            }
+            pa = pb; ca = cbn; sa = sbn;
+        }
+        feed.finish();
+        if (k1 == L) {
+            double b[3];
+            finish_vertex(L, sl, gprev, pa.x, pa.y, b);
+            if (L - 1 > k0 || k0 == 0) lag_term(bprev, b);
+        } else tail_pending = true;
+    }
+    if (hd_tid() == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q) { M.G(0)[q] = 0; M.G(0)[3 + q] = 0; }
+    }
+    bsync<NT>();                        // every gradient is in the scratch
+    if (tail_pending) {
+        const double* gq = M.G(ts.tid + 2);         // vertex k1 + 1 = the first vertex of thread tid + 1
+        const double bn[3] = {gq[0], gq[1], gq[2]};
+        lag_term(bprev, bn);
+    }
+    if (hd_tid() == 0) {
+        const double* gf = M.G(vslot<NT>(cjf, ts.S)); const double* gt = M.G(vslot<NT>(cjt, ts.S));
+        double bf[3] = {gf[0], gf[1], gf[2]}, bt[3] = {gt[0], gt[1], gt[2]}, q0, q1, q2;
+        dlin2(ec, bf, bt, q0, q1, q2); v[3] += quad3(Lc.D, q0, q1, q2);
+        if (g.K == 2) {
+            gf = M.G(vslot<NT>(mjf, ts.S)); gt = M.G(vslot<NT>(mjt, ts.S));
+            double mf[3] = {gf[0], gf[1], gf[2]}, mt[3] = {gt[0], gt[1], gt[2]};
+            dlin2(em, mf, mt, q0, q1, q2); v[3] += quad3(Lm.D, q0, q1, q2);
+        }
+    }
+    hd_block_sum<NT, 4>(v, M.red2());
+    bb = v[0]; bh = v[1]; hh = v[2]; bHb = v[3];
+}
+
 struct CheckParams {
     double fast_th, slow_th;
     int fast_iter, slow_iter;
@@ -1214,11 +1658,12 @@ enum { P_INIT = 0, P_TRIAL_SPEC, P_TRIAL_GN, P_TRIAL_BLEND, P_RELIN_SPECFAIL, P_
 
 // STG (device, UNI only): `stage` = shared-memory buffer for the window's odometry records + an mbarrier behind it (StageMem).
 struct StageMem { double* buf; unsigned long long* mbar; unsigned phase; };
-template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void run_check(const ChainMem& M, const double* odom, const double* Du, const double* Vu,
+template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void run_check(const ChainMem& M_in, const double* odom, const double* Du, const double* Vu,
                                                   const LoopRec2* Lc_in, const LoopRec2* Lm_in, const CheckParams& prm, bool want_info, CheckResult& res,
                                                   StageMem* stage = nullptr) {
     using SA = StateAt<NT, GST>;
     constexpr int CS = SA::CS;
+    ChainMem M = M_in;                                      // st / stw swap when a trial is accepted (global-memory state)
     const int tid = hd_tid();
 #if defined(IPC_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
     const long long ph_start = clock64();
@@ -1288,12 +1733,21 @@ template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void run_
     const int k0 = ts.k0, k1 = ts.k1;
 
     // ---- dead-reckoning (propagateGuess, src/consensus_utils.cpp:98-116) as two block scans --------------
+    // The loops walk in chunks of four steps with the loads of a chunk issued together: when the state lives in global memory a
+    // step-by-step loop would pay one L2 / HBM round trip per step (loads cannot be hoisted above the state stores by the compiler).
+    // ODOM_DIRECT (ring kernels): the records come straight from the graph's array in every pass, no per-check copy is made.
+    constexpr bool ODOM_DIRECT = GST && UNI && !STG && (IPC_RING_DEVICE != 0) && (IPC_RING_ODOM_SHARED != 0);
     {
         double v[1] = {0};
         {   // the only strided read of the odometry: the records go to the scratch in slot order
             int es = tid;
             if (STG) { for (int k = k0; k < k1; ++k) v[0] += O.sm[3 * k + 2]; }
-            else for (int k = k0; k < k1; ++k, es += NT) {
+            else if (ODOM_DIRECT) {
+#pragma unroll 4
+                for (int k = k0; k < k1; ++k) v[0] += ldg_d(odom_rec<UNI>(O, k) + 2);
+            } else
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k, es += NT) {
                 const double* zr = odom_rec<UNI>(O, k);
                 double* zo = O.zs + (UNI ? 3 : 9) * (size_t)es;
 #pragma unroll
@@ -1303,33 +1757,55 @@ template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void run_
         hd_block_excl_scan<NT, 1>(v, M.red2());
         double acc = v[0];
         const double th0 = wrap_pi_hd(acc);                 // heading of vertex k0
-        if (tid == 0) { double* p0 = SA::vertex(M, 0, 1); p0[0] = 0; p0[CS] = 0; p0[2 * CS] = 0; p0[3 * CS] = 1; p0[4 * CS] = 0; }
+        if (tid == 0) {
+            double* p0 = SA::vertex(M, 0, 1); p0[0] = 0; p0[CS] = 0; p0[2 * CS] = 0; p0[3 * CS] = 1; p0[4 * CS] = 0;
+            if (GST) { double* p1 = M.stw; p1[0] = 0; p1[CS] = 0; p1[2 * CS] = 0; p1[3 * CS] = 1; p1[4 * CS] = 0; }
+        }
         double p[2] = {0, 0};
         double s, c; ipc_sincos(th0, &s, &c);
         ts.pa.t = th0; ts.ca = c; ts.sa = s;
-        int es = tid;
-        for (int k = k0; k < k1; ++k, es += NT) {
-            const double* zr = STG ? O.sm + 3 * k : O.zs + (UNI ? 3 : 9) * (size_t)es;
-            const double zx = zr[0], zy = zr[1], zt = zr[2];
-            p[0] += c * zx - s * zy; p[1] += s * zx + c * zy;
-            acc += zt;
-            const double thk = wrap_pi_hd(acc);
-            ipc_sincos(thk, &s, &c);
-            double* pq = SA::step(M, k + 1, k - k0, tid);
-            pq[2 * CS] = thk; pq[3 * CS] = c; pq[4 * CS] = s;
+        auto rec_of = [&](int k) -> const double* {         // record of local edge k (this thread's step k - k0)
+            return STG ? O.sm + 3 * k : (ODOM_DIRECT ? odom_rec<UNI>(O, k) : O.zs + (UNI ? 3 : 9) * (size_t)((k - k0) * NT + tid));
+        };
+        for (int kb = k0; kb < k1; kb += 4) {
+            double zx[4], zy[4], zt[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const double* zr = rec_of(kb + u < k1 ? kb + u : k1 - 1); zx[u] = zr[0]; zy[u] = zr[1]; zt[u] = zr[2]; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u;
+                if (k < k1) {
+                    p[0] += c * zx[u] - s * zy[u]; p[1] += s * zx[u] + c * zy[u];
+                    acc += zt[u];
+                    const double thk = wrap_pi_hd(acc);
+                    ipc_sincos(thk, &s, &c);
+                    double* pq = SA::step(M, k + 1, k - k0, tid);
+                    pq[2 * CS] = thk; pq[3 * CS] = c; pq[4 * CS] = s;
+                }
+            }
         }
         bsync<NT>();
         hd_block_excl_scan<NT, 2>(p, M.red2());
         double ax = p[0], ay = p[1];
         ts.pa.x = ax; ts.pa.y = ay;
         c = ts.ca; s = ts.sa;
-        es = tid;
-        for (int k = k0; k < k1; ++k, es += NT) {
-            const double* zr = STG ? O.sm + 3 * k : O.zs + (UNI ? 3 : 9) * (size_t)es;
-            const double zx = zr[0], zy = zr[1];
-            ax += c * zx - s * zy; ay += s * zx + c * zy;
-            double* pq = SA::step(M, k + 1, k - k0, tid);
-            pq[0] = ax; pq[CS] = ay; c = pq[3 * CS]; s = pq[4 * CS];
+        for (int kb = k0; kb < k1; kb += 4) {
+            double zx[4], zy[4], cn[4], sn[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u < k1 ? kb + u : k1 - 1;
+                const double* zr = rec_of(k); zx[u] = zr[0]; zy[u] = zr[1];
+                const double* pq = SA::step(M, k + 1, k - k0, tid); cn[u] = pq[3 * CS]; sn[u] = pq[4 * CS];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = kb + u;
+                if (k < k1) {
+                    ax += c * zx[u] - s * zy[u]; ay += s * zx[u] + c * zy[u];
+                    double* pq = SA::step(M, k + 1, k - k0, tid);
+                    pq[0] = ax; pq[CS] = ay; c = cn[u]; s = sn[u];
+                }
+            }
         }
 #pragma unroll
         for (int m = 0; m < NPRE; ++m) ts.base[m] = 0;
@@ -1398,6 +1874,7 @@ template <int NT, bool UNI, bool STG = false, bool GST = false> IPC_HD void run_
             if (rho > 0.75) delta = fmax(delta, 3 * hdlNorm);
             else if (rho < 0.25) delta *= 0.5;
             if (rho > 0) {
+                if (GST) { double* t_ = M.st; M.st = M.stw; M.stw = t_; }     // the trial state becomes the state
                 cur_chi = newChi; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
                 gain_loops = M.U()->sol.gain_loops;
                 prev_hnorm = hdlNorm;

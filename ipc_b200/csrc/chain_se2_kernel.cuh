@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(NT, MINB) chain_check_se2(BatchArgs A) {
     ChainMem M;
     M.small = sm; M.scr = scr; M.capv = capv; M.capg = scratch_slots<NT>(capv);
     M.st = (MODE != 1) ? sm + CHAIN_SMALL_DOUBLES : scr + (size_t)CHAIN_SCRATCH_ARRAYS * M.capg;
+    M.stw = (MODE != 1) ? M.st : M.st + global_state_doubles(capv, NT);
+    M.ring = (MODE == 1) ? sm + CHAIN_SMALL_DOUBLES : nullptr;
     StageMem stg{nullptr, nullptr, 0u};
     if (MODE == 2) {
         stg.buf = sm + CHAIN_SMALL_DOUBLES + (size_t)CHAIN_STATE_ARRAYS * capv;

@@ -84,13 +84,22 @@ namespace {
 // vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
 const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3}, {2600, 128, 0, 2}, {5400, 256, 0, 1}, {1 << 30, 256, 1, 1}};
 
+// Uniform-information SE(2) graphs (M3500, City10000, the 50 k config): ONE WARP PER CHECK, eight independent checks per SM. No block
+// barriers, no idle warps while one lane solves the force system; windows up to 540 edges keep their state in shared memory, longer
+// ones stream it from L2 / HBM in coalesced step tiles through a cp.async ring (TileFeed) and write trial states to a second buffer
+// (no backup, no rollback pass). Measured against the CTA-per-check table on the M3500 sample (profiles/r02_ab_*): 1.73x for
+// 320 < L <= 540, +16 % / +4 % / +33 % for 1300-2000 / 2000-2600 / 2600-3499, +24 % on the whole list. Windows beyond 5400 edges keep
+// 256 threads per check (one check per SM) on the same streamed layout. The three middle rows share one shape: the split only evens
+// out the tail of the dynamic work claim (longest windows first within a launch).
+const Bucket kBuckets2U[NB] = {{96, 32, 0, 16}, {540, 32, 0, 8}, {1500, 32, 1, 8}, {2600, 32, 1, 8}, {5400, 32, 1, 8}, {1 << 30, 256, 1, 1}};
+
 // MODE 2 (option stage_odom = 1, uniform-information graphs): + 24 B / vertex for the odometry window staged by cp.async.bulk: the
 // same CTAs per SM hold shorter windows (measured A/B in profiles/)
 const Bucket kBuckets2S[NB] = {{96, 32, 2, 16}, {320, 64, 2, 8}, {1100, 128, 2, 3}, {1700, 128, 2, 2}, {3500, 256, 2, 1}, {1 << 30, 256, 1, 1}};
 
 // SE(3): 7 doubles of state per vertex, 256 resident threads per SM (the 27 running prefix values need the registers)
 const Bucket kBuckets3[NB] = {{96, 32, 0, 8}, {320, 64, 0, 4}, {800, 128, 0, 2}, {3700, 256, 0, 1}, {3701, 256, 0, 1}, {1 << 30, 256, 1, 1}};
-const Bucket* buckets_of(int dim) { return dim == 2 ? kBuckets2 : kBuckets3; }
+const Bucket* buckets_of(int dim, bool uni = false) { return dim == 2 ? (uni ? kBuckets2U : kBuckets2) : kBuckets3; }
 
 
 }  // namespace
@@ -241,7 +250,7 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     CUDA_TRY(cudaMalloc(&h->d_counts, sizeof(int) * 2 * NB));
     CUDA_TRY(cudaMalloc(&h->d_bucket_cap, sizeof(int) * NB));
     CUDA_TRY(cudaMalloc(&h->d_stats, sizeof(unsigned long long) * 2));
-    for (int b = 0; b < NB; ++b) h->buckets[b] = buckets_of(dim)[b];
+    for (int b = 0; b < NB; ++b) h->buckets[b] = buckets_of(dim, dim == 2 && h->hs.uniform_iso && h->use_uniform && h->d_odom3)[b];
     { int rc2 = size_scratch(h); if (rc2 != IPC_OK) return rc2; }
     CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     {   // IPC::IPC: vertex 0 at the origin, everything else dead-reckoned (propagateGuess, src/consensus_utils.cpp:98-116)
@@ -303,11 +312,25 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
     }
     if (!strcmp(name, "stage_odom")) {     // 1: odometry window staged in shared memory by one bulk copy per check (MODE 2 kernels)
         if (value != 0 && !(h->dim == 2 && h->hs.uniform_iso && h->d_odom3)) return fail(IPC_ERR_UNSUPPORTED, "stage_odom needs an SE(2) graph with uniform isotropic odometry information");
-        for (int b = 0; b < NB; ++b) h->buckets[b] = (value != 0 ? kBuckets2S : kBuckets2)[b];
+        for (int b = 0; b < NB; ++b) h->buckets[b] = (value != 0 ? kBuckets2S : buckets_of(2, h->use_uniform))[b];
         CUDA_TRY(cudaSetDevice(h->device));
         return size_scratch(h);
     }
-    if (!strcmp(name, "use_uniform")) { h->use_uniform = value != 0; return IPC_OK; }
+    if (!strcmp(name, "use_uniform")) {      // 0: general-information kernels (72-byte records) and their CTA-per-check launch table
+        h->use_uniform = value != 0;
+        if (h->dim == 2) {
+            for (int b = 0; b < NB; ++b) h->buckets[b] = buckets_of(2, h->hs.uniform_iso && h->use_uniform && h->d_odom3)[b];
+            CUDA_TRY(cudaSetDevice(h->device));
+            return size_scratch(h);
+        }
+        return IPC_OK;
+    }
+    if (!strcmp(name, "cta_per_check")) {    // 1: the CTA-per-check launch table (state in shared memory) on a uniform-information graph too (A/B runs)
+        if (h->dim != 2) return fail(IPC_ERR_UNSUPPORTED, "cta_per_check: SE(2) only");
+        for (int b = 0; b < NB; ++b) h->buckets[b] = buckets_of(2, value == 0 && h->hs.uniform_iso && h->use_uniform && h->d_odom3)[b];
+        CUDA_TRY(cudaSetDevice(h->device));
+        return size_scratch(h);
+    }
     if (!strcmp(name, "speculate")) { h->speculate = value != 0; return IPC_OK; }
     if (!strcmp(name, "early_accept")) { h->early_accept = value != 0; return IPC_OK; }
     if (!strcmp(name, "max_tries")) { h->max_tries = (int)value; return IPC_OK; }

@@ -23,7 +23,7 @@ struct Bucket { int cap; int nt; int mode; int minb; };   // minb: CTAs per SM t
 
 inline size_t smem_bytes(int mode, int cap, int dim = 2, int nt = 0) {
     size_t capv = std::max(cap + 2, nt);
-    size_t n = dim == 2 ? CHAIN_SMALL_DOUBLES + (mode != 1 ? (size_t)CHAIN_STATE_ARRAYS * capv : 0) + (mode == 2 ? (size_t)stage_doubles((int)capv) + 2 : 0)
+    size_t n = dim == 2 ? CHAIN_SMALL_DOUBLES + (mode != 1 ? (size_t)CHAIN_STATE_ARRAYS * capv : (size_t)ring_doubles(nt > 0 ? nt : 512)) + (mode == 2 ? (size_t)stage_doubles((int)capv) + 2 : 0)
                         : se3::CHAIN3_SMALL_DOUBLES + (mode == 0 ? (size_t)se3::CHAIN3_STATE * capv : 0);
     return n * sizeof(double);
 }
@@ -32,7 +32,7 @@ inline size_t scratch_doubles_per_cta(int mode, int cap, int dim = 2, int nt = 0
     // SE(2): the scratch is indexed by slot (vslot, chain_se2.cuh): up to capv + 2 nt + 2 records; nt = 0 sizes for the widest CTA
     if (mode == 1) nt = 512;                        // global-state kernels: sized for the widest CTA (32 .. 512 threads, launch_se2_variant)
     const size_t capg = capv + 2 * (size_t)(nt > 0 ? nt : 512) + 2;
-    return dim == 2 ? (size_t)CHAIN_SCRATCH_ARRAYS * capg + (mode == 1 ? (size_t)global_state_doubles((int)capv, 512) : 0)
+    return dim == 2 ? (size_t)CHAIN_SCRATCH_ARRAYS * capg + (mode == 1 ? 2 * (size_t)global_state_doubles((int)capv, 512) : 0)
                     : (size_t)(se3::CHAIN3_SCRATCH + (mode == 1 ? se3::CHAIN3_STATE : 0)) * capv;
 }
 // the instantiated (threads, CTAs per SM) variants of the SE(2) kernel, and the SE(3) variants by thread count

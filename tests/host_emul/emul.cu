@@ -37,9 +37,10 @@ static void cta_group(int n_poses, const double* odom, const double* Du, const d
                       const int* cand, const CheckParams& prm, bool want_info, std::atomic<int>& next, Out&& out) {
     const int capv = n_poses + 2, capg = scratch_slots<NT>(capv);
     const size_t st_doubles = std::max((size_t)CHAIN_STATE_ARRAYS * capv, (size_t)global_state_doubles(capv, NT));
-    std::vector<double> buf(st_doubles + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
+    std::vector<double> buf(2 * st_doubles + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
     ChainMem M; double* p = buf.data();
-    M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + st_doubles; M.capv = capv; M.capg = capg;
+    M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + 2 * st_doubles; M.capv = capv; M.capg = capg;
+    M.stw = g_gst ? M.st + st_doubles : M.st; M.ring = nullptr;
     SpinBarrier bar; bar.n = NT;
     const bool gst = g_gst != 0;
     int cur = 0;
@@ -104,9 +105,10 @@ template <class PT> static int emul_impl(int n_poses, const double* odom_meas, c
         const int capv = n_poses + 2;
         const int capg = scratch_slots<1>(capv);
         const size_t st_doubles = std::max((size_t)CHAIN_STATE_ARRAYS * capv, (size_t)global_state_doubles(capv, 1));
-        std::vector<double> buf(st_doubles + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
+        std::vector<double> buf(2 * st_doubles + (size_t)CHAIN_SCRATCH_ARRAYS * capg + CHAIN_SMALL_DOUBLES, 0.0);
         ChainMem M; double* p = buf.data();
-        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + st_doubles; M.capv = capv; M.capg = capg;
+        M.small = p; M.st = p + CHAIN_SMALL_DOUBLES; M.scr = M.st + 2 * st_doubles; M.capv = capv; M.capg = capg;
+        M.stw = g_gst ? M.st + st_doubles : M.st; M.ring = nullptr;
         const bool gst = g_gst != 0;
         for (;;) {
             int c = next.fetch_add(1);
