@@ -186,15 +186,32 @@ def run_reference(args):
 
 
 def traffic_capture():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this command (profiles/)."""
-    for name in ("r02_traffic_capture.json", "r01_traffic_capture.json"):
-        path = os.path.join(ROOT, "profiles", name)
-        try:
-            with open(path) as f:
-                return json.load(f)
-        except (OSError, ValueError):
-            continue
-    return None
+    """ncu launch metrics of THIS command's own first step (profiles/r02_bench_launch_traffic.json, made by scripts/make_traffic_json.py
+    from `ncu --metrics ... -k regex:chain_check python bench.py --steps 1 --warmup 0`): DRAM bytes and fp64 instruction counts of every
+    chain_check launch of one step of the default workload. The counts are properties of the step (same list, same kernels), the
+    durations under ncu are not used."""
+    path = os.path.join(ROOT, "profiles", "r02_bench_launch_traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return None
+
+
+def gpu_stream_leg(g, cfg, n_prefix: int):
+    """The reference-native workload (src/simulation.cpp:34-47): the sequential agreementCheck stream through ipc_agreement_check_stream,
+    (a) on the same time-ordered prefix the single-threaded oracle managed in its budget, (b) on the whole candidate list."""
+    from ipc_b200 import api
+    o = g.time_order()
+    res = {}
+    for key, sel in (("prefix", o[:n_prefix]), ("full", o)):
+        ipc = api.IPC.from_graph(g, cfg, candidates=False)
+        t = time.perf_counter()
+        acc, _ = ipc.agreementCheckStream(g.loop_from[sel], g.loop_to[sel], g.loop_meas[sel], g.loop_info[sel])
+        dt = time.perf_counter() - t
+        ipc.close()
+        res[key] = (len(sel) / dt, len(sel), dt, int(np.asarray(acc).sum()))
+    return res
 
 
 def run_ours(args):
@@ -332,6 +349,8 @@ def run_ours(args):
         alg_bytes = B_ODOM[g.dim] * sum_L + B_LOOP[g.dim] * sum_K + n / 8.0
         k_ms = float(np.mean(kern_ms)) if kern_ms else float(np.mean(step_ms))
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        cap = traffic_capture() if (world == 1 and args.config == "m3500" and args.checks == 0 and args.noise_exit == 1) else None
+        traffic = float(cap["dram_bytes_read"] + cap["dram_bytes_write"]) if cap else None
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic",
@@ -343,10 +362,17 @@ def run_ours(args):
                        "matches_device_resident": same,
                        "note": "ipc_check_batch_sharded with pinned host buffers: H2D of every rank's shard, kernels, all-gather, D2H of all verdict words on every rank"},
                "gpu_launches": n_launch * n_batches,
-               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                             "peak_source": peak_src, "algorithmic_bytes_per_launch_set": alg_bytes, "kernel_ms": k_ms, "scope": "rank 0's shard on one GPU",
-                            "traffic_capture": traffic_capture(),
-                            "note": "working set is L2-resident; the kernel is fp64-pipe / latency bound, not HBM bound (DESIGN.md)"},
+                            "traffic_source": (cap or {}).get("source"),
+                            "dram_throughput_GBs": (traffic / (k_ms * 1e-3) / 1e9) if traffic else None,
+                            "note": "algorithmic bytes charge every check ONE read of its chain; a check makes ~118 passes over it and the chain never leaves "
+                                    "L1/L2, so the contracted fraction is tiny by construction. `traffic` = measured DRAM bytes of the chain_check launches of one "
+                                    "step (ncu on this command): the per-check window state (2 x 40 B x L, eight checks per SM) streams through HBM (DESIGN.md 4)"},
+               "roofline_fp64": ({"bound": "fp64", "achieved": cap["fp64_flops"] / (k_ms * 1e-3) / 1e12, "peak": 148 * 64 * 2 * 1.965e9 / 1e12, "unit": "TFLOP/s",
+                                  "frac": cap["fp64_flops"] / (k_ms * 1e-3) / (148 * 64 * 2 * 1.965e9),
+                                  "note": "2 x DFMA + DADD + DMUL thread instructions of one step (ncu, profiles/) / the live kernel time; peak = 148 SM x 64 "
+                                          "fp64 lanes x 2 x 1.965 GHz"} if cap else None),
                "verdict_only_early_accept": {"value": ea_value, "unit": UNIT, "verdict_bits_identical": ea_same,
                                              "note": "same verdict bits, checks stop once sum chi2 <= threshold; not the headline"},
                "clocks": clk.summary(), "wall_s_timed_region": t_wall}
@@ -367,6 +393,13 @@ def run_ours(args):
                 sv, sn, sdt = stream_leg(g, cfg, args.stream_seconds)
                 out["stream_cpu_B1"] = {"value": sv, "unit": "agreementCheck calls/s", "cores": 1, "kind": "port",
                                         "sample": f"first {sn} time-ordered candidates of the sequential stream, {sdt:.1f} s (BASELINE.md row B1)"}
+                if world == 1:
+                    gs = gpu_stream_leg(g, cfg, sn)
+                    out["stream"] = {"unit": "agreementCheck calls/s", "what": "the reference-native workload (src/simulation.cpp:34-47): sequential, stateful, "
+                                     "clusters of K >> 2 loops; persistent cooperative kernel per check, speculative candidates (DESIGN.md 5c)",
+                                     "gpu_value_same_prefix": gs["prefix"][0], "cpu_B1_value": sv, "prefix_candidates": sn,
+                                     "gpu_value_full_stream": gs["full"][0], "full_stream_candidates": gs["full"][1], "full_stream_s": gs["full"][2],
+                                     "accepted_full_stream": gs["full"][3]}
         sys.stdout.flush()
         os.dup2(_saved_fd1, 1)
         print(json.dumps(out), flush=True)
@@ -389,7 +422,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernel-timing", action="store_true")
     ap.add_argument("--no-full-retries", action="store_true", help="skip the g2o-verbatim (noise_exit = 0) side measurement")
-    ap.add_argument("--stream-seconds", type=float, default=0.0, help="also time the single-threaded sequential stream (oracle) for this long")
+    ap.add_argument("--stream-seconds", type=float, default=5.0,
+                    help="N = 1: also time the sequential stream — single-threaded oracle for this long (BASELINE.md row B1), then the GPU stream on "
+                         "the same prefix and on the whole list (0 = skip)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("bench.py: warning: fewer than 3 warm-up steps", file=sys.stderr)
