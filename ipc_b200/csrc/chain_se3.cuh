@@ -338,16 +338,29 @@ template <int NT, int NS> struct ScanSumMax3 {
 // ---- per-check working set ------------------------------------------------------------------------------------------
 struct StepSpec3 { double z[3][6]; double C[3][6]; double model; double gain_loops; int rs, re; };
 struct CheckGeom3 { int K, lo, L, rs, re, first_is_c, last_is_c, c_a_is_rs, c_b_is_L, m_a_is_rs, m_b_is_L; };
-struct UniBlock3 { LoopRec3 Lc, Lm; StepSpec3 sol; double n_c, n_m; CheckGeom3 g; };
+struct UniBlock3 { LoopRec3 Lc, Lm; StepSpec3 sol; double n_c, n_m; CheckGeom3 g;
+                   double lt[2][32];        // per loop (candidate, member), staged by lanes 0 / 1 of warp 0: prefix terms t (27), chi2, sigma, gain part
+                   double zs[12]; };        // forces (zc, zm) of the last solve
 constexpr int RED3_DOUBLES = 16 * (NP3 + 4);
 constexpr int UNI3_DOUBLES = (sizeof(UniBlock3) + 7) / 8;
 constexpr int CHAIN3_SMALL_DOUBLES = 2 * RED3_DOUBLES + 2 * NSPEC * SPECW3 + UNI3_DOUBLES + 16 * 7 + 32 * 7;   // + dead-reckoning staging
 constexpr int CHAIN3_STATE = 7;      // per-vertex doubles of state: t (3), q (4)
 constexpr int CHAIN3_SCRATCH = 7 + 12;   // per-vertex doubles of global scratch: backup (7), b (6), h_gn (6)
+IPC_HD constexpr int global_state3_doubles(int capv, int nt) { return 7 * (capv + 4 * nt); }   // step tiles: (S + 1) * 7 * NT <= 7 (L + 3 NT)
 
+// State record of a vertex (t, q: 7 doubles). Shared-memory state (gst = 0): AoS by vertex, components 1 double apart. Global-memory state
+// (gst = 1: the one-warp-per-check kernels): tiles of 7 x nt doubles by STEP as in chain_se2.cuh (StateAt) — the vertex thread t reaches at
+// step i of its segment walk is element t of tile i + 1, components nt doubles apart, tile 0 holds the fixed origin — so every access of a
+// warp is one contiguous run; a trial sweep writes its new poses to the second buffer stw (accepted: swap; rejected: nothing to undo).
 struct ChainMem3 {
     double* st; double* scr; double* small; int capv;
-    IPC_HD double* P(int j) const { return st + 7 * j; }
+    double* stw;             // == st for shared-memory state
+    int gst, nt, S, cs;      // layout: global tiles?, threads, segment length (vertices per thread), component stride
+    IPC_HD size_t tile_off(int j) const { if (j == 0) return 0; const int t = (j - 1) / S, i = (j - 1) - t * S; return ((size_t)(i + 1) * 7) * nt + t; }
+    IPC_HD double* P(int j) const { return gst ? st + tile_off(j) : st + 7 * j; }
+    IPC_HD double* PW(int j) const { return gst ? stw + tile_off(j) : stw + 7 * j; }
+    IPC_HD double* Pit(int j, int i, int t) const { return gst ? st + ((size_t)(i + 1) * 7) * nt + t : st + 7 * j; }        // vertex j = k0(t) + 1 + i
+    IPC_HD double* PWit(int j, int i, int t) const { return gst ? stw + ((size_t)(i + 1) * 7) * nt + t : stw + 7 * j; }
     IPC_HD double* B(int j) const { return scr + 7 * j; }
     IPC_HD double* G(int j) const { return scr + 7 * (size_t)capv + 12 * j; }
     IPC_HD double* red() const { return small; }
@@ -355,8 +368,8 @@ struct ChainMem3 {
     IPC_HD UniBlock3* U() const { return reinterpret_cast<UniBlock3*>(small + 2 * RED3_DOUBLES + 2 * NSPEC * SPECW3); }
     IPC_HD double* stage() const { return small + 2 * RED3_DOUBLES + 2 * NSPEC * SPECW3 + UNI3_DOUBLES; }
 };
-IPC_HD void load_pose(const double* p, P3& o) { o.t[0] = p[0]; o.t[1] = p[1]; o.t[2] = p[2]; o.q[0] = p[3]; o.q[1] = p[4]; o.q[2] = p[5]; o.q[3] = p[6]; }
-IPC_HD void store_pose(double* p, const P3& o) { p[0] = o.t[0]; p[1] = o.t[1]; p[2] = o.t[2]; p[3] = o.q[0]; p[4] = o.q[1]; p[5] = o.q[2]; p[6] = o.q[3]; }
+IPC_HD void load_pose(const double* p, P3& o, int cs = 1) { o.t[0] = p[0]; o.t[1] = p[cs]; o.t[2] = p[2 * cs]; o.q[0] = p[3 * cs]; o.q[1] = p[4 * cs]; o.q[2] = p[5 * cs]; o.q[3] = p[6 * cs]; }
+IPC_HD void store_pose(double* p, const P3& o, int cs = 1) { p[0] = o.t[0]; p[cs] = o.t[1]; p[2 * cs] = o.t[2]; p[3 * cs] = o.q[0]; p[4 * cs] = o.q[1]; p[5 * cs] = o.q[2]; p[6 * cs] = o.q[3]; }
 
 struct ThreadState3 { int k0, k1; P3 pa; double base[NP3]; };
 
@@ -384,7 +397,7 @@ struct SweepOut3 { double chi, mx, hh, gain; };
 // edge, keeping both running prefixes alive in one loop spills hundreds of bytes per thread even at 255 registers.
 template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int mode, double c1, double c2, bool acc_gain, ThreadState3& ts, SweepOut3& out,
                                      int& buf, const int* spec_v) {
-    const int k0 = ts.k0, k1 = ts.k1;
+    const int k0 = ts.k0, k1 = ts.k1, tid_ = hd_tid();
     const StepSpec3* sp = &M.U()->sol;
     double* spec = M.spec() + (size_t)buf * NSPEC * SPECW3;
     double hh = 0, gain = 0;
@@ -404,7 +417,7 @@ template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int
         for (int k = k0; k < k1; ++k) {
             const int j = k + 1;
             const double* rec = odom + (size_t)ODOM_REC3 * k;
-            P3 ob; load_pose(M.P(j), ob);
+            P3 ob; load_pose(M.Pit(j, k - k0, tid_), ob, M.cs);
             double u[6];
             if (mode == STEP_GN) {
                 Lin3 eo; lin3(rec, oa, ob, rec + 7, eo);
@@ -417,11 +430,11 @@ template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int
             } else { const double* gq = M.G(j);
 #pragma unroll
                 for (int q = 0; q < 6; ++q) u[q] = c1 * gq[q] + c2 * gq[6 + q]; }
-            store_pose(M.B(j), ob);
+            if (!M.gst) store_pose(M.B(j), ob);
             P3 nb; oplus3(ob, u, nb);
 #pragma unroll
             for (int q = 0; q < 6; ++q) hh += u[q] * u[q];
-            store_pose(M.P(j), nb);
+            store_pose(M.PWit(j, k - k0, tid_), nb, M.cs);
             oa = ob;
         }
     }
@@ -437,7 +450,7 @@ template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int
         for (int k = k0; k < k1; ++k) {
             const int j = k + 1;
             const double* rec = odom + (size_t)ODOM_REC3 * k;
-            P3 nb; load_pose(M.P(j), nb);
+            P3 nb; load_pose(mode != STEP_NONE ? M.PWit(j, k - k0, tid_) : M.Pit(j, k - k0, tid_), nb, M.cs);
             Lin3 e; lin3(rec, na, nb, rec + 7, e);
             double t[NP3]; edge_terms3(e, rec + 7 + NS6, t);
             chi += e.chi; mx = fmax(mx, e.chi);
@@ -471,11 +484,11 @@ template <int NT> IPC_HD void sweep3(const ChainMem3& M, const double* odom, int
 }
 
 template <int NT> IPC_HD void rollback3(const ChainMem3& M, ThreadState3& ts) {
-    for (int k = ts.k0; k < ts.k1; ++k) { const int j = k + 1; const double* b = M.B(j); double* p = M.P(j);
+    if (!M.gst) for (int k = ts.k0; k < ts.k1; ++k) { const int j = k + 1; const double* b = M.B(j); double* p = M.P(j);
 #pragma unroll
         for (int q = 0; q < 7; ++q) p[q] = b[q]; }
     bsync<NT>();
-    if (ts.k0 < ts.k1 && ts.k0 > 0) load_pose(M.P(ts.k0), ts.pa);
+    if (ts.k0 < ts.k1 && ts.k0 > 0) load_pose(M.P(ts.k0), ts.pa, M.cs);
     bsync<NT>();
 }
 
@@ -565,8 +578,152 @@ IPC_HD_COLD void eval_and_solve3_t0(ChainMem3 M, int buf, double odom_chi, doubl
         sp->gain_loops = gl + g2;
     }
 }
+#ifdef __CUDA_ARCH__
+// Device form of eval_and_solve3_t0, executed by the 32 lanes of warp 0 (the CTA-per-check kernels spent 55 % of their warp samples at the
+// barrier behind the one-thread version, ncu profiles/r02_ncu_se3.txt): lanes 0 / 1 linearise the candidate / member loop, lane r owns row r
+// of the augmented 6K x (6K + 1) force system (assembled from the special-vertex table in shared memory) and the SPD system is solved by
+// Gaussian elimination with the pivot row broadcast by shuffles (no pivoting needed: SPD), then lanes 0..5 form z / C component-wise.
+template <int N> __device__ __forceinline__ double warp_spd_solve(double (&a)[13], int lane) {
+    // elimination: after step p, rows r > p have a zero in column p
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+        const double piv = __shfl_sync(0xffffffffu, a[p], p);
+        const double f = (lane > p && lane < N) ? a[p] / piv : 0.0;
+#pragma unroll
+        for (int c = p + 1; c <= N; ++c) {
+            const double pc = __shfl_sync(0xffffffffu, a[c == N ? 12 : c], p);
+            a[c == N ? 12 : c] = fma(-f, pc, a[c == N ? 12 : c]);
+        }
+    }
+    // back substitution: lane p produces x_p once x_{p+1..N-1} are known
+    double x = 0.0;
+#pragma unroll
+    for (int p = N - 1; p >= 0; --p) {
+        const double xp = __shfl_sync(0xffffffffu, a[12] / a[p], p);      // lane p: (rhs - sum_{c>p} a[c] x_c) / a[p], the sum already folded into a[12]
+        if (lane == p) x = xp;
+        if (lane < p) a[12] = fma(-a[p], xp, a[12]);
+    }
+    return x;
+}
+__device__ __noinline__ void eval_and_solve3_w0(ChainMem3 M, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
+    UniBlock3* U = M.U();
+    const CheckGeom3& g = U->g;
+    const int lane = threadIdx.x & 31;
+    const double* spec = M.spec() + (size_t)(buf ^ 1) * NSPEC * SPECW3;
+    const double* o1 = spec + 1 * SPECW3; const double* o2 = spec + 2 * SPECW3; const double* o3 = spec + 3 * SPECW3;
+    const bool z1 = g.rs == 0;
+    // ---- lanes 0 / 1: the loop edges at the published state
+    Lin3 le;
+    const LoopRec3& Lp = lane == 0 ? U->Lc : U->Lm;
+    double sigma = 0;
+    if (lane < g.K) {
+        P3 org; org.t[0] = org.t[1] = org.t[2] = 0; org.q[0] = 1; org.q[1] = org.q[2] = org.q[3] = 0;
+        P3 p1 = org, p2, p3;
+        if (!z1) load_pose(o1 + NP3, p1);
+        load_pose(o2 + NP3, p2); load_pose(o3 + NP3, p3);
+        const bool a_is_rs = lane == 0 ? g.c_a_is_rs : g.m_a_is_rs, b_is_L = lane == 0 ? g.c_b_is_L : g.m_b_is_L;
+        const P3& pa = a_is_rs ? p1 : org; const P3& pb = b_is_L ? p3 : p2;
+        const bool to_hi = Lp.to > Lp.from;
+        lin3(Lp.zinv, to_hi ? pa : pb, to_hi ? pb : pa, Lp.Om, le);
+        double t[NP3]; edge_terms3(le, Lp.V, t);
+        sigma = to_hi ? 1.0 : -1.0;
+        double* o = U->lt[lane];
+#pragma unroll
+        for (int q = 0; q < NP3; ++q) o[q] = t[q];
+        o[27] = le.chi; o[28] = sigma;
+    }
+    __syncwarp();
+    const double* tc = U->lt[0]; const double* tm = U->lt[1];
+    const double c = tc[27], m = g.K == 2 ? tm[27] : 0.0;
+    if (fabs(linearGain) < 1e-12) linearGain = 1e-12;
+    const double rho = (cur_chi - (odom_chi + c + m)) / linearGain;
+    if (lane == 0) { U->n_c = c; U->n_m = m; }
+    if (!(force || rho > 0)) return;
+    // ---- GN solve: (P_ll' + delta W_l) z_l' = q_l + sigma_l Q_l e_l; lane r assembles row r (region sums read on the fly:
+    //      acc0 = pre1 (0 when rs == 0), acc1 = pre2 - pre1, acc2 = pre3 - pre2)
+    StepSpec3* sp = &U->sol;
+    auto A0 = [&](int q) { return z1 ? 0.0 : o1[q]; };
+    auto A1 = [&](int q) { return o2[q] - (z1 ? 0.0 : o1[q]); };
+    auto A2 = [&](int q) { return o3[q] - o2[q]; };
+    double a[13];
+#pragma unroll
+    for (int q = 0; q < 13; ++q) a[q] = 0.0;
+    const int i6 = lane % 6, blk = lane / 6;
+    double x;
+    if (g.K == 1) {
+        if (lane < 6) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { const int sx = sidx(i6, j); a[j] = A1(sx) + tc[sx]; }
+            a[12] = A1(NS6 + i6) - tc[28] * tc[NS6 + i6];
+        }
+        x = warp_spd_solve<6>(a, lane);
+    } else {
+        if (lane < 12) {
+            const bool fc = g.first_is_c != 0, lc_ = g.last_is_c != 0;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int sx = sidx(i6, j);
+                const double a0 = A0(sx), a1 = A1(sx), a2 = A2(sx);
+                const double pcc = a1 + (fc ? a0 : 0.0) + (lc_ ? a2 : 0.0) + tc[sx];
+                const double pmm = a1 + (fc ? 0.0 : a0) + (lc_ ? 0.0 : a2) + tm[sx];
+                a[j] = blk == 0 ? pcc : a1;
+                a[6 + j] = blk == 0 ? a1 : pmm;
+            }
+            const double r0 = A0(NS6 + i6), r1 = A1(NS6 + i6), r2 = A2(NS6 + i6);
+            a[12] = blk == 0 ? r1 + (fc ? r0 : 0.0) + (lc_ ? r2 : 0.0) - tc[28] * tc[NS6 + i6]
+                             : r1 + (fc ? 0.0 : r0) + (lc_ ? 0.0 : r2) - tm[28] * tm[NS6 + i6];
+        }
+        x = warp_spd_solve<12>(a, lane);
+    }
+    if (lane < 12) U->zs[lane] = (lane < 6 * g.K) ? x : 0.0;
+    __syncwarp();
+    const double* zc = U->zs; const double* zm = U->zs + 6;
+    if (lane == 0) { sp->rs = g.rs; sp->re = g.re; }
+    if (lane < 6) {     // component `lane` of z / C of the three regions
+        const int q = lane;
+        auto zreg = [&](int r, int p) { return g.K == 1 ? (r == 1 ? zc[p] : 0.0) : (r == 0 ? (g.first_is_c ? zc[p] : zm[p]) : (r == 1 ? zc[p] + zm[p] : (g.last_is_c ? zc[p] : zm[p]))); };
+        double c1 = 0, c2 = 0;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+            const int sx = sidx(q, p);
+            c1 += A0(sx) * (zreg(0, p) - zreg(1, p));                 // C_1 = PM(rs) (z_0 - z_1)
+            c2 += o2[sx] * (zreg(1, p) - zreg(2, p));                 // C_2 = C_1 + PM(re) (z_1 - z_2)
+        }
+        sp->z[0][q] = zreg(0, q); sp->z[1][q] = zreg(1, q); sp->z[2][q] = zreg(2, q);
+        sp->C[0][q] = 0; sp->C[1][q] = c1; sp->C[2][q] = c1 + c2;
+    }
+    __syncwarp();
+    // model value: lanes 0..4 take one quadratic form each (loop c, loop m, regions 0..2), summed by shuffles
+    double mq = 0;
+    if (lane < 5) {
+        double zz[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) zz[p] = lane == 0 ? zc[p] : (lane == 1 ? zm[p] : sp->z[lane - 2][p]);
+        if (!(lane == 1 && g.K == 1)) {
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+                double y = 0;
+#pragma unroll
+                for (int p = 0; p < 6; ++p) { const int sx = sidx(r, p); y += (lane == 0 ? tc[sx] : lane == 1 ? tm[sx] : lane == 2 ? A0(sx) : lane == 3 ? A1(sx) : A2(sx)) * zz[p]; }
+                mq += zz[r] * y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) mq += __shfl_down_sync(0xffffffffu, mq, o, 8);
+    // loop part of the predicted gain: lanes 0 / 1 again (their linearisation is still in registers)
+    double gl = 0;
+    if (lane < g.K) { double tt[NP3]; edge_terms3(le, Lp.V, tt, lane == 0 ? zc : zm, Lp.Om, sigma, &gl); }
+    gl += __shfl_down_sync(0xffffffffu, gl, 1);
+    if (lane == 0) { sp->model = mq; sp->gain_loops = gl; }
+}
+#endif
 template <int NT> IPC_HD void eval_and_solve3(const ChainMem3& M, int buf, double odom_chi, double cur_chi, double linearGain, bool force, double& n_c, double& n_m) {
+#ifdef __CUDA_ARCH__
+    if (threadIdx.x < 32) eval_and_solve3_w0(M, buf, odom_chi, cur_chi, linearGain, force);
+#else
     if (hd_tid() == 0) eval_and_solve3_t0(M, buf, odom_chi, cur_chi, linearGain, force);
+#endif
     bsync<NT>();
     n_c = M.U()->n_c; n_m = M.U()->n_m;
 }
@@ -581,7 +738,7 @@ template <int NT> IPC_HD double gn_norm_sq3(const ChainMem3& M, const double* od
     for (int k = ts.k0; k < ts.k1; ++k) {
         const int j = k + 1;
         const double* rec = odom + (size_t)ODOM_REC3 * k;
-        P3 pb; load_pose(M.P(j), pb);
+        P3 pb; load_pose(M.Pit(j, k - ts.k0, hd_tid()), pb, M.cs);
         Lin3 e; lin3(rec, pa, pb, rec + 7, e);
         double t[NP3]; edge_terms3(e, rec + 7 + NS6, t);
 #pragma unroll
@@ -605,13 +762,13 @@ template <int NT> IPC_HD void sd_sweeps3(const ChainMem3& M, const double* odom,
     double gci[6], gcj[6], gmi[6] = {0, 0, 0, 0, 0, 0}, gmj[6] = {0, 0, 0, 0, 0, 0};
     double Jci[36], Jcj[36], Jmi[36], Jmj[36];
     {
-        P3 pf, pt; load_pose(M.P(cjf), pf); load_pose(M.P(cjt), pt);
+        P3 pf, pt; load_pose(M.P(cjf), pf, M.cs); load_pose(M.P(cjt), pt, M.cs);
         Lin3 e; lin3(Lc.zinv, pf, pt, Lc.Om, e); jac3(Lc.zinv, e, Jci, Jcj);
         m6t_vec(Jci, e.we, gci); m6t_vec(Jcj, e.we, gcj);
     }
     if (g.K == 2) {
         mjf = Lm.from - g.lo; mjt = Lm.to - g.lo;
-        P3 pf, pt; load_pose(M.P(mjf), pf); load_pose(M.P(mjt), pt);
+        P3 pf, pt; load_pose(M.P(mjf), pf, M.cs); load_pose(M.P(mjt), pt, M.cs);
         Lin3 e; lin3(Lm.zinv, pf, pt, Lm.Om, e); jac3(Lm.zinv, e, Jmi, Jmj);
         m6t_vec(Jmi, e.we, gmi); m6t_vec(Jmj, e.we, gmj);
     }
@@ -640,7 +797,7 @@ template <int NT> IPC_HD void sd_sweeps3(const ChainMem3& M, const double* odom,
         double gprev[6] = {0, 0, 0, 0, 0, 0};
         for (int k = k0; k <= k1 && k < L; ++k) {
             const double* rec = odom + (size_t)ODOM_REC3 * k;
-            P3 pb; load_pose(M.P(k + 1), pb);
+            P3 pb; load_pose(k < k1 ? M.Pit(k + 1, k - k0, hd_tid()) : M.P(k + 1), pb, M.cs);
             Lin3 e; lin3(rec, pa, pb, rec + 7, e);
             double Ji[36], Jj[36]; jac3(rec, e, Ji, Jj);
             double gi[6], gj[6]; m6t_vec(Ji, e.we, gi); m6t_vec(Jj, e.we, gj);
@@ -674,7 +831,7 @@ template <int NT> IPC_HD void sd_sweeps3(const ChainMem3& M, const double* odom,
           for (int q = 0; q < 6; ++q) ba[q] = gq[q]; }
         for (int k = k0; k < k1; ++k) {
             const double* rec = odom + (size_t)ODOM_REC3 * k;
-            P3 pb; load_pose(M.P(k + 1), pb);
+            P3 pb; load_pose(M.Pit(k + 1, k - k0, hd_tid()), pb, M.cs);
             Lin3 e; lin3(rec, pa, pb, rec + 7, e);
             double Ji[36], Jj[36]; jac3(rec, e, Ji, Jj);
             double bv[6]; { const double* gq = M.G(k + 1);
@@ -737,9 +894,10 @@ template <int NT> IPC_HD void se3_excl_scan(const ChainMem3& M, const P3& mine, 
 }
 
 // One SE(3) check. odom_all: AoS records of ODOM_REC3 doubles per odometry edge (global index).
-template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_all, const LoopRec3* Lc_in, const LoopRec3* Lm_in, const CheckParams& prm,
+template <int NT> IPC_HD void run_check3(const ChainMem3& M_in, const double* odom_all, const LoopRec3* Lc_in, const LoopRec3* Lm_in, const CheckParams& prm,
                                          bool want_info, CheckResult& res) {
     const int tid = hd_tid();
+    ChainMem3 M = M_in;                                     // st / stw swap when a trial is accepted (global-memory state); S is set below
     bsync<NT>();
     if (tid == 0) {
         UniBlock3* U = M.U();
@@ -779,6 +937,7 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
     int S = (L + NT - 1) / NT; if (S < 1) S = 1; S |= 1;
     ts.k0 = tid * S < L ? tid * S : L; ts.k1 = ts.k0 + S < L ? ts.k0 + S : L;
     const int k0 = ts.k0, k1 = ts.k1;
+    M.S = S; M.nt = NT; M.cs = M.gst ? NT : 1;
 
     // ---- dead-reckoning (propagateGuess): compose the measurements. Records hold Z^-1: Z = (Z^-1)^-1.
     {
@@ -789,13 +948,13 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
             P3 zz, r; se3_rel(zi, id, zz); se3_mul(mine, zz, r); mine = r;
         }
         P3 excl; se3_excl_scan<NT>(M, mine, excl);
-        if (tid == 0) store_pose(M.P(0), id);
+        if (tid == 0) { store_pose(M.P(0), id, M.cs); if (M.gst) store_pose(M.PW(0), id, M.cs); }
         ts.pa = excl;
         P3 cur = excl;
         for (int k = k0; k < k1; ++k) {
             P3 zi; load_pose(odom + (size_t)ODOM_REC3 * k, zi);
             P3 zz, r; se3_rel(zi, id, zz); se3_mul(cur, zz, r); q_normalize(r.q); cur = r;
-            store_pose(M.P(k + 1), cur);
+            store_pose(M.Pit(k + 1, k - k0, tid), cur, M.cs);
         }
 #pragma unroll
         for (int m = 0; m < NP3; ++m) ts.base[m] = 0;
@@ -846,6 +1005,7 @@ template <int NT> IPC_HD void run_check3(const ChainMem3& M, const double* odom_
             if (rho > 0.75) delta = fmax(delta, 3 * hdlNorm);
             else if (rho < 0.25) delta *= 0.5;
             if (rho > 0) {
+                if (M.gst) { double* t_ = M.st; M.st = M.stw; M.stw = t_; }     // the trial state becomes the state
                 cur_chi = newChi; cur_max = fmax(so.mx, fmax(n_c, n_m)); cand_chi = n_c;
                 gain_loops = M.U()->sol.gain_loops;
                 prev_hnorm = hdlNorm;

@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(NT, 256 / NT > 0 ? 256 / NT : 1) chain_check_s
     se3::ChainMem3 M;
     M.small = sm; M.scr = scr; M.capv = capv;
     M.st = (MODE == 0) ? sm + se3::CHAIN3_SMALL_DOUBLES : scr + (size_t)se3::CHAIN3_SCRATCH * capv;
+    M.gst = (MODE == 1); M.nt = NT; M.S = 1; M.cs = (MODE == 1) ? NT : 1;
+    M.stw = (MODE == 1) ? M.st + se3::global_state3_doubles(capv, NT) : M.st;
     const se3::LoopRec3* loops = static_cast<const se3::LoopRec3*>(A.loops);
     CheckParams prm{A.fast_th, A.slow_th, A.fast_iter, A.slow_iter, A.noise_eps, A.max_tries, A.speculate, A.early_accept, A.sd_fuse};
     const int n_work = *A.n_work;

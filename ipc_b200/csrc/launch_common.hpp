@@ -33,7 +33,7 @@ inline size_t scratch_doubles_per_cta(int mode, int cap, int dim = 2, int nt = 0
     if (mode == 1) nt = 512;                        // global-state kernels: sized for the widest CTA (32 .. 512 threads, launch_se2_variant)
     const size_t capg = capv + 2 * (size_t)(nt > 0 ? nt : 512) + 2;
     return dim == 2 ? (size_t)CHAIN_SCRATCH_ARRAYS * capg + (mode == 1 ? 2 * (size_t)global_state_doubles((int)capv, 512) : 0)
-                    : (size_t)(se3::CHAIN3_SCRATCH + (mode == 1 ? se3::CHAIN3_STATE : 0)) * capv;
+                    : (size_t)se3::CHAIN3_SCRATCH * capv + (mode == 1 ? 2 * (size_t)se3::global_state3_doubles((int)capv, 512) : 0);
 }
 // the instantiated (threads, CTAs per SM) variants of the SE(2) kernel, and the SE(3) variants by thread count
 int launch_se2_variant(int nt, int minb, int mode, const BatchArgs& a, int grid, cudaStream_t st, bool uni);

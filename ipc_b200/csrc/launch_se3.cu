@@ -21,7 +21,11 @@ template <int NT, int MODE> int launch_se3(const BatchArgs& a, int grid, cudaStr
     return IPC_OK;
 }
 int launch_se3_variant(int nt, int mode, const BatchArgs& a, int grid, cudaStream_t st) {
-    if (mode == 1) return launch_se3<256, 1>(a, grid, st);
+    if (mode == 1) {      // state in global memory (step tiles, second buffer)
+        if (nt == 32) return launch_se3<32, 1>(a, grid, st);
+        if (nt == 64) return launch_se3<64, 1>(a, grid, st);
+        return launch_se3<256, 1>(a, grid, st);
+    }
     if (nt == 32) return launch_se3<32, 0>(a, grid, st);
     if (nt == 64) return launch_se3<64, 0>(a, grid, st);
     if (nt == 128) return launch_se3<128, 0>(a, grid, st);

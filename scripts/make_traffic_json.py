@@ -15,12 +15,13 @@ for r in rows[start + 2:]:
         continue
     d.setdefault((int(r[idx["ID"]]), r[idx["Kernel Name"]], r[idx["Grid Size"]], r[idx["Block Size"]]), {})[r[idx["Metric Name"]]] = float(r[idx["Metric Value"]].replace(",", ""))
 launches = []
-seen = set()
+first = None
 for (i, name, grid, block), v in d.items():
     key = (name, grid, block)
-    if key in seen:          # the second step's launches start here
+    if first is None:
+        first = key
+    elif key == first:       # the next batch starts with the same shortest-window launch
         break
-    seen.add(key)
     fl = 2 * v["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"] + v["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"] + v["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"]
     launches.append({"kernel": name.replace("void ", "").replace("(BatchArgs)", ""), "grid": grid, "block": block, "ms_under_ncu": v["gpu__time_duration.sum"] / 1e6,
                      "dram_bytes_read": v.get("dram__bytes_read.sum", 0.0), "dram_bytes_write": v.get("dram__bytes_write.sum", 0.0), "fp64_flops": fl,

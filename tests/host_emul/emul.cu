@@ -144,9 +144,10 @@ static void cta_group3(int n_poses, const double* odom, const ipcb::se3::LoopRec
                        const CheckParams& prm, bool want_info, std::atomic<int>& next, Out&& out) {
     using namespace ipcb::se3;
     const int capv = std::max(n_poses + 2, NT);
-    std::vector<double> buf((size_t)(CHAIN3_STATE + CHAIN3_SCRATCH) * capv + CHAIN3_SMALL_DOUBLES, 0.0);
+    std::vector<double> buf(2 * (size_t)global_state3_doubles(capv, NT) + (size_t)CHAIN3_SCRATCH * capv + CHAIN3_SMALL_DOUBLES, 0.0);
     ChainMem3 M; double* p = buf.data();
-    M.small = p; M.st = p + CHAIN3_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN3_STATE * capv; M.capv = capv;
+    M.small = p; M.st = p + CHAIN3_SMALL_DOUBLES; M.scr = M.st + 2 * (size_t)global_state3_doubles(capv, NT); M.capv = capv;
+    M.gst = g_gst; M.nt = NT; M.S = 1; M.cs = g_gst ? NT : 1; M.stw = g_gst ? M.st + global_state3_doubles(capv, NT) : M.st;
     SpinBarrier bar; bar.n = NT;
     int cur = 0;
     auto body = [&](int tid) {
@@ -209,6 +210,7 @@ extern "C" int emul_check_batch3(int n_poses, const double* odom_meas, const dou
         std::vector<double> buf((size_t)(CHAIN3_STATE + CHAIN3_SCRATCH) * capv + CHAIN3_SMALL_DOUBLES, 0.0);
         ChainMem3 M; double* p = buf.data();
         M.small = p; M.st = p + CHAIN3_SMALL_DOUBLES; M.scr = M.st + (size_t)CHAIN3_STATE * capv; M.capv = capv;
+        M.gst = 0; M.nt = 1; M.S = 1; M.cs = 1; M.stw = M.st;
         for (;;) {
             int c = next.fetch_add(1);
             if (c >= n_checks) break;
