@@ -78,10 +78,11 @@ __global__ void shard_spread(const uint32_t* __restrict__ gathered, size_t wpr, 
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-// window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh). Every kernel is compiled for
-// 512 resident threads per SM (<= 128 registers): 16 x 32, 8 x 64, 4 x 128, 2 x 256 or 1 x 512 CTAs, so the serial part of
-// one check (capacitance solve by thread 0) overlaps with the sweeps of the CTAs sharing its SM. MODE 0 keeps 5 doubles per
-// vertex in shared memory; beyond 5400 edges the state moves to the global scratch (MODE 1).
+// Launch tables: window-length caps (edges), threads per CTA, memory mode (see chain_se2_kernel.cuh), CTAs per SM the variant is
+// compiled for. The edge loop needs ~245 registers, so the variants that matter hold 256 threads per SM (8 x 32, 4 x 64, 2 x 128,
+// 1 x 256); the 128-register variants (16 x 32, 8 x 64) only serve windows too short to matter. MODE 0 keeps 5 doubles per vertex in
+// shared memory, MODE 1 streams the state from global memory (step tiles + cp.async ring + second buffer), MODE 2 adds the staged odometry.
+// CTA-per-check table (general-information graphs; option cta_per_check):
 const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3}, {2600, 128, 0, 2}, {5400, 256, 0, 1}, {1 << 30, 256, 1, 1}};
 
 // Uniform-information SE(2) graphs (M3500, City10000, the 50 k config): ONE WARP PER CHECK, eight independent checks per SM. No block
