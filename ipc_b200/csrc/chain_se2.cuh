@@ -1207,7 +1207,10 @@ IPC_HD void gn_solve(const SpecVals& sv, const CheckGeom& g, const LoopNow& lc, 
 // After a sweep, warp 0: (phase 1) lane l linearises loop l at the published state and stages its terms in shared memory;
 // (phase 2) lane 0 decides whether the trial is kept (rho > 0, or `force`) and if so solves the new linearisation into
 // M.U()->sol, reading the interval sums straight from the special-vertex table. Everything is staged through shared memory
-// so this serial, latency-critical section keeps almost nothing in registers / local memory.
+// so this serial, latency-critical section keeps almost nothing in registers / local memory. (Round 2 A/B: spreading the 6x6 system
+// over six lanes — one row per lane, Gaussian elimination with shuffle broadcasts, as the SE(3) kernel does for its 12x12 system —
+// LOSES 18 % here (207 K -> 170 K checks/s): twelve fp64 divisions and shuffle round trips are slower than the two reciprocals of the
+// 3x3 block-Schur form that one lane runs with full ILP. profiles/r02_ab_log.txt.)
 IPC_HD_COLD void eval_and_solve_w0(ChainMem M, int buf, double odom_chi, double cur_chi, double linearGain, bool force) {
     UniBlock* U = M.U();
     const CheckGeom& g = U->g;
