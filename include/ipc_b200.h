@@ -172,7 +172,9 @@ int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsign
  * early_accept: 1 lets verdict-only batches stop as soon as sum chi2 <= threshold (same bits). stream_depth (1..8): candidates
  * ipc_agreement_check_stream solves side by side. speculate, use_uniform,
  * max_tries, sd_fuse (0 / 1 / 2: when the steepest-descent pass replaces the norm pass; results identical),
- * bucket<i>_cap / bucket<i>_nt / bucket<i>_minb (launch shapes, i = 0..4): tuning, see DESIGN.md. */
+ * bucket<i>_cap / bucket<i>_nt / bucket<i>_minb / bucket<i>_mode (launch shapes, i = 0..5; mode 0 = window state in shared memory,
+ * 1 = streamed from global memory, 2 = + staged odometry): tuning, see DESIGN.md 3. cta_per_check: 1 selects the CTA-per-check launch
+ * table (state in shared memory) on a uniform-information SE(2) graph instead of the default one-warp-per-check table. stage_odom. */
 int ipc_set_option(ipc_handle* h, const char* name, double value);
 
 #ifdef __cplusplus

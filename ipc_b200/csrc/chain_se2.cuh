@@ -1309,15 +1309,10 @@ IPC_HD_COLD void eval_and_solve_w0(ChainMem M, int buf, double odom_chi, double 
 #pragma unroll
         for (int q = 0; q < 3; ++q) { sp->C[0][q] = 0; sp->C[1][q] = c1v[q]; sp->C[2][q] = c1v[q] + c2v[q]; }
     }
-    {   // model value (cheap predicted gain = chi2 - model) and the loop part of the accurate gain
-        double model = quad3(tc, zc[0], zc[1], zc[2]);
-        if (g.K == 2) model += quad3(tm, zm[0], zm[1], zm[2]);
-        const double p1[6] = {P1(0), P1(1), P1(2), P1(3), P1(4), P1(5)};
-        double a1[6], a2[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) { a1[q] = o2[q] - p1[q]; a2[q] = o3[q] - o2[q]; }
-        model += quad3(p1, z0[0], z0[1], z0[2]) + quad3(a1, zz1[0], zz1[1], zz1[2]) + quad3(a2, z2[0], z2[1], z2[2]);
-        sp->model = model;
+    {   // the loop part of the predicted gain. (The model value chi2 - model, five more quadratic forms, is not evaluated here any more:
+        // nothing reads it in the SE(2) kernels since the gain is accumulated edge by edge, and this section is on the critical path of
+        // every sweep.)
+        sp->model = 0.0;
         double gl = 0;
         for (int l = 0; l < g.K; ++l) {   // residual change of loop l is sigma V Q^T z_l - d_l
             const double* o = U->lt[l];
