@@ -249,7 +249,9 @@ def test_launch_variants_and_global_state_mode(gpu_lib):
                  {"cta_per_check": 1, "bucket0_minb": 8, "bucket1_minb": 4, "bucket2_nt": 64, "bucket2_minb": 4},
                  {"cta_per_check": 1, "bucket0_cap": 4, "bucket1_cap": 4, "bucket2_cap": 4, "bucket3_cap": 4, "bucket4_cap": 4},   # 256 threads, global state
                  {"bucket1_cap": 96, "bucket2_nt": 64, "bucket2_minb": 4, "bucket3_nt": 64, "bucket3_minb": 4},                   # two warps per check, streamed state
-                 {"use_uniform": 0}, {"speculate": 0}):
+                 {"use_uniform": 0},
+                 {"use_uniform": 0, "bucket0_cap": 4, "bucket1_cap": 4, "bucket2_cap": 4, "bucket3_cap": 4, "bucket4_cap": 4},   # general records, streamed state
+                 {"speculate": 0}):
         ipc = gpu_lib.IPC.from_graph(g, cfg)
         for k, v in opts.items():
             ipc.set_option(k, v)

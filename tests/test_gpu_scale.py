@@ -94,6 +94,28 @@ def test_long_windows_match_oracle(gpu_lib, oracle_lib, name, n_checks):
     ipc.close()
 
 
+def test_m3500_full_size_streamed_windows_match_oracle(gpu_lib, oracle_lib):
+    """The default launch table on the FULL-SIZE M3500 list: windows longer than 540 edges go through the one-warp-per-check kernels with
+    the window state streamed from global memory (step tiles, cp.async ring, second buffer for trial states). A seeded sample of those
+    checks against the live oracle: verdicts identical, chi2 within 1e-4; the CTA-per-check table must give the same verdicts."""
+    g, cfg = synth.make_config("m3500")
+    mem, cnd = api.pair_checks(g)
+    L = sharding.window_lengths(g, mem, cnd)
+    pool = np.nonzero(L > 540)[0]
+    sel = np.sort(np.random.default_rng(11).choice(pool, 1500, replace=False))
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    acc, info = ipc.check_batch(mem[sel], cnd[sel])
+    assert info["window_len"].min() > 540 and info["window_len"].max() > 3000
+    ptr, idx = api.checks_to_csr(mem[sel], cnd[sel])
+    oacc, orep = oracle_lib.OracleIPC(g, cfg, noise_exit=True).check_batch(ptr, idx, n_threads=os.cpu_count())
+    assert np.array_equal(acc, oacc)
+    assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
+    ipc.set_option("cta_per_check", 1)
+    acc2, info2 = ipc.check_batch(mem[sel], cnd[sel])
+    assert np.array_equal(acc2, acc) and rel_err(info2["max_chi2"], info["max_chi2"]).max() < 1e-6
+    ipc.close()
+
+
 def test_sphere2500_full_size_sample_matches_oracle(gpu_lib, oracle_lib):
     """BASELINE.json configs[2]: Sphere2500 SE(3) + 2000 outliers at full size, seeded sample of 5000 of the matrix checks."""
     g, cfg = synth.make_config("sphere")
