@@ -352,8 +352,76 @@ inline SimResult simulate(const Config& cfg, const Problem& p, int device, bool 
     return r;
 }
 
+
+// --matrix [--gpus N]: the batch path instead of the sequential stream — the N_c x N_c pairwise consistency matrix (fast checks on the
+// diagonal, overlapping pairs off it, time order of src/simulation.cpp:26) and the greedy consensus growth over it. With N > 1 one handle
+// per GPU runs on its own host thread; the solved checks are dealt over the GPUs and ONE NCCL all-gather of the packed verdict words (behind
+// the C ABI: ipc_comm_init / ipc_consistency_matrix_sharded) gives every rank the same rows. Labels and precision / recall as in
+// simulating_incremental_data (:24-25, :80-81); writes <output minus 3 chars>PR like the stream does.
+struct MatrixResult { int tp = 0, fp = 0, tn = 0, fn = 0; float precision = 0, recall = 0; double total_s = 0; long long solved = 0; int n_candidates = 0; int gpus = 1;
+                      std::vector<int> accepted; };
+inline MatrixResult consistency_matrix_run(const Config& cfg, const Problem& p, int gpus, int first_device, bool quiet) {
+    const int n = (int)p.loops.size(), w = p.dim == 2 ? 3 : 7, dd = p.dim == 2 ? 9 : 36, words = (n + 31) / 32;
+    std::vector<int> from(n), to(n);
+    std::vector<double> meas((size_t)n * w), info((size_t)n * dd);
+    for (int k = 0; k < n; ++k) {
+        const EdgeRec& e = p.loops[k];
+        from[k] = e.from; to[k] = e.to;
+        std::copy(e.meas.begin(), e.meas.end(), meas.begin() + (size_t)k * w);
+        std::copy(e.info.begin(), e.info.end(), info.begin() + (size_t)k * dd);
+    }
+    ipc_config c{cfg.s_factor, cfg.fast_reject_th, cfg.slow_reject_th, cfg.fast_reject_iter_base, cfg.slow_reject_iter_base};
+    unsigned char id[IPC_COMM_ID_BYTES] = {0};
+    if (gpus > 1) check(ipc_comm_unique_id(id));
+    std::vector<std::vector<uint32_t>> rows(gpus);
+    std::vector<std::vector<int>> order(gpus, std::vector<int>(n));
+    std::vector<std::vector<unsigned char>> in_set(gpus, std::vector<unsigned char>(n, 0));
+    std::vector<long long> solved(gpus, 0);
+    std::vector<std::string> err(gpus);
+    std::vector<double> secs(gpus, 0.0);
+    auto work = [&](int r) {
+        ipc_handle* h = nullptr;
+        auto ok = [&](int rc) { if (rc != IPC_OK) { err[r] = ipc_last_error(); return false; } return true; };
+        do {
+            if (!ok(ipc_create(p.dim, p.n_poses, p.odom_meas.data(), p.odom_info.data(), &c, first_device + r, &h))) break;
+            if (!ok(ipc_set_candidates(h, n, from.data(), to.data(), meas.data(), info.data()))) break;
+            if (gpus > 1 && !ok(ipc_comm_init(h, id, r, gpus))) break;
+            rows[r].assign((size_t)n * words, 0u);
+            int64_t ns = 0;
+            auto t0 = std::chrono::steady_clock::now();
+            if (!ok(gpus > 1 ? ipc_consistency_matrix_sharded(h, rows[r].data(), order[r].data(), &ns)
+                             : ipc_consistency_matrix(h, rows[r].data(), order[r].data(), &ns))) break;
+            if (!ok(ipc_greedy_consensus(h, rows[r].data(), n, in_set[r].data()))) break;
+            secs[r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            solved[r] = ns;
+        } while (false);
+        if (h) ipc_destroy(h);
+    };
+    std::vector<std::thread> th;
+    for (int r = 1; r < gpus; ++r) th.emplace_back(work, r);
+    work(0);
+    for (auto& t : th) t.join();
+    for (int r = 0; r < gpus; ++r) if (!err[r].empty()) throw std::runtime_error("ipc_b200 (GPU " + std::to_string(first_device + r) + "): " + err[r]);
+    for (int r = 1; r < gpus; ++r)
+        if (rows[r] != rows[0] || in_set[r] != in_set[0]) throw std::runtime_error("ranks disagree on the gathered consistency matrix");
+    MatrixResult m; m.n_candidates = n; m.gpus = gpus; m.solved = solved[0]; m.accepted.assign(n, 0);
+    for (int r = 0; r < gpus; ++r) m.total_s = std::max(m.total_s, secs[r]);
+    for (int k = 0; k < n; ++k) {                      // row k of the matrix is candidate order[k] of the file
+        const int li = order[0][k]; const bool acc = in_set[0][k] != 0, truth = li < cfg.canonic_inliers;
+        m.accepted[li] = acc;
+        if (acc && truth) ++m.tp; else if (acc && !truth) ++m.fp; else if (!acc && truth) ++m.fn; else ++m.tn;
+    }
+    m.precision = (m.tp + m.fp) > 0 ? (float)m.tp / (float)(m.tp + m.fp) : 0.f;
+    m.recall = (m.tp + m.fn) > 0 ? (float)m.tp / (float)(m.tp + m.fn) : 0.f;
+    const std::string pr = cfg.output.substr(0, cfg.output.size() >= 3 ? cfg.output.size() - 3 : 0) + "PR";
+    std::ofstream f(pr);
+    f << m.precision << " " << m.recall << "\n" << m.total_s << " " << (m.solved ? m.total_s / (double)m.solved : 0.0) << "\n";
+    (void)quiet;
+    return m;
+}
+
 inline int tester_main(int argc, char** argv, int dim) {
-    std::string cfg_path; int device = 0; bool parse_only = false, quiet = false, final_pgo = true, one_by_one = false;
+    std::string cfg_path; int device = 0, gpus = 1; bool parse_only = false, quiet = false, final_pgo = true, one_by_one = false, matrix = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "-c" && i + 1 < argc) cfg_path = argv[++i];
@@ -362,7 +430,9 @@ inline int tester_main(int argc, char** argv, int dim) {
         else if (a == "--no-final-pgo") final_pgo = false;
         else if (a == "--quiet") quiet = true;
         else if (a == "--one-by-one") one_by_one = true;
-        else { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [--device N] [--parse-only] [--no-final-pgo] [--quiet] [--one-by-one]\n"; return 2; }
+        else if (a == "--matrix") matrix = true;
+        else if (a == "--gpus" && i + 1 < argc) gpus = std::stoi(argv[++i]);
+        else { std::cerr << "usage: " << argv[0] << " -c <config.yaml> [--device N] [--parse-only] [--no-final-pgo] [--quiet] [--one-by-one] [--matrix [--gpus N]]\n"; return 2; }
     }
     if (cfg_path.empty()) { std::cerr << "usage: " << argv[0] << " -c <config.yaml>\n"; return 2; }
     try {
@@ -374,6 +444,17 @@ inline int tester_main(int argc, char** argv, int dim) {
         if (parse_only) {
             std::cout << "s_factor " << cfg.s_factor << " fast " << cfg.fast_reject_th << "/" << cfg.fast_reject_iter_base << " slow " << cfg.slow_reject_th << "/"
                       << cfg.slow_reject_iter_base << "\n";
+            return 0;
+        }
+        if (matrix) {
+            if (gpus < 1 || device + gpus > ipc_device_count()) throw std::runtime_error("--gpus " + std::to_string(gpus) + " from device " + std::to_string(device) + ": only " +
+                                                                                        std::to_string(ipc_device_count()) + " CUDA device(s)");
+            (void)readSolutionFile(cfg.ground_truth, p.dim);
+            MatrixResult m = consistency_matrix_run(cfg, p, gpus, device, quiet);
+            std::cout << "Consistency matrix: " << m.n_candidates << " candidates, " << m.solved << " solved checks on " << m.gpus << " GPU(s) in " << m.total_s << " s ("
+                      << (m.total_s > 0 ? (double)m.solved / m.total_s : 0.0) << " checks/s incl. transfers)\n";
+            std::cout << "TP " << m.tp << " FP " << m.fp << " TN " << m.tn << " FN " << m.fn << "\n";
+            std::cout << "Precision = " << m.precision << "  Recall = " << m.recall << "\n";
             return 0;
         }
         SimResult r = simulate(cfg, p, device, final_pgo, quiet, one_by_one);

@@ -72,3 +72,50 @@ def test_two_gpu_sharded_batch_and_matrix(gpu_lib):
         assert info[0] == r and info[1] == world and info[2] == 2      # exactly one all-gather per batch / matrix
         assert np.array_equal(sharding.decode_gathered(words, parts, len(cnd)), want)
         assert solved == solved_want and np.array_equal(order, order_want) and np.array_equal(rows, rows_want)
+
+
+def _cli_case(tmp_path, name, scale):
+    import os
+    from ipc_b200 import g2o
+    g, cfg = synth.make_config(name, scale=scale)
+    ds, gt, out, yml = (str(tmp_path / f) for f in ("graph.g2o", "gt.txt", "res.txt", "cfg.yaml"))
+    g2o.write_g2o(g, ds)
+    g2o.write_trajectory(g.gt, gt)
+    g2o.write_config(yml, name, ds, gt, out, g.n_true, cfg)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return g, cfg, yml, out, os.path.join(root, "cli")
+
+
+def _matrix_cli(exe, yml, *extra):
+    import re
+    import subprocess
+    r = subprocess.run([exe, "-c", yml, "--matrix", *extra], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"TP (\d+) FP (\d+) TN (\d+) FN (\d+)", r.stdout)
+    s = re.search(r"(\d+) candidates, (\d+) solved checks on (\d+) GPU", r.stdout)
+    return tuple(int(x) for x in m.groups()), tuple(int(x) for x in s.groups())
+
+
+@pytest.mark.parametrize("name,scale,tester", [("intel", 0.3, "ipc_tester_2D"), ("sphere", 0.05, "ipc_tester_3D")])
+def test_cli_matrix_mode_equals_api(gpu_lib, tmp_path, name, scale, tester):
+    """`ipc_tester_* --matrix` (C++ host over the C ABI): consistency matrix + greedy consensus, same confusion counts as the Python mirror;
+    with two or more GPUs `--gpus N` (one handle per device on host threads, NCCL all-gather behind the C ABI) gives the same answer."""
+    import os
+    import subprocess
+    g, cfg, yml, out, cli = _cli_case(tmp_path, name, scale)
+    subprocess.check_call(["make", "-s", "-C", cli])
+    ipc = gpu_lib.IPC.from_graph(g, cfg)
+    rows, order, solved = ipc.consistency_matrix()
+    sel = ipc.greedy_consensus(rows)
+    ipc.close()
+    acc = np.zeros(g.n_loops, bool); acc[order[sel]] = True
+    truth = np.arange(g.n_loops) < g.n_true
+    want = (int((acc & truth).sum()), int((acc & ~truth).sum()), int((~acc & ~truth).sum()), int((~acc & truth).sum()))
+    got, (n_c, n_solved, n_gpu) = _matrix_cli(os.path.join(cli, tester), yml)
+    assert got == want and n_c == g.n_loops and n_solved == solved and n_gpu == 1
+    pr = open(out[:-3] + "PR").read().split()
+    assert abs(float(pr[0]) - want[0] / max(want[0] + want[1], 1)) < 1e-5
+    world = min(gpu_lib.lib().ipc_device_count(), 4)
+    if world >= 2:
+        got_n, (_, n_solved_n, n_gpu_n) = _matrix_cli(os.path.join(cli, tester), yml, "--gpus", str(world))
+        assert got_n == want and n_solved_n == solved and n_gpu_n == world
