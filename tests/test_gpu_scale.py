@@ -112,7 +112,8 @@ def test_m3500_full_size_streamed_windows_match_oracle(gpu_lib, oracle_lib):
     assert rel_err(info["max_chi2"], orep["max_chi2"]).max() < CHI2_RTOL
     ipc.set_option("cta_per_check", 1)
     acc2, info2 = ipc.check_batch(mem[sel], cnd[sel])
-    assert np.array_equal(acc2, acc) and rel_err(info2["max_chi2"], info["max_chi2"]).max() < 1e-6
+    # the two decompositions (32 vs 128 - 256 threads per check) sum in different orders and may stop at different noise-level retries
+    assert np.array_equal(acc2, acc) and rel_err(info2["max_chi2"], info["max_chi2"]).max() < 0.1 * CHI2_RTOL
     ipc.close()
 
 
