@@ -158,3 +158,16 @@ def test_threaded_loader_keeps_file_order(clis, tmp_path):
     keep = g.loop_from < g.loop_to
     assert np.array_equal(r.loop_meas[keep], g.loop_meas[keep])
     assert "FIX 0" in open(fixed).read()
+
+
+def test_cli_matrix_mode_needs_a_gpu_and_says_so(clis, tmp_path):
+    """No CPU fallback: on a box without a CUDA device the batch path of the tester fails loudly (exit code 1, the library's message)."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "ipc_b200", "libipc_b200.so"))
+    if lib.ipc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    _, _, yml = _write_case(tmp_path, "intel", 0.1)
+    out = subprocess.run([clis[0], "-c", yml, "--matrix"], capture_output=True, text=True)
+    assert out.returncode == 1 and "CUDA device" in out.stderr
+    out = subprocess.run([clis[0], "-c", yml, "--matrix", "--gpus", "2"], capture_output=True, text=True)
+    assert out.returncode == 1 and "CUDA device" in out.stderr
