@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
-from ipc_b200 import g2o, synth  # noqa: E402
+from ipc_b200 import g2o, spoil, synth  # noqa: E402
 
 OVERRIDES_2D = dict(s_factor=10.0, k_buddies=2, use_best_k_buddies=False, use_recovery=True, fast_reject_th=10.64, slow_reject_th=10.64)
 OVERRIDES_3D = dict(s_factor=50.0, use_best_k_buddies=False, use_recovery=True)      # _3D.sh sets neither k_buddies nor the thresholds
@@ -89,6 +89,9 @@ def main(argv=None):
     ap.add_argument("--opt", default="B200_IPC")
     ap.add_argument("--date", default=time.strftime("%d%m%y"))
     ap.add_argument("--mode", choices=["stream", "matrix"], default="stream")
+    ap.add_argument("--spoiler", choices=["file", "numpy"], default="file",
+                    help="file: ipc_b200.spoil — the clean g2o is spoiled on disk exactly like generateDataset.py -n <outliers> --seed <s> "
+                         "(byte-identical output, pinned by tests/golden/spoil); numpy: synth.add_outliers on the in-memory graph")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--tester", help="tester executable (default cli/ipc_tester_2D|3D)")
     ap.add_argument("--tester-args", default="--quiet", help="extra arguments for the tester")
@@ -110,6 +113,9 @@ def main(argv=None):
         gt_path = os.path.abspath(a.gt)
     else:
         g2o.write_trajectory(clean.gt if clean.gt is not None else np.zeros((clean.n_poses, 3 if dim == 2 else 7)), gt_path)
+    clean_path = os.path.abspath(a.g2o) if a.g2o else os.path.join(root, "clean.g2o")
+    if not a.g2o:
+        g2o.write_g2o(clean, clean_path)
     levels = [int(x) for x in a.outliers.split(",") if x]
     summary = dict(dataset=name, dim=dim, n_poses=clean.n_poses, true_loops=clean.n_loops, mode=a.mode, runs=a.runs, levels={})
     t_all = time.perf_counter()
@@ -120,9 +126,14 @@ def main(argv=None):
         jobs, results = [], []
         for run in range(a.runs):
             tag = f"{run:02d}"
-            g = synth.add_outliers(clean, out, seed=100000 + 1000 * out + run)
             ds = os.path.join(spoiled_dir, tag + ".g2o")
-            g2o.write_g2o(g, ds)
+            seed = 100000 + 1000 * out + run
+            if a.spoiler == "file":
+                spoil.spoil_g2o(clean_path, ds, outliers=out, seed=seed)
+                g = g2o.read_g2o(ds, dim, n_true=clean.n_loops) if a.mode == "matrix" else None
+            else:
+                g = synth.add_outliers(clean, out, seed=seed)
+                g2o.write_g2o(g, ds)
             trj = os.path.join(exp_dir, tag + ".TRJ")
             yml = os.path.join(root, f"{a.opt}_{out}_{tag}.yaml")
             cfg = run_yaml(yml, name, ds, gt_path, trj, clean.n_loops, base_cfg, dim)
