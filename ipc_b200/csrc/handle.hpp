@@ -50,7 +50,12 @@ struct ipc_handle {
     uint32_t* d_bits = nullptr;
     ipc_check_info* d_info = nullptr;
     unsigned long long* d_stats = nullptr;
-    double* d_scratch = nullptr; size_t scratch_doubles = 0;   // per-CTA scratch, shared by the (serialised) bucket launches
+    double* d_scratch = nullptr; size_t scratch_doubles = 0;   // per-CTA scratch: one region per launch bucket (the bucket launches of a batch overlap)
+    size_t scratch_off[NB] = {}, scratch_len[NB] = {};         // region of bucket b, in doubles
+    int overlap_buckets = 1;                                   // option: 1 = every bucket on its own stream (fork / join around the batch), 0 = one after the other
+    cudaStream_t bucket_stream[NB] = {};
+    cudaEvent_t bucket_ev[NB] = {};
+    cudaEvent_t fork_ev = nullptr;
     int last_launches = 0;
     cudaStream_t stream = nullptr;
     // ---- sequential stream (stateful agreementCheck): global pose state + cluster-solve work buffers

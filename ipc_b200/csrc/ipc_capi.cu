@@ -89,10 +89,11 @@ const Bucket kBuckets2[NB] = {{96, 32, 0, 16}, {320, 64, 0, 8}, {1300, 128, 0, 3
 // barriers, no idle warps while one lane solves the force system; windows up to 540 edges keep their state in shared memory, longer
 // ones stream it from L2 / HBM in coalesced step tiles through a cp.async ring (TileFeed) and write trial states to a second buffer
 // (no backup, no rollback pass). Measured against the CTA-per-check table on the M3500 sample (profiles/r02_ab_*): 1.73x for
-// 320 < L <= 540, +16 % / +4 % / +33 % for 1300-2000 / 2000-2600 / 2600-3499, +24 % on the whole list. Windows beyond 5400 edges keep
-// 256 threads per check (one check per SM) on the same streamed layout. The three middle rows share one shape: the split only evens
+// 320 < L <= 540, +16 % / +4 % / +33 % for 1300-2000 / 2000-2600 / 2600-3499, +24 % on the whole list; on the City10000-shaped matrix (windows up to 9997 edges)
+// one warp per check up to 10000 edges gives +7.7 % over handing over at 5400 (profiles/r02_ab_log.txt). Windows beyond 10000 edges keep
+// 256 threads per check (one check per SM) on the same streamed layout (50 k-pose config: no difference between the two within noise). The three middle rows share one shape: the split only evens
 // out the tail of the dynamic work claim (longest windows first within a launch).
-const Bucket kBuckets2U[NB] = {{96, 32, 0, 16}, {540, 32, 0, 8}, {1500, 32, 1, 8}, {2600, 32, 1, 8}, {5400, 32, 1, 8}, {1 << 30, 256, 1, 1}};
+const Bucket kBuckets2U[NB] = {{96, 32, 0, 16}, {540, 32, 0, 8}, {1500, 32, 1, 8}, {2600, 32, 1, 8}, {10000, 32, 1, 8}, {1 << 30, 256, 1, 1}};
 
 // MODE 2 (option stage_odom = 1, uniform-information graphs): + 24 B / vertex for the odometry window staged by cp.async.bulk: the
 // same CTAs per SM hold shorter windows (measured A/B in profiles/)
@@ -111,10 +112,12 @@ extern "C" { namespace { int stream_solver_setup(ipc_handle* h); void slot_free(
 
 namespace {
 
-// per-CTA scratch: every bucket launch fits grid * stride into it; also uploads the bucket caps for plan_checks
+// per-CTA scratch: every bucket has its own region (grid * stride doubles), because the bucket launches of one batch run side by
+// side on their own streams; also uploads the bucket caps for plan_checks
 int size_scratch(ipc_handle* h) {
     size_t need = 0;
     const Bucket* kB = h->buckets;
+    for (int b = 0; b < NB; ++b) { h->scratch_off[b] = 0; h->scratch_len[b] = 0; }
     for (int b = 0; b < NB; ++b) {
         int lo_cap = b == 0 ? 0 : kB[b - 1].cap;
         if (lo_cap >= h->n - 1) break;
@@ -123,7 +126,9 @@ int size_scratch(ipc_handle* h) {
         if (kB[b].mode == 0 && sm > 226 * 1024) return fail(IPC_ERR_ARG, "bucket " + std::to_string(b) + " does not fit shared memory");
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
         per_sm = std::min(per_sm, kB[b].minb);
-        need = std::max(need, (size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kB[b].mode, Lcap, h->dim, kB[b].nt));
+        h->scratch_off[b] = need;
+        h->scratch_len[b] = ((size_t)h->n_sm * per_sm * scratch_doubles_per_cta(kB[b].mode, Lcap, h->dim, kB[b].nt) + 31) & ~(size_t)31;   // 256-byte aligned regions
+        need += h->scratch_len[b];
     }
     if (need > h->scratch_doubles) {
         cudaFree(h->d_scratch); h->d_scratch = nullptr; h->scratch_doubles = 0;
@@ -164,10 +169,18 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
     CUDA_TRY(cudaGetLastError());
     int launches = 1;
     CUDA_TRY(cudaEventRecord(h->ev_k0, st));
-    for (int b = 0; b < NB; ++b) {
+    // The buckets are independent (own work list, own counters, own scratch region, disjoint verdict slots): fork them onto one
+    // stream each behind the plan, longest windows first, and join before the pack — the tail of one launch (a few long checks still
+    // running) and an underfilled launch (few checks of one length class) overlap with the other buckets instead of idling SMs.
+    const bool overlap = h->overlap_buckets != 0 && h->fork_ev != nullptr;
+    if (overlap) CUDA_TRY(cudaEventRecord(h->fork_ev, st));
+    int n_b = 0;
+    while (n_b < NB && (n_b == 0 ? 0 : kB[n_b - 1].cap) < h->n - 1) ++n_b;        // buckets some window of this graph can fall into
+    for (int q = 0; q < n_b; ++q) {
+        const int b = overlap ? n_b - 1 - q : q;
         const Bucket& bk = kB[b];
-        int lo_cap = b == 0 ? 0 : kB[b - 1].cap;
-        if (lo_cap >= h->n - 1) break;                 // no window can be this long
+        cudaStream_t bs = overlap ? h->bucket_stream[b] : st;
+        if (overlap) CUDA_TRY(cudaStreamWaitEvent(bs, h->fork_ev, 0));
         BatchArgs a{};
         for (int c = 0; c < 6; ++c) { a.Du[c] = h->hs.Du[c]; a.Vu[c] = h->hs.Vu[c]; }
         const bool uni = h->dim == 2 && h->hs.uniform_iso && h->use_uniform && h->d_odom3;
@@ -177,18 +190,23 @@ int enqueue_batch(ipc_handle* h, int n_checks, const int* member_dev, const int*
         a.fast_th = h->cfg.fast_reject_th; a.slow_th = h->cfg.slow_reject_th;
         a.fast_iter = h->cfg.fast_reject_iter_base; a.slow_iter = h->cfg.slow_reject_iter_base;
         a.noise_eps = h->noise_eps; a.max_tries = h->max_tries; a.speculate = h->speculate; a.early_accept = h->early_accept; a.sd_fuse = h->sd_fuse;
-        a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch;
+        a.verdict = verdict_dev; a.info = info_dev; a.scratch = h->d_scratch + h->scratch_off[b];
         a.scratch_stride = scratch_doubles_per_cta(bk.mode, a.Lcap, h->dim, bk.nt);
         size_t sm = smem_bytes(bk.mode, a.Lcap, h->dim, bk.nt);
         int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32, (227 * 1024) / (sm + 1024)));
         per_sm = std::min(per_sm, bk.minb);
         int grid = std::min(n_checks, h->n_sm * per_sm);
-        grid = (int)std::min<size_t>(grid, h->scratch_doubles / a.scratch_stride);
+        grid = (int)std::min<size_t>(grid, h->scratch_len[b] / a.scratch_stride);
+        if (grid < 1) return fail(IPC_ERR_CUDA, "scratch region of bucket " + std::to_string(b) + " is smaller than one CTA's stride");
         int rc = IPC_OK;
         if (h->dim == 3) {
-            rc = launch_se3_variant(bk.nt, bk.mode, a, grid, st);
-        } else rc = launch_se2_variant(bk.nt, bk.minb, bk.mode, a, grid, st, uni);
+            rc = launch_se3_variant(bk.nt, bk.mode, a, grid, bs);
+        } else rc = launch_se2_variant(bk.nt, bk.minb, bk.mode, a, grid, bs, uni);
         if (rc != IPC_OK) return rc;
+        if (overlap) {
+            CUDA_TRY(cudaEventRecord(h->bucket_ev[b], bs));
+            CUDA_TRY(cudaStreamWaitEvent(st, h->bucket_ev[b], 0));
+        }
         ++launches;
     }
     CUDA_TRY(cudaEventRecord(h->ev_k1, st));
@@ -271,6 +289,11 @@ int ipc_create(int dim, int n_poses, const double* odom_meas, const double* odom
     }
     CUDA_TRY(cudaEventCreate(&h->ev_k0));
     CUDA_TRY(cudaEventCreate(&h->ev_k1));
+    for (int b = 0; b < NB; ++b) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->bucket_stream[b], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->bucket_ev[b], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming));
     guard.h = nullptr;
     *out = h;
     return IPC_OK;
@@ -291,6 +314,8 @@ void ipc_destroy(ipc_handle* h) {
     if (h->cl_hout) cudaFreeHost(h->cl_hout);
     if (h->cl_hargs) cudaFreeHost(h->cl_hargs);
     if (h->stream) cudaStreamDestroy(h->stream);
+    for (int b = 0; b < NB; ++b) { if (h->bucket_stream[b]) cudaStreamDestroy(h->bucket_stream[b]); if (h->bucket_ev[b]) cudaEventDestroy(h->bucket_ev[b]); }
+    if (h->fork_ev) cudaEventDestroy(h->fork_ev);
     if (h->ev_k0) cudaEventDestroy(h->ev_k0);
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     delete h;
@@ -332,6 +357,7 @@ int ipc_set_option(ipc_handle* h, const char* name, double value) {
         CUDA_TRY(cudaSetDevice(h->device));
         return size_scratch(h);
     }
+    if (!strcmp(name, "overlap_buckets")) { h->overlap_buckets = value != 0; return IPC_OK; }   // 0: the bucket launches of a batch one after the other on the caller's stream
     if (!strcmp(name, "speculate")) { h->speculate = value != 0; return IPC_OK; }
     if (!strcmp(name, "early_accept")) { h->early_accept = value != 0; return IPC_OK; }
     if (!strcmp(name, "max_tries")) { h->max_tries = (int)value; return IPC_OK; }

@@ -72,8 +72,9 @@ def test_m3500_stream_prefix_matches_oracle_fixture(gpu_lib):
 
 @pytest.mark.parametrize("name,n_checks", [("synth50k", 160), ("city10k", 120)])
 def test_long_windows_match_oracle(gpu_lib, oracle_lib, name, n_checks):
-    """Windows longer than the shared-memory state holds (L > 5400 edges) at real size: the streamed-state kernel (MODE 1, 256 threads
-    per check). Verdicts must be identical. chi2: 1e-4 on all but a handful of checks — on chains of 27 000 - 47 000 edges a few checks
+    """Windows longer than the shared-memory state holds (L > 5400 edges) at real size: the streamed-state kernels (MODE 1) — one warp
+    per check up to 10 000 edges (every City10000 window), 256 threads per check beyond (the 50 k config), and the 256-thread kernel on
+    the City10000 windows too (hand-over moved back to 5400 by option). Verdicts must be identical. chi2: 1e-4 on all but a handful of checks — on chains of 27 000 - 47 000 edges a few checks
     either hit the iteration cap (500) before converging or stop at different noise-level retries, and the state after a fixed number of
     Dogleg iterations depends on the summation order (measured: 2 of 160 checks at 1.9e-4 / 2.7e-4, scripts/diag_long.py); those stay
     within 1e-3."""
@@ -91,6 +92,16 @@ def test_long_windows_match_oracle(gpu_lib, oracle_lib, name, n_checks):
     assert np.array_equal(acc, oacc)
     rel = rel_err(info["max_chi2"], orep["max_chi2"])
     assert rel.max() < 10 * CHI2_RTOL and (rel > CHI2_RTOL).mean() <= 0.03
+    if name == "city10k":
+        ipc.set_option("bucket4_cap", 5400)                      # the same windows through the 256-thread kernel
+        acc2, info2 = ipc.check_batch(mem[sel], cnd[sel])
+        assert np.array_equal(acc2, oacc)
+        rel2 = rel_err(info2["max_chi2"], orep["max_chi2"])
+        assert rel2.max() < 10 * CHI2_RTOL and (rel2 > CHI2_RTOL).mean() <= 0.03
+        ipc.set_option("bucket4_cap", 10000)
+        ipc.set_option("overlap_buckets", 0)                     # bucket launches one after the other: same results bit for bit
+        acc3, info3 = ipc.check_batch(mem[sel], cnd[sel])
+        assert np.array_equal(acc3, acc) and np.array_equal(info3["max_chi2"], info["max_chi2"])
     ipc.close()
 
 
