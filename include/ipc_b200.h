@@ -174,7 +174,9 @@ int ipc_greedy_consensus(ipc_handle* h, const uint32_t* rows_bits, int n, unsign
  * max_tries, sd_fuse (0 / 1 / 2: when the steepest-descent pass replaces the norm pass; results identical),
  * bucket<i>_cap / bucket<i>_nt / bucket<i>_minb / bucket<i>_mode (launch shapes, i = 0..5; mode 0 = window state in shared memory,
  * 1 = streamed from global memory, 2 = + staged odometry): tuning, see DESIGN.md 3. cta_per_check: 1 selects the CTA-per-check launch
- * table (state in shared memory) on a uniform-information SE(2) graph instead of the default one-warp-per-check table. stage_odom. */
+ * table (state in shared memory) on a uniform-information SE(2) graph instead of the default one-warp-per-check table. stage_odom.
+ * overlap_buckets: 1 (default) runs the bucket launches of a batch side by side on internal streams (forked behind the caller's
+ * stream, joined before the call's last kernel: stream order as seen by the caller is unchanged), 0 one after the other. */
 int ipc_set_option(ipc_handle* h, const char* name, double value);
 
 #ifdef __cplusplus
