@@ -378,18 +378,33 @@ def run_ours(args):
                "clocks": clk.summary(), "wall_s_timed_region": t_wall}
         if full is not None:
             out["g2o_full_retries"] = full
+        # The legs below run on rank 0 only, after the last collective, and report BESIDE the headline: a failure in one of them is
+        # written into the line (`side_leg_errors`) instead of taking the measured headline down with it.
+        side_errors = {}
+
+        def side(name, fn):
+            try:
+                fn()
+            except Exception as e:      # noqa: BLE001 — reported, not swallowed
+                side_errors[name] = f"{type(e).__name__}: {e}"
+                print(f"bench.py: side leg '{name}' failed: {e}", file=sys.stderr)
+
         if not args.no_cpu:
             cores = os.cpu_count() or 1
             ne = args.noise_exit != 0
-            v, ns, dt, sel, oacc = cpu_leg(g, cfg, mem, cnd, args.cpu_seconds, cores, noise_exit=ne)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                   "sample": f"seeded random sample of {ns} checks of the same list, {dt:.1f} s, one check per thread, same termination rule as the GPU arm",
-                                   "verdict_mismatches_vs_gpu": int((verdict_all[sel] != oacc).sum())}
-            if full is not None:
+
+            def leg_cpu():
+                v, ns, dt, sel, oacc = cpu_leg(g, cfg, mem, cnd, args.cpu_seconds, cores, noise_exit=ne)
+                out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                       "sample": f"seeded random sample of {ns} checks of the same list, {dt:.1f} s, one check per thread, same termination rule as the GPU arm",
+                                       "verdict_mismatches_vs_gpu": int((verdict_all[sel] != oacc).sum())}
+
+            def leg_cpu_full():
                 v0, ns0, dt0, sel0, oacc0 = cpu_leg(g, cfg, mem, cnd, max(3.0, args.cpu_seconds / 3), cores, noise_exit=False)
                 full.update({"cpu_value": v0, "cpu_sample": f"{ns0} checks, {dt0:.1f} s, {cores} threads",
                              "verdict_mismatches_vs_gpu": int((verdict_all[sel0] != oacc0).sum())})
-            if args.stream_seconds > 0:
+
+            def leg_stream():
                 sv, sn, sdt = stream_leg(g, cfg, args.stream_seconds)
                 out["stream_cpu_B1"] = {"value": sv, "unit": "agreementCheck calls/s", "cores": 1, "kind": "port",
                                         "sample": f"first {sn} time-ordered candidates of the sequential stream, {sdt:.1f} s (BASELINE.md row B1)"}
@@ -400,6 +415,14 @@ def run_ours(args):
                                      "gpu_value_same_prefix": gs["prefix"][0], "cpu_B1_value": sv, "prefix_candidates": sn,
                                      "gpu_value_full_stream": gs["full"][0], "full_stream_candidates": gs["full"][1], "full_stream_s": gs["full"][2],
                                      "accepted_full_stream": gs["full"][3]}
+
+            side("cpu_baseline", leg_cpu)
+            if full is not None:
+                side("g2o_full_retries.cpu", leg_cpu_full)
+            if args.stream_seconds > 0:
+                side("stream", leg_stream)
+        if side_errors:
+            out["side_leg_errors"] = side_errors
         sys.stdout.flush()
         os.dup2(_saved_fd1, 1)
         print(json.dumps(out), flush=True)
