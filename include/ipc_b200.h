@@ -117,9 +117,9 @@ int ipc_check_batch(ipc_handle* h, int n_checks, const int* member, const int* c
                     uint32_t* out_bits, ipc_check_info* out_info);
 /* Device-resident variant: all pointers are device pointers; kernels are enqueued on `stream`
  * (a cudaStream_t, may be NULL) and the call does not synchronise. ONE batch may be in flight per handle: the
- * work lists, verdict bytes and per-CTA scratch belong to the handle, so the caller must not enqueue a second
- * batch (on any stream) before the previous one has finished, and member/cand must index the candidate table
- * (not checked here — the host-buffer entry point validates). */
+ * work lists, verdict bytes and per-CTA scratch belong to the handle, so batches of one handle must be ordered — enqueue them on
+ * the same stream (stream order serialises them; bench.py does that) or wait for the previous one before using another stream —
+ * and member/cand must index the candidate table (not checked here — the host-buffer entry point validates). */
 int ipc_check_batch_dev(ipc_handle* h, int n_checks, const int* member_dev, const int* cand_dev,
                         uint32_t* out_bits_dev, ipc_check_info* out_info_dev, void* stream);
 /* Plan for ipc_check_batch_dev: the call sorts checks by window length into launch buckets on the
