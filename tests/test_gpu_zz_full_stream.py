@@ -30,3 +30,16 @@ def test_m3500_full_stream_inlier_set_matches_oracle_fixture(gpu_lib):
     rel = rel_err(info["max_chi2"], z["max_chi2"])
     assert np.median(rel) < 1e-6 and (rel > 1e-4).mean() <= 0.01              # the decision quantity, candidate by candidate
     ipc.close()
+
+
+def test_cpp_class_runs_on_the_device(gpu_lib, tmp_path):
+    """include/ipc_b200.hpp end to end on the GPU: the check program of tests/test_cpp_wrapper.py constructs an IPC2D on a small chain,
+    calls agreementCheck and reads the consensus set back; any C-ABI error would surface as ipc_b200::Error -> WRAPPER_FAIL."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "wrapper_check")
+    lib_dir = os.path.join(root, "ipc_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "wrapper_check.cpp"),
+                           "-L" + lib_dir, "-lipc_b200", "-Wl,-rpath," + lib_dir, "-o", exe])
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0 and "WRAPPER_OK" in p.stdout and "device run: agreementCheck" in p.stdout, p.stdout + p.stderr
